@@ -1,0 +1,169 @@
+/*
+ * lattice_ajtai.h -- C ABI of the B200-native Ajtai commitment engine for Latticeum's LatticeFold prover.
+ *
+ * This is the drop-in boundary for ONE path of Nesquiko/Latticeum: the per-fold-step Ajtai commitment
+ * pipeline (iCRT -> balanced gadget decomposition -> CRT -> kappa x n matrix-vector product in CRT form)
+ * over the Goldilocks ring Z_q[X]/(X^24 - X^12 + 1), q = 2^64 - 2^32 + 1.  The reference has no FFI of its
+ * own (it is pure Rust); each entry point below names the Rust function it replaces.  A `crates/zkvm-cuda`
+ * FFI crate binds exactly these symbols.  Paths are relative to
+ * /root/reference/latticeum/ :
+ *     LF     = crates/latticefold/src
+ *     RING   = crates/stark-rings/crates/ring/src
+ *     LINALG = crates/stark-rings/crates/linear_algebra/src
+ *     GOLD   = RING/cyclotomic_ring/models/goldilocks
+ *     ZKVM   = crates/zkvm/src
+ *
+ * Data layout at the boundary (RING/cyclotomic_ring/flatten.rs:10-17, GOLD/utils.rs:5-23):
+ *   - a ring element is 24 contiguous uint64_t, little-endian limbs;
+ *     CRT ("NTT") form: index = slot*3 + component (8 slots x Fq3);  coefficient form: index = degree;
+ *   - vectors of ring elements are contiguous; the matrix is uploaded row by row (the host's
+ *     Matrix<R> is Vec<Vec<R>>, LINALG/matrix.rs:17-21);
+ *   - `repr` fixes what a limb means for EVERY buffer crossing this ABI through that handle:
+ *       LAT_REPR_CANONICAL  : the integer x in [0, q);
+ *       LAT_REPR_MONTGOMERY : x * 2^64 mod q, the in-memory form of ark-ff's Fp64<MontBackend>
+ *                             (GOLD/mod.rs:20-24) -- what a Rust caller passes without conversion.
+ *
+ * Pointers are HOST memory unless the function name ends in `_dev` (then they are device pointers on the
+ * handle's GPU and the call is asynchronous on the handle's stream).  A handle is used by one thread at a
+ * time (the reference calls this path from its single main thread, ZKVM/main.rs:121-219).
+ *
+ * Every function returns a lat_status.  There is no CPU fallback: without a usable CUDA device
+ * lat_ajtai_create fails with LAT_E_CUDA.
+ */
+#ifndef LATTICE_AJTAI_H
+#define LATTICE_AJTAI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LAT_RING_DEGREE 24 /* GOLD/ntt.rs:9  */
+#define LAT_RING_SLOTS 8   /* GOLD/ntt.rs:12 */
+#define LAT_ABI_VERSION 1
+
+typedef enum lat_status {
+    LAT_OK = 0,
+    /* CommitmentError::WrongWitnessLength(got, expected)            LF/commitment.rs:15-17 */
+    LAT_E_WRONG_WITNESS_LENGTH = 1,
+    /* CommitmentError::WrongCommitmentLength                        LF/commitment.rs:18-20 */
+    LAT_E_WRONG_COMMITMENT_LENGTH = 2,
+    /* CommitmentError::WrongAjtaiMatrixDimensions                   LF/commitment.rs:21-26 */
+    LAT_E_WRONG_MATRIX_DIMENSIONS = 3,
+    /* A coefficient needs more digits than the padding: the reference panics (index out of bounds at
+     * RING/balanced_decomposition/mod.rs:80,85,87); this engine reports it and never truncates.        */
+    LAT_E_DIGIT_OVERFLOW = 4,
+    LAT_E_INVALID_ARGUMENT = 5,
+    LAT_E_CUDA = 6,            /* CUDA runtime failure or no device; see lat_last_error()              */
+    LAT_E_MATRIX_INCOMPLETE = 7 /* a commit was requested before all kappa rows were uploaded           */
+} lat_status;
+
+typedef enum lat_repr { LAT_REPR_CANONICAL = 0, LAT_REPR_MONTGOMERY = 1 } lat_repr;
+
+/* Opaque engine: owns the device-resident Ajtai matrix, work buffers and a stream on one GPU.
+ * Replaces AjtaiCommitmentScheme<GoldilocksRingNTT> (LF/commitment/commitment_scheme.rs:38-58). */
+typedef struct lat_ajtai lat_ajtai;
+
+const char *lat_strerror(int status);
+/* Message of the last failure on the calling thread (CUDA error string etc.); never NULL. */
+const char *lat_last_error(void);
+int lat_abi_version(void);
+
+/* ---- construction: AjtaiCommitmentScheme::new / ::rand   LF/commitment/commitment_scheme.rs:43-58 ---------
+ * kappa x n matrix over the d = 24 Goldilocks ring.  (log2_B, L) are DecompositionParams::B, ::L and K is
+ * ::K with B_SMALL fixed to 2 (LF/decomposition_parameters.rs:11-20; zkVM: 15, 5, 15, ZKVM/ccs.rs:26-34).
+ * Requires 1 <= log2_B <= 15, 1 <= L <= 8, 1 <= K <= 15 (digits are held as int16 on the device).
+ * `device` is the CUDA ordinal.  The matrix starts empty: upload all rows before committing.             */
+int lat_ajtai_create(lat_ajtai **out, uint32_t kappa, uint64_t n, uint32_t log2_B, uint32_t L, uint32_t K,
+                     int repr, int device);
+void lat_ajtai_destroy(lat_ajtai *h);
+
+/* Upload rows [row0, row0 + nrows) of the matrix.  Row r starts at rows + r * row_stride * 24 and holds n
+ * ring elements in CRT form (row_stride >= n, in ring elements; pass n for a dense block, or the full
+ * width when uploading a column shard of a wider host matrix).  The engine re-lays the matrix out for
+ * streaming and, for LAT_REPR_MONTGOMERY, converts it to canonical form once here.                       */
+int lat_ajtai_upload_rows(lat_ajtai *h, uint32_t row0, uint32_t nrows, const uint64_t *rows, uint64_t row_stride);
+int lat_ajtai_upload_rows_dev(lat_ajtai *h, uint32_t row0, uint32_t nrows, const uint64_t *rows_dev,
+                              uint64_t row_stride);
+
+/* AjtaiCommitmentScheme::kappa / ::width                    LF/commitment/commitment_scheme.rs:85-94 */
+uint32_t lat_ajtai_kappa(const lat_ajtai *h);
+uint64_t lat_ajtai_width(const lat_ajtai *h);
+
+/* Use an existing CUDA stream (cudaStream_t) for all work of this handle, e.g. the caller's current
+ * stream so that its own events bracket the kernels.  NULL restores the handle's own stream.            */
+int lat_ajtai_set_stream(lat_ajtai *h, void *cuda_stream);
+/* Block until all work queued on the handle's stream has finished; returns the sticky asynchronous status
+ * (LAT_E_DIGIT_OVERFLOW raised by a *_dev call, or LAT_OK) and clears it.                                 */
+int lat_ajtai_synchronize(lat_ajtai *h);
+
+/* ---- commitments ------------------------------------------------------------------------------------------
+ * commit / commit_ntt: cm = A * f.        LF/commitment/commitment_scheme.rs:63-80,101-103 -> LINALG/matrix.rs:168-178
+ * f: f_len ring elements in CRT form; f_len != n -> LAT_E_WRONG_WITNESS_LENGTH.  cm: kappa ring elements.  */
+int lat_ajtai_commit_ntt(lat_ajtai *h, const uint64_t *f, uint64_t f_len, uint64_t *cm);
+int lat_ajtai_commit_ntt_dev(lat_ajtai *h, const uint64_t *f_dev, uint64_t f_len, uint64_t *cm_dev);
+/* Batched: `count` witnesses of n elements each, contiguous; cms: count x kappa x 24.  One launch streams the
+ * matrix once for the whole batch (the reference loops, LF/nifs/decomposition.rs:185-187).                  */
+int lat_ajtai_commit_ntt_batch(lat_ajtai *h, const uint64_t *fs, uint32_t count, uint64_t f_len, uint64_t *cms);
+int lat_ajtai_commit_ntt_batch_dev(lat_ajtai *h, const uint64_t *fs_dev, uint32_t count, uint64_t f_len,
+                                   uint64_t *cms_dev);
+/* commit_coeff: CRT every element, then commit.              LF/commitment/commitment_scheme.rs:107-112 */
+int lat_ajtai_commit_coeff(lat_ajtai *h, const uint64_t *f_coeff, uint64_t f_len, uint64_t *cm);
+/* decompose_and_commit_coeff: base-B, L-limb balanced decomposition (element-major, limb-minor), CRT,
+ * commit.  w_coeff: w_len elements, w_len * L must equal n.  LF/commitment/commitment_scheme.rs:116-127   */
+int lat_ajtai_decompose_and_commit_coeff(lat_ajtai *h, const uint64_t *w_coeff, uint64_t w_len, uint64_t *cm);
+/* decompose_and_commit_ntt: iCRT first.                      LF/commitment/commitment_scheme.rs:132-139 */
+int lat_ajtai_decompose_and_commit_ntt(lat_ajtai *h, const uint64_t *w, uint64_t w_len, uint64_t *cm);
+
+/* ---- Witness::from_w_ccs (+ Witness::commit)                LF/arith.rs:230-248, 357-362; ZKVM/main.rs:348-367
+ * w_ccs: w_len elements in CRT form, w_len * L == n.  Computes w_coeff = iCRT(w_ccs),
+ * f_coeff = gadget_decompose(w_coeff, B, L) (out[i*L + l] = limb l of element i,
+ * RING/balanced_decomposition/mod.rs:163-175), f = CRT(f_coeff) and cm = A * f in one pass on the device.
+ * Any of f_coeff (n x 24), f (n x 24), cm (kappa x 24) may be NULL to skip that output (and its copy).
+ * The decomposed witness stays resident on the device as the handle's "current witness" for
+ * lat_ajtai_decompose_commit_resident.                                                                    */
+int lat_ajtai_witness_from_w_ccs(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_len, uint64_t *f_coeff,
+                                 uint64_t *f, uint64_t *cm);
+int lat_ajtai_witness_from_w_ccs_dev(lat_ajtai *h, const uint64_t *w_ccs_dev, uint64_t w_len,
+                                     uint64_t *f_coeff_dev, uint64_t *f_dev, uint64_t *cm_dev);
+
+/* ---- LFDecompositionProver::{decompose_witness, commit_witnesses}   LF/nifs/decomposition.rs:162-201
+ * f_coeff: n elements in coefficient form whose signed representatives satisfy |c| < 2^K, else
+ * LAT_E_DIGIT_OVERFLOW (the reference panics).  Plane k, element j = digit k (base 2, so sign * bit_k(|c|))
+ * of f_coeff[j] (LF/nifs/decomposition/utils.rs:45-49).  cm: the commitment of the undecomposed witness
+ * (cm_i.cm), kappa x 24.  Outputs, each may be NULL:
+ *   planes_coeff : K x n x 24, coefficient form (Witness::f_coeff of each wit_s[k]);
+ *   planes_f     : K x n x 24, CRT form        (Witness::f of each wit_s[k], LF/arith.rs:327);
+ *   cms          : K x kappa x 24; cms[k] = A * planes_f[k] for k >= 1 and
+ *                  cms[0] = cm - fold_rev((acc + cms[k]) * 2) by homomorphism (decomposition.rs:189-197).
+ * All K - 1 matrix commits run in one batched launch that streams the matrix once.                         */
+int lat_ajtai_decompose_commit(lat_ajtai *h, const uint64_t *f_coeff, uint64_t n, const uint64_t *cm,
+                               uint64_t *planes_coeff, uint64_t *planes_f, uint64_t *cms);
+int lat_ajtai_decompose_commit_dev(lat_ajtai *h, const uint64_t *f_coeff_dev, uint64_t n, const uint64_t *cm_dev,
+                                   uint64_t *planes_coeff_dev, uint64_t *planes_f_dev, uint64_t *cms_dev);
+/* Same, on the witness left resident by the last lat_ajtai_witness_from_w_ccs* call (no re-upload).        */
+int lat_ajtai_decompose_commit_resident(lat_ajtai *h, const uint64_t *cm, uint64_t *planes_coeff,
+                                        uint64_t *planes_f, uint64_t *cms);
+
+/* ---- standalone batched ring transforms (no handle; run on `device`, synchronous) ----------------------------
+ * CRT::elementwise_crt / ICRT::elementwise_icrt      RING/cyclotomic_ring/crt.rs:10-49 -> GOLD/ntt.rs:135-319
+ * `count` ring elements; in-place allowed (in == out).  Both maps are linear, so `repr` does not matter.   */
+int lat_ring_crt(const uint64_t *coeff, uint64_t count, uint64_t *ntt, int device);
+int lat_ring_icrt(const uint64_t *ntt, uint64_t count, uint64_t *coeff, int device);
+int lat_ring_crt_dev(const uint64_t *coeff_dev, uint64_t count, uint64_t *ntt_dev, void *cuda_stream);
+int lat_ring_icrt_dev(const uint64_t *ntt_dev, uint64_t count, uint64_t *coeff_dev, void *cuda_stream);
+/* GadgetDecompose for &[R]: out[i*L + l] = limb l (base 2^log2_b) of in[i], coefficient form.
+ * RING/balanced_decomposition/mod.rs:163-175, coeff_form.rs:588-606.  out: count*L x 24.                   */
+int lat_ring_gadget_decompose(const uint64_t *in, uint64_t count, uint32_t log2_b, uint32_t L, uint64_t *out,
+                              int repr, int device);
+
+/* ---- pinned host memory for callers that want the fast copy path (optional) -------------------------------- */
+int lat_host_alloc(void **ptr, size_t bytes);
+void lat_host_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LATTICE_AJTAI_H */

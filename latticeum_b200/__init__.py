@@ -1,0 +1,34 @@
+"""latticeum_b200 -- B200-native Ajtai commitment engine for Latticeum's LatticeFold prover.
+
+Only the one hot path: iCRT -> balanced gadget decomposition -> CRT -> kappa x n Ajtai mat-vec in CRT form over
+the Goldilocks ring Z_q[X]/(X^24 - X^12 + 1).  The product is the C-ABI shared library
+(include/lattice_ajtai.h, built by latticeum_b200.build); this package is its host-side mirror of the
+reference's API.  There is no CPU fallback.
+"""
+from .scheme import (  # noqa: F401
+    AjtaiCommitmentScheme,
+    Commitment,
+    CommitmentError,
+    DecompositionParams,
+    DigitOverflow,
+    EngineError,
+    GoldiLocksDP,
+    KAPPA,
+    LFDecompositionProver,
+    N,
+    W_SIZE,
+    Witness,
+    WrongAjtaiMatrixDimensions,
+    WrongCommitmentLength,
+    WrongWitnessLength,
+    from_mont,
+    get_fhat,
+    ntt_from_scalar,
+    to_mont,
+)
+
+__all__ = [
+    "AjtaiCommitmentScheme", "Commitment", "CommitmentError", "DecompositionParams", "DigitOverflow", "EngineError",
+    "GoldiLocksDP", "KAPPA", "LFDecompositionProver", "N", "W_SIZE", "Witness", "WrongAjtaiMatrixDimensions",
+    "WrongCommitmentLength", "WrongWitnessLength", "from_mont", "get_fhat", "ntt_from_scalar", "to_mont",
+]

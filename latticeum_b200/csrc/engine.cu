@@ -1,0 +1,542 @@
+// C ABI of the engine (include/lattice_ajtai.h): handle, device buffers, stream plumbing.  No torch types, no
+// CPU fallback: every compute entry point ends in a CUDA kernel launch or fails with LAT_E_CUDA.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/lattice_ajtai.h"
+#include "kernels.h"
+
+using lat::u64;
+
+namespace {
+
+thread_local std::string g_last_error = "";
+
+int fail_cuda(cudaError_t e, const char *what, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) at engine.cu:%d: %s", (int)e, cudaGetErrorString(e), line, what);
+    g_last_error = buf;
+    return LAT_E_CUDA;
+}
+int fail(int status, const std::string &msg) {
+    g_last_error = msg;
+    return status;
+}
+
+#define CK(call)                                                  \
+    do {                                                          \
+        cudaError_t _e = (call);                                  \
+        if (_e != cudaSuccess) return fail_cuda(_e, #call, __LINE__); \
+    } while (0)
+
+constexpr size_t ELEM_BYTES = LAT_RING_DEGREE * sizeof(uint64_t);  // 192
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t want) {
+        if (want <= bytes) return LAT_OK;
+        if (p) {
+            cudaError_t e = cudaFree(p);
+            p = nullptr;
+            bytes = 0;
+            if (e != cudaSuccess) return fail_cuda(e, "cudaFree", __LINE__);
+        }
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail_cuda(e, "cudaMalloc", __LINE__);
+        }
+        bytes = want;
+        return LAT_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace
+
+struct lat_ajtai {
+    int device = 0;
+    int sm_count = 148;
+    bool mont = false;
+    uint32_t kappa = 0, log2_B = 0, L = 0, K = 0;
+    u64 n = 0;
+    lat::MatLayout lay{};
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+
+    DevBuf A;            // re-laid-out matrix, canonical form
+    std::vector<uint8_t> row_done;
+    uint32_t rows_done = 0;
+
+    DevBuf stage;        // upload staging (one row at a time)
+    DevBuf in;           // host-call input staging (w_ccs / f / f_coeff)
+    DevBuf f16;          // resident decomposed witness, int16 digits, n x 24
+    DevBuf f;            // CRT-form witness, n x 24 u64
+    DevBuf fcoeff64;     // f_coeff as u64 for host output
+    DevBuf planes;       // K x n x 24 CRT-form planes
+    DevBuf planes_coeff; // K x n x 24 coefficient-form planes (host output only)
+    DevBuf cms;          // up to max(K, batch) x kappa x 24
+    DevBuf cm_in;        // kappa x 24
+    DevBuf ws;           // mac partials
+    DevBuf flag;         // int
+    int *h_flag = nullptr;  // pinned
+    bool has_resident = false;
+
+    int bind() {
+        CK(cudaSetDevice(device));
+        return LAT_OK;
+    }
+    int matrix_ready() const {
+        if (rows_done != kappa)
+            return fail(LAT_E_MATRIX_INCOMPLETE, "Ajtai matrix incomplete: " + std::to_string(rows_done) + " of " +
+                                                     std::to_string(kappa) + " rows uploaded");
+        return LAT_OK;
+    }
+    int wrong_len(u64 got) const {
+        return fail(LAT_E_WRONG_WITNESS_LENGTH, "Wrong length of the witness: " + std::to_string(got) +
+                                                    ", expected: " + std::to_string(n));
+    }
+    // mac + reduce into cms_dev for `count` witnesses laid out count x stride x 24
+    int mac(const u64 *F, u64 stride, uint32_t count, u64 *cms_dev) {
+        lat::MacPlan plan = lat::plan_mac(lay, count, sm_count);
+        int st = ws.ensure(plan.ws_elems * sizeof(u64));
+        if (st) return st;
+        lat::launch_mac(A.as<u64>(), lay, F, stride, count, plan, ws.as<u64>(), cms_dev, stream);
+        CK(cudaGetLastError());
+        return LAT_OK;
+    }
+    int clear_flag() {
+        CK(cudaMemsetAsync(flag.p, 0, sizeof(int), stream));
+        return LAT_OK;
+    }
+    // synchronise, fetch and clear the overflow flag
+    int finish() {
+        CK(cudaMemcpyAsync(h_flag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemsetAsync(flag.p, 0, sizeof(int), stream));
+        CK(cudaStreamSynchronize(stream));
+        if (*h_flag)
+            return fail(LAT_E_DIGIT_OVERFLOW, "a coefficient needs more digits than the decomposition padding allows");
+        return LAT_OK;
+    }
+};
+
+extern "C" {
+
+const char *lat_strerror(int status) {
+    switch (status) {
+        case LAT_OK: return "ok";
+        case LAT_E_WRONG_WITNESS_LENGTH: return "wrong length of the witness";
+        case LAT_E_WRONG_COMMITMENT_LENGTH: return "wrong length of the commitment";
+        case LAT_E_WRONG_MATRIX_DIMENSIONS: return "Ajtai matrix has wrong dimensions";
+        case LAT_E_DIGIT_OVERFLOW: return "coefficient does not fit in the requested number of digits";
+        case LAT_E_INVALID_ARGUMENT: return "invalid argument";
+        case LAT_E_CUDA: return "CUDA failure (no CPU fallback exists)";
+        case LAT_E_MATRIX_INCOMPLETE: return "Ajtai matrix rows missing";
+        default: return "unknown status";
+    }
+}
+const char *lat_last_error(void) { return g_last_error.c_str(); }
+int lat_abi_version(void) { return LAT_ABI_VERSION; }
+
+int lat_ajtai_create(lat_ajtai **out, uint32_t kappa, uint64_t n, uint32_t log2_B, uint32_t L, uint32_t K, int repr,
+                     int device) {
+    if (!out) return fail(LAT_E_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (kappa == 0 || n == 0) return fail(LAT_E_WRONG_MATRIX_DIMENSIONS, "kappa and n must be positive");
+    if (log2_B < 1 || log2_B > 15 || L < 1 || L > 8 || K < 1 || K > 15)
+        return fail(LAT_E_INVALID_ARGUMENT, "need 1<=log2_B<=15, 1<=L<=8, 1<=K<=15");
+    if (repr != LAT_REPR_CANONICAL && repr != LAT_REPR_MONTGOMERY) return fail(LAT_E_INVALID_ARGUMENT, "bad repr");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(LAT_E_CUDA, "no such CUDA device (this engine has no CPU fallback)");
+    CK(cudaSetDevice(device));
+    lat_ajtai *h = new (std::nothrow) lat_ajtai();
+    if (!h) return fail(LAT_E_INVALID_ARGUMENT, "out of host memory");
+    h->device = device;
+    h->mont = repr == LAT_REPR_MONTGOMERY;
+    h->kappa = kappa;
+    h->n = n;
+    h->log2_B = log2_B;
+    h->L = L;
+    h->K = K;
+    h->lay = lat::make_layout(kappa, n);
+    h->row_done.assign(kappa, 0);
+    int st = LAT_OK;
+    cudaError_t e;
+    do {
+        if ((e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) break;
+        if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) break;
+        h->stream = h->own_stream;
+        if ((e = cudaHostAlloc((void **)&h->h_flag, sizeof(int), cudaHostAllocDefault)) != cudaSuccess) break;
+        size_t a_bytes = h->lay.total_elems() * sizeof(u64);
+        if ((st = h->A.ensure(a_bytes))) break;
+        if ((e = cudaMemsetAsync(h->A.p, 0, a_bytes, h->stream)) != cudaSuccess) break;  // zero padding rows/columns
+        if ((st = h->flag.ensure(sizeof(int)))) break;
+        if ((e = cudaMemsetAsync(h->flag.p, 0, sizeof(int), h->stream)) != cudaSuccess) break;
+        if ((st = h->f16.ensure(n * LAT_RING_DEGREE * sizeof(int16_t)))) break;
+        if ((st = h->f.ensure(n * ELEM_BYTES))) break;
+        if ((st = h->cms.ensure((size_t)K * kappa * ELEM_BYTES))) break;
+        if ((st = h->cm_in.ensure((size_t)kappa * ELEM_BYTES))) break;
+        if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) break;
+    } while (0);
+    if (st == LAT_OK && e != cudaSuccess) st = fail_cuda(e, "lat_ajtai_create", __LINE__);
+    if (st != LAT_OK) {
+        lat_ajtai_destroy(h);
+        return st;
+    }
+    *out = h;
+    return LAT_OK;
+}
+
+void lat_ajtai_destroy(lat_ajtai *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+    DevBuf *bufs[] = {&h->A, &h->stage, &h->in, &h->f16, &h->f, &h->fcoeff64, &h->planes, &h->planes_coeff,
+                      &h->cms, &h->cm_in, &h->ws, &h->flag};
+    for (DevBuf *b : bufs) b->release();
+    if (h->h_flag) cudaFreeHost(h->h_flag);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+uint32_t lat_ajtai_kappa(const lat_ajtai *h) { return h ? h->kappa : 0; }
+uint64_t lat_ajtai_width(const lat_ajtai *h) { return h ? h->n : 0; }
+
+int lat_ajtai_set_stream(lat_ajtai *h, void *cuda_stream) {
+    if (!h) return fail(LAT_E_INVALID_ARGUMENT, "NULL handle");
+    int st = h->bind();
+    if (st) return st;
+    CK(cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return LAT_OK;
+}
+
+int lat_ajtai_synchronize(lat_ajtai *h) {
+    if (!h) return fail(LAT_E_INVALID_ARGUMENT, "NULL handle");
+    int st = h->bind();
+    if (st) return st;
+    return h->finish();
+}
+
+static int mark_rows(lat_ajtai *h, uint32_t row0, uint32_t nrows) {
+    for (uint32_t r = row0; r < row0 + nrows; ++r)
+        if (!h->row_done[r]) {
+            h->row_done[r] = 1;
+            h->rows_done++;
+        }
+    return LAT_OK;
+}
+
+int lat_ajtai_upload_rows_dev(lat_ajtai *h, uint32_t row0, uint32_t nrows, const uint64_t *rows_dev, uint64_t row_stride) {
+    if (!h || !rows_dev) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if ((u64)row0 + nrows > h->kappa || row_stride < h->n)
+        return fail(LAT_E_WRONG_MATRIX_DIMENSIONS, "rows outside the kappa x n matrix");
+    int st = h->bind();
+    if (st) return st;
+    lat::launch_relayout((const u64 *)rows_dev, row0, nrows, row_stride, h->mont, h->lay, h->A.as<u64>(), h->stream);
+    CK(cudaGetLastError());
+    return mark_rows(h, row0, nrows);
+}
+
+int lat_ajtai_upload_rows(lat_ajtai *h, uint32_t row0, uint32_t nrows, const uint64_t *rows, uint64_t row_stride) {
+    if (!h || !rows) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if ((u64)row0 + nrows > h->kappa || row_stride < h->n)
+        return fail(LAT_E_WRONG_MATRIX_DIMENSIONS, "rows outside the kappa x n matrix");
+    int st = h->bind();
+    if (st) return st;
+    size_t row_bytes = h->n * ELEM_BYTES;
+    if ((st = h->stage.ensure(row_bytes))) return st;
+    for (uint32_t r = 0; r < nrows; ++r) {
+        // stream order makes the single staging row safe: the copy of row r+1 starts after relayout of row r
+        CK(cudaMemcpyAsync(h->stage.p, rows + (size_t)r * row_stride * LAT_RING_DEGREE, row_bytes, cudaMemcpyHostToDevice,
+                           h->stream));
+        lat::launch_relayout(h->stage.as<u64>(), row0 + r, 1, h->n, h->mont, h->lay, h->A.as<u64>(), h->stream);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return mark_rows(h, row0, nrows);
+}
+
+// ---- commit ----------------------------------------------------------------------------------------------------
+int lat_ajtai_commit_ntt_batch_dev(lat_ajtai *h, const uint64_t *fs_dev, uint32_t count, uint64_t f_len,
+                                   uint64_t *cms_dev) {
+    if (!h || !fs_dev || !cms_dev) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (f_len != h->n) return h->wrong_len(f_len);
+    if (count == 0) return LAT_OK;
+    int st = h->bind();
+    if (st || (st = h->matrix_ready())) return st;
+    return h->mac((const u64 *)fs_dev, f_len, count, (u64 *)cms_dev);
+}
+int lat_ajtai_commit_ntt_dev(lat_ajtai *h, const uint64_t *f_dev, uint64_t f_len, uint64_t *cm_dev) {
+    return lat_ajtai_commit_ntt_batch_dev(h, f_dev, 1, f_len, cm_dev);
+}
+
+int lat_ajtai_commit_ntt_batch(lat_ajtai *h, const uint64_t *fs, uint32_t count, uint64_t f_len, uint64_t *cms) {
+    if (!h || !fs || !cms) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (f_len != h->n) return h->wrong_len(f_len);
+    if (count == 0) return LAT_OK;
+    int st = h->bind();
+    if (st || (st = h->matrix_ready())) return st;
+    size_t in_bytes = (size_t)count * f_len * ELEM_BYTES, out_bytes = (size_t)count * h->kappa * ELEM_BYTES;
+    if ((st = h->in.ensure(in_bytes)) || (st = h->cms.ensure(out_bytes))) return st;
+    CK(cudaMemcpyAsync(h->in.p, fs, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    if ((st = h->mac(h->in.as<u64>(), f_len, count, h->cms.as<u64>()))) return st;
+    CK(cudaMemcpyAsync(cms, h->cms.p, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    return h->finish();
+}
+int lat_ajtai_commit_ntt(lat_ajtai *h, const uint64_t *f, uint64_t f_len, uint64_t *cm) {
+    return lat_ajtai_commit_ntt_batch(h, f, 1, f_len, cm);
+}
+
+int lat_ajtai_commit_coeff(lat_ajtai *h, const uint64_t *f_coeff, uint64_t f_len, uint64_t *cm) {
+    if (!h || !f_coeff || !cm) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (f_len != h->n) return h->wrong_len(f_len);
+    int st = h->bind();
+    if (st || (st = h->matrix_ready())) return st;
+    size_t in_bytes = f_len * ELEM_BYTES;
+    if ((st = h->in.ensure(in_bytes))) return st;
+    CK(cudaMemcpyAsync(h->in.p, f_coeff, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    lat::launch_crt(h->in.as<u64>(), h->f.as<u64>(), f_len, h->stream);
+    CK(cudaGetLastError());
+    h->has_resident = false;
+    if ((st = h->mac(h->f.as<u64>(), f_len, 1, h->cms.as<u64>()))) return st;
+    CK(cudaMemcpyAsync(cm, h->cms.p, (size_t)h->kappa * ELEM_BYTES, cudaMemcpyDeviceToHost, h->stream));
+    return h->finish();
+}
+
+// shared by from_w_ccs and decompose_and_commit_*: device input -> digits -> CRT -> (commit)
+static int witness_core(lat_ajtai *h, const u64 *w_dev, u64 w_len, bool in_coeff, u64 *f_coeff_dev, u64 *f_dev,
+                        u64 *cm_dev) {
+    lat::launch_icrt_decompose(w_dev, w_len, (int)h->log2_B, (int)h->L, h->mont, in_coeff, h->f16.as<int16_t>(),
+                               f_coeff_dev, h->flag.as<int>(), h->stream);
+    CK(cudaGetLastError());
+    u64 *f_target = f_dev ? f_dev : h->f.as<u64>();
+    lat::launch_crt_small(h->f16.as<int16_t>(), h->n, h->mont, f_target, h->stream);
+    CK(cudaGetLastError());
+    h->has_resident = true;
+    if (cm_dev) return h->mac(f_target, h->n, 1, cm_dev);
+    return LAT_OK;
+}
+
+int lat_ajtai_witness_from_w_ccs_dev(lat_ajtai *h, const uint64_t *w_ccs_dev, uint64_t w_len, uint64_t *f_coeff_dev,
+                                     uint64_t *f_dev, uint64_t *cm_dev) {
+    if (!h || !w_ccs_dev) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (w_len * h->L != h->n) return h->wrong_len(w_len * h->L);
+    int st = h->bind();
+    if (st) return st;
+    if (cm_dev && (st = h->matrix_ready())) return st;
+    return witness_core(h, (const u64 *)w_ccs_dev, w_len, false, (u64 *)f_coeff_dev, (u64 *)f_dev, (u64 *)cm_dev);
+}
+
+static int witness_host(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool in_coeff, uint64_t *f_coeff, uint64_t *f,
+                        uint64_t *cm) {
+    if (!h || !w) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (w_len * h->L != h->n) return h->wrong_len(w_len * h->L);
+    int st = h->bind();
+    if (st) return st;
+    if (cm && (st = h->matrix_ready())) return st;
+    size_t in_bytes = w_len * ELEM_BYTES, n_bytes = h->n * ELEM_BYTES;
+    if ((st = h->in.ensure(in_bytes))) return st;
+    if (f_coeff && (st = h->fcoeff64.ensure(n_bytes))) return st;
+    CK(cudaMemcpyAsync(h->in.p, w, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    st = witness_core(h, h->in.as<u64>(), w_len, in_coeff, f_coeff ? h->fcoeff64.as<u64>() : nullptr, nullptr,
+                      cm ? h->cms.as<u64>() : nullptr);
+    if (st) return st;
+    if (cm) CK(cudaMemcpyAsync(cm, h->cms.p, (size_t)h->kappa * ELEM_BYTES, cudaMemcpyDeviceToHost, h->stream));
+    if (f_coeff) CK(cudaMemcpyAsync(f_coeff, h->fcoeff64.p, n_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (f) CK(cudaMemcpyAsync(f, h->f.p, n_bytes, cudaMemcpyDeviceToHost, h->stream));
+    return h->finish();
+}
+
+int lat_ajtai_witness_from_w_ccs(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_len, uint64_t *f_coeff, uint64_t *f,
+                                 uint64_t *cm) {
+    return witness_host(h, w_ccs, w_len, false, f_coeff, f, cm);
+}
+int lat_ajtai_decompose_and_commit_ntt(lat_ajtai *h, const uint64_t *w, uint64_t w_len, uint64_t *cm) {
+    if (!cm) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    return witness_host(h, w, w_len, false, nullptr, nullptr, cm);
+}
+int lat_ajtai_decompose_and_commit_coeff(lat_ajtai *h, const uint64_t *w_coeff, uint64_t w_len, uint64_t *cm) {
+    if (!cm) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    return witness_host(h, w_coeff, w_len, true, nullptr, nullptr, cm);
+}
+
+// ---- decompose_witness + commit_witnesses ---------------------------------------------------------------------------
+// f16 already holds the coefficients; produce planes (to caller buffers or internal), K-1 commits and y_0.
+static int planes_core(lat_ajtai *h, const u64 *cm_dev, u64 *planes_coeff_dev, u64 *planes_f_dev, u64 *cms_dev) {
+    int st;
+    u64 *pf = planes_f_dev;
+    if (!pf && cms_dev) {
+        if ((st = h->planes.ensure((size_t)h->K * h->n * ELEM_BYTES))) return st;
+        pf = h->planes.as<u64>();
+    }
+    if (pf || planes_coeff_dev) {
+        lat::launch_planes(h->f16.as<int16_t>(), h->n, (int)h->K, h->mont, pf, h->n, planes_coeff_dev, h->stream);
+        CK(cudaGetLastError());
+    }
+    if (cms_dev) {
+        if (h->K > 1) {
+            st = h->mac(pf + h->n * LAT_RING_DEGREE, h->n, h->K - 1, cms_dev + (size_t)h->kappa * LAT_RING_DEGREE);
+            if (st) return st;
+        }
+        lat::launch_y0(cm_dev, cms_dev, h->K, h->kappa, h->stream);
+        CK(cudaGetLastError());
+    }
+    return LAT_OK;
+}
+
+int lat_ajtai_decompose_commit_dev(lat_ajtai *h, const uint64_t *f_coeff_dev, uint64_t n, const uint64_t *cm_dev,
+                                   uint64_t *planes_coeff_dev, uint64_t *planes_f_dev, uint64_t *cms_dev) {
+    if (!h || !f_coeff_dev) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (cms_dev && !cm_dev) return fail(LAT_E_INVALID_ARGUMENT, "cm is required to derive cms[0]");
+    if (n != h->n) return h->wrong_len(n);
+    int st = h->bind();
+    if (st) return st;
+    if (cms_dev && (st = h->matrix_ready())) return st;
+    lat::launch_pack_coeff((const u64 *)f_coeff_dev, n, h->mont, (int)h->K, h->f16.as<int16_t>(), h->flag.as<int>(),
+                           h->stream);
+    CK(cudaGetLastError());
+    h->has_resident = true;
+    return planes_core(h, (const u64 *)cm_dev, (u64 *)planes_coeff_dev, (u64 *)planes_f_dev, (u64 *)cms_dev);
+}
+
+static int planes_host(lat_ajtai *h, const uint64_t *cm, uint64_t *planes_coeff, uint64_t *planes_f, uint64_t *cms) {
+    int st;
+    size_t plane_bytes = (size_t)h->K * h->n * ELEM_BYTES, cm_bytes = (size_t)h->kappa * ELEM_BYTES;
+    if (cms) {
+        if (!cm) return fail(LAT_E_INVALID_ARGUMENT, "cm is required to derive cms[0]");
+        if ((st = h->cms.ensure((size_t)h->K * cm_bytes))) return st;
+        CK(cudaMemcpyAsync(h->cm_in.p, cm, cm_bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (planes_coeff && (st = h->planes_coeff.ensure(plane_bytes))) return st;
+    if ((planes_f || cms) && (st = h->planes.ensure(plane_bytes))) return st;
+    st = planes_core(h, h->cm_in.as<u64>(), planes_coeff ? h->planes_coeff.as<u64>() : nullptr,
+                     (planes_f || cms) ? h->planes.as<u64>() : nullptr, cms ? h->cms.as<u64>() : nullptr);
+    if (st) return st;
+    if (cms) CK(cudaMemcpyAsync(cms, h->cms.p, (size_t)h->K * cm_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (planes_f) CK(cudaMemcpyAsync(planes_f, h->planes.p, plane_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (planes_coeff) CK(cudaMemcpyAsync(planes_coeff, h->planes_coeff.p, plane_bytes, cudaMemcpyDeviceToHost, h->stream));
+    return h->finish();
+}
+
+int lat_ajtai_decompose_commit(lat_ajtai *h, const uint64_t *f_coeff, uint64_t n, const uint64_t *cm,
+                               uint64_t *planes_coeff, uint64_t *planes_f, uint64_t *cms) {
+    if (!h || !f_coeff) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (n != h->n) return h->wrong_len(n);
+    int st = h->bind();
+    if (st) return st;
+    if (cms && (st = h->matrix_ready())) return st;
+    size_t in_bytes = n * ELEM_BYTES;
+    if ((st = h->in.ensure(in_bytes))) return st;
+    CK(cudaMemcpyAsync(h->in.p, f_coeff, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    lat::launch_pack_coeff(h->in.as<u64>(), n, h->mont, (int)h->K, h->f16.as<int16_t>(), h->flag.as<int>(), h->stream);
+    CK(cudaGetLastError());
+    h->has_resident = true;
+    return planes_host(h, cm, planes_coeff, planes_f, cms);
+}
+
+int lat_ajtai_decompose_commit_resident(lat_ajtai *h, const uint64_t *cm, uint64_t *planes_coeff, uint64_t *planes_f,
+                                        uint64_t *cms) {
+    if (!h) return fail(LAT_E_INVALID_ARGUMENT, "NULL handle");
+    if (!h->has_resident) return fail(LAT_E_INVALID_ARGUMENT, "no resident witness: call lat_ajtai_witness_from_w_ccs first");
+    int st = h->bind();
+    if (st) return st;
+    if (cms && (st = h->matrix_ready())) return st;
+    // the resident digits are base-B limbs (|c| <= B/2 <= 2^14 < 2^K for the zkVM parameters); re-check the bound
+    // only when it could fail
+    if (h->log2_B > h->K) {
+        return fail(LAT_E_INVALID_ARGUMENT, "resident limbs may exceed 2^K (log2_B > K): use lat_ajtai_decompose_commit");
+    }
+    return planes_host(h, cm, planes_coeff, planes_f, cms);
+}
+
+// ---- standalone transforms ---------------------------------------------------------------------------------------
+int lat_ring_crt_dev(const uint64_t *coeff_dev, uint64_t count, uint64_t *ntt_dev, void *cuda_stream) {
+    if (count && (!coeff_dev || !ntt_dev)) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    lat::launch_crt((const u64 *)coeff_dev, (u64 *)ntt_dev, count, (cudaStream_t)cuda_stream);
+    CK(cudaGetLastError());
+    return LAT_OK;
+}
+int lat_ring_icrt_dev(const uint64_t *ntt_dev, uint64_t count, uint64_t *coeff_dev, void *cuda_stream) {
+    if (count && (!ntt_dev || !coeff_dev)) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    lat::launch_icrt((const u64 *)ntt_dev, (u64 *)coeff_dev, count, (cudaStream_t)cuda_stream);
+    CK(cudaGetLastError());
+    return LAT_OK;
+}
+
+static int ring_host(const uint64_t *in, uint64_t count, uint64_t *out, int device, bool inverse) {
+    if (count == 0) return LAT_OK;
+    if (!in || !out) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    CK(cudaSetDevice(device));
+    DevBuf buf;
+    int st = buf.ensure(count * ELEM_BYTES);
+    if (st) return st;
+    cudaError_t e = cudaMemcpy(buf.p, in, count * ELEM_BYTES, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        if (inverse) lat::launch_icrt(buf.as<u64>(), buf.as<u64>(), count, nullptr);
+        else lat::launch_crt(buf.as<u64>(), buf.as<u64>(), count, nullptr);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, buf.p, count * ELEM_BYTES, cudaMemcpyDeviceToHost);
+    buf.release();
+    if (e != cudaSuccess) return fail_cuda(e, "lat_ring_crt/icrt", __LINE__);
+    return LAT_OK;
+}
+int lat_ring_crt(const uint64_t *coeff, uint64_t count, uint64_t *ntt, int device) {
+    return ring_host(coeff, count, ntt, device, false);
+}
+int lat_ring_icrt(const uint64_t *ntt, uint64_t count, uint64_t *coeff, int device) {
+    return ring_host(ntt, count, coeff, device, true);
+}
+
+int lat_ring_gadget_decompose(const uint64_t *in, uint64_t count, uint32_t log2_b, uint32_t L, uint64_t *out, int repr,
+                              int device) {
+    if (count == 0) return LAT_OK;
+    if (!in || !out) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (log2_b < 1 || log2_b > 15 || L < 1 || L > 32) return fail(LAT_E_INVALID_ARGUMENT, "need 1<=log2_b<=15, 1<=L<=32");
+    CK(cudaSetDevice(device));
+    DevBuf din, d16, dout, dflag;
+    int st = LAT_OK;
+    int h_flag = 0;
+    cudaError_t e = cudaSuccess;
+    do {
+        if ((st = din.ensure(count * ELEM_BYTES)) || (st = d16.ensure(count * L * LAT_RING_DEGREE * sizeof(int16_t))) ||
+            (st = dout.ensure(count * L * ELEM_BYTES)) || (st = dflag.ensure(sizeof(int))))
+            break;
+        if ((e = cudaMemset(dflag.p, 0, sizeof(int))) != cudaSuccess) break;
+        if ((e = cudaMemcpy(din.p, in, count * ELEM_BYTES, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        lat::launch_icrt_decompose(din.as<u64>(), count, (int)log2_b, (int)L, repr == LAT_REPR_MONTGOMERY, true,
+                                   d16.as<int16_t>(), dout.as<u64>(), dflag.as<int>(), nullptr);
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        if ((e = cudaMemcpy(out, dout.p, count * L * ELEM_BYTES, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(&h_flag, dflag.p, sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+    } while (0);
+    din.release(); d16.release(); dout.release(); dflag.release();
+    if (st) return st;
+    if (e != cudaSuccess) return fail_cuda(e, "lat_ring_gadget_decompose", __LINE__);
+    if (h_flag) return fail(LAT_E_DIGIT_OVERFLOW, "a coefficient needs more than L digits");
+    return LAT_OK;
+}
+
+int lat_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    CK(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return LAT_OK;
+}
+void lat_host_free(void *ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+// Internal launcher interface between engine.cu (the C ABI) and the kernel translation units.
+// Everything here is asynchronous on `stream`; pointers are device pointers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace lat {
+
+typedef unsigned long long u64;
+
+// ---- ring_kernels.cu ------------------------------------------------------------------------------------
+// Batched CRT / iCRT of `count` ring elements of 24 u64 (in-place allowed).
+void launch_crt(const u64 *in, u64 *out, u64 count, cudaStream_t stream);
+void launch_icrt(const u64 *in, u64 *out, u64 count, cudaStream_t stream);
+
+// w (CRT form, `mont` says which representation) -> iCRT -> balanced digits base 2^log2b, L limbs.
+//   f16      : w_len*L x 24 int16 digits, element-major / limb-minor (always written)
+//   f_coeff  : same as u64 field elements in the caller's representation, or nullptr
+//   in_coeff : if true the input is already in coefficient form (skip the iCRT)
+//   flag     : device int, OR-ed with 1 when a coefficient does not fit in L digits
+void launch_icrt_decompose(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool in_coeff, int16_t *f16,
+                           u64 *f_coeff, int *flag, cudaStream_t stream);
+
+// int16 digits -> CRT-form elements.  out has `count` elements.
+void launch_crt_small(const int16_t *f16, u64 count, bool mont, u64 *out, cudaStream_t stream);
+
+// int16 coefficients -> K base-2 digit planes: plane k of element j = sign * bit_k(|c|).
+//   planes_f     : K x plane_stride x 24 CRT form (plane_stride >= n, in elements), or nullptr
+//   planes_coeff : K x n x 24 coefficient form, or nullptr
+void launch_planes(const int16_t *f16, u64 n, int K, bool mont, u64 *planes_f, u64 plane_stride, u64 *planes_coeff,
+                   cudaStream_t stream);
+
+// u64 coefficient-form elements (caller's representation) -> int16, flag |= 1 unless |c| < 2^bits for all c.
+void launch_pack_coeff(const u64 *f_coeff, u64 count, bool mont, int bits, int16_t *f16, int *flag,
+                       cudaStream_t stream);
+
+// ---- mac_kernels.cu -------------------------------------------------------------------------------------
+// Geometry of the device-resident matrix, fixed at creation.
+struct MatLayout {
+    uint32_t kappa;      // logical rows
+    uint32_t kappa_pad;  // rows incl. zero padding
+    uint32_t rb;         // rows per row block (multiple of 4, <= 32)
+    uint32_t nrb;        // row blocks
+    uint32_t rg;         // row groups (warps along rows) per CTA = rb / 4
+    uint32_t cg;         // column groups (warps along columns) per CTA
+    uint32_t tj;         // columns per tile
+    u64 n;               // logical columns
+    u64 n_pad;           // columns incl. zero padding (multiple of tj)
+    u64 ntiles;          // n_pad / tj
+    __host__ __device__ u64 tile_elems() const { return (u64)tj * 3 * rb * 8; }           // u64 per tile
+    __host__ __device__ u64 total_elems() const { return tile_elems() * ntiles * nrb; }   // u64 in the whole matrix
+};
+MatLayout make_layout(uint32_t kappa, u64 n);
+
+// rows: nrows x row_stride x 24 (CRT form, caller's representation) -> tiles of A_dev (canonical form).
+void launch_relayout(const u64 *rows, uint32_t row0, uint32_t nrows, u64 row_stride, bool mont, const MatLayout &lay,
+                     u64 *A_dev, cudaStream_t stream);
+
+// Number of partial-sum slots mac needs for `planes` witnesses, and the workspace size in u64.
+struct MacPlan {
+    uint32_t pt;        // planes per thread
+    uint32_t grid_x;    // column-chunk CTAs
+    uint32_t nslots;    // partial slots per (plane, row)
+    size_t ws_elems;    // u64 of workspace
+    size_t smem_bytes;
+    uint32_t stages;
+};
+MacPlan plan_mac(const MatLayout &lay, uint32_t planes, int sm_count);
+
+// cms[p][i][24] = sum_j A[i][j] * F[p][j]   for p < planes;  F: planes x f_stride x 24 (f_stride >= n; no padding needed).
+void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *F, u64 f_stride, uint32_t planes, const MacPlan &plan,
+                u64 *workspace, u64 *cms, cudaStream_t stream);
+
+// cms[0] = cm - sum_{k=1..K-1} 2^k cms[k]      (LF/nifs/decomposition.rs:189-197)
+void launch_y0(const u64 *cm, u64 *cms, uint32_t K, uint32_t kappa, cudaStream_t stream);
+
+}  // namespace lat

@@ -1,0 +1,306 @@
+// The Ajtai matrix-vector product in CRT form on sm_100a:  cm[p][i] = sum_j A[i][j] (*) F[p][j]  with (*) the
+// slot-wise Fq3 product.  Replaces Matrix::checked_mul_vec (stark-rings/crates/linear_algebra/src/matrix.rs:168-178,
+// called from AjtaiCommitmentScheme::commit, latticefold/src/commitment/commitment_scheme.rs:63-80) and the loop of
+// K-1 such commits in LFDecompositionProver::commit_witnesses (latticefold/src/nifs/decomposition.rs:185-187).
+//
+// Design (DESIGN.md "mac kernel"):
+//  * The matrix is re-laid out ONCE at upload into column tiles  [row block][tile][column jj][component c][row i][slot s]
+//    (canonical form), so that a tile is one contiguous run of bytes in HBM and a warp's shared-memory read of
+//    (jj, c) is 32 consecutive u64 (conflict-free).  Tiles are streamed with TMA bulk copies (cp.async.bulk ->
+//    UBLKCP) into a multi-stage shared-memory ring guarded by mbarriers; one producer warp, RG*CG consumer warps.
+//  * Split-K over columns: every CTA owns a contiguous range of tiles and keeps, per thread, the UNREDUCED
+//    accumulators of one output (row, slot) for PT witnesses ("planes"): 5 sums x 3 columns x (64+32) bits
+//    (gl::Fq3Acc).  One 64x64 product = 4 IMAD.WIDE.U32 with carry-out + 2 IADD3.X; a single special-form
+//    reduction per output at the end.  No tensor cores: this is exact 64-bit modular integer work.
+//  * Per-CTA partial results (canonical u64) go to a small workspace; mac_reduce_kernel sums them mod q.
+//  * A is canonical and F is in the caller's representation, so canonical(A) * repr(F) = repr(A*F): the
+//    commitment comes out in the caller's representation without any conversion (the map is Fq-linear).
+#include <cstdio>
+
+#include "kernels.h"
+#include "ring24.cuh"
+
+namespace lat {
+using gl::u32;
+
+constexpr int SM_RESERVED_SMEM = 1024;
+constexpr int MAX_STAGES = 4;
+
+MatLayout make_layout(uint32_t kappa, u64 n) {
+    MatLayout l{};
+    l.kappa = kappa;
+    l.n = n;
+    uint32_t k4 = (kappa + 3) / 4 * 4;
+    if (k4 <= 32) {
+        l.kappa_pad = k4;
+        l.rb = k4;
+    } else {
+        l.kappa_pad = (kappa + 31) / 32 * 32;
+        l.rb = 32;
+    }
+    l.nrb = l.kappa_pad / l.rb;
+    l.rg = l.rb / 4;
+    l.cg = 8 / l.rg;
+    if (l.cg < 1) l.cg = 1;
+    // ~12 KB tiles: tj * rb * 192 B
+    uint32_t tj = 64 / l.rb;
+    if (tj < 2) tj = 2;
+    tj = (tj / l.cg) * l.cg;
+    if (tj < l.cg) tj = l.cg;
+    l.tj = tj;
+    l.ntiles = (n + tj - 1) / tj;
+    if (l.ntiles == 0) l.ntiles = 1;
+    l.n_pad = l.ntiles * tj;
+    return l;
+}
+
+// ---- upload-time re-layout ------------------------------------------------------------------------------------
+// One thread per destination u64 of the rows being uploaded.  dst index inside a tile: ((jj*3 + c)*rb + il)*8 + s.
+template <bool MONT>
+__global__ void __launch_bounds__(256)
+relayout_kernel(const u64 *__restrict__ rows, uint32_t row0, uint32_t nrows, u64 row_stride, MatLayout lay,
+                u64 *__restrict__ A_dev) {
+    // thread -> (r, j, c, s) with s fastest, then c... we iterate in SOURCE order for coalesced reads:
+    u64 idx = (u64)blockIdx.x * 256 + threadIdx.x;
+    u64 per_row = lay.n * ring::D;
+    if (idx >= (u64)nrows * per_row) return;
+    uint32_t r = (uint32_t)(idx / per_row);
+    u64 rem = idx - (u64)r * per_row;
+    u64 j = rem / ring::D;
+    uint32_t t = (uint32_t)(rem - j * ring::D);
+    uint32_t s = t / 3, c = t - 3 * s;
+    u64 v = rows[((u64)r * row_stride + j) * ring::D + t];
+    if constexpr (MONT) v = gl::from_mont(v);
+    else v = gl::reduce128(v, 0);
+    uint32_t i = row0 + r;
+    uint32_t rbk = i / lay.rb, il = i - rbk * lay.rb;
+    u64 tile = j / lay.tj;
+    uint32_t jj = (uint32_t)(j - tile * lay.tj);
+    u64 dst = ((u64)rbk * lay.ntiles + tile) * lay.tile_elems() + ((u64)(jj * 3 + c) * lay.rb + il) * 8 + s;
+    A_dev[dst] = v;
+}
+
+void launch_relayout(const u64 *rows, uint32_t row0, uint32_t nrows, u64 row_stride, bool mont, const MatLayout &lay,
+                     u64 *A_dev, cudaStream_t stream) {
+    u64 total = (u64)nrows * lay.n * ring::D;
+    if (!total) return;
+    unsigned grid = (unsigned)((total + 255) / 256);
+    if (mont) relayout_kernel<true><<<grid, 256, 0, stream>>>(rows, row0, nrows, row_stride, lay, A_dev);
+    else relayout_kernel<false><<<grid, 256, 0, stream>>>(rows, row0, nrows, row_stride, lay, A_dev);
+}
+
+// ---- mbarrier / TMA bulk-copy primitives (inline PTX; SASS: SYNCS.*, UBLKCP) -------------------------------------
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u64 *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    u32 done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- the MAC kernel --------------------------------------------------------------------------------------------
+// grid = (column chunks, row blocks, plane groups); block = (RG*CG consumer warps + 1 producer warp) * 32.
+// Shared memory: stages x { A tile | PT x tj x 24 u64 of F } + 2*stages mbarriers.
+// Partials layout: ws[((slot * planes + p) * kappa_pad + row) * 24 + s*3 + c], slot = blockIdx.x * CG + cg.
+template <int PT>
+__global__ void __launch_bounds__(288, (PT == 1) ? 2 : 1)
+mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__ F, u64 f_stride, uint32_t planes,
+           uint32_t stages, u64 *__restrict__ ws) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const u32 tile_bytes = (u32)(lay.tile_elems() * 8);
+    const u32 f_bytes = lay.tj * ring::D * 8;  // per plane per tile
+    const u32 stage_bytes = tile_bytes + PT * f_bytes;
+    u64 *bars = reinterpret_cast<u64 *>(smem_raw + (size_t)stages * stage_bytes);  // [full x stages][empty x stages]
+
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 n_cons = lay.rg * lay.cg;  // consumer warps; warp n_cons is the producer
+    const u32 rbk = blockIdx.y;
+    const u32 p0 = blockIdx.z * PT;
+
+    // contiguous tile range of this CTA
+    const u64 t_begin = lay.ntiles * blockIdx.x / gridDim.x;
+    const u64 t_end = lay.ntiles * (blockIdx.x + 1) / gridDim.x;
+    const u32 my_tiles = (u32)(t_end - t_begin);
+
+    if (threadIdx.x == 0) {
+        for (u32 st = 0; st < stages; ++st) {
+            mbar_init(&bars[st], 1);                // full: one arrive (producer) + tx bytes
+            mbar_init(&bars[stages + st], n_cons);  // empty: one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == n_cons) {
+        // ===== producer: one elected lane streams tiles with TMA bulk copies =====
+        if (lane == 0) {
+            const u64 *a_src = A_dev + ((u64)rbk * lay.ntiles + t_begin) * lay.tile_elems();
+            for (u32 t = 0; t < my_tiles; ++t) {
+                u32 st = t % stages, ph = (t / stages) & 1;
+                if (t >= stages) mbar_wait(&bars[stages + st], ph ^ 1);
+                unsigned char *dst = smem_raw + (size_t)st * stage_bytes;
+                // The last tile may hang over the end of F (columns >= n): copy only the valid columns.  The
+                // matching matrix columns are zero padding, so whatever the stale tail of the stage holds
+                // contributes 0 (exact integer arithmetic, no NaNs to worry about).
+                u64 col0 = (t_begin + t) * lay.tj;
+                u32 fcols = (u32)min((u64)lay.tj, lay.n - col0);
+                u32 fb = fcols * ring::D * 8;
+                mbar_arrive_expect_tx(&bars[st], tile_bytes + PT * fb);
+                tma_bulk_g2s(dst, a_src + (u64)t * lay.tile_elems(), tile_bytes, &bars[st]);
+#pragma unroll
+                for (int p = 0; p < PT; ++p) {
+                    const u64 *f_src = F + ((u64)(p0 + p) * f_stride + col0) * ring::D;
+                    tma_bulk_g2s(dst + tile_bytes + p * f_bytes, f_src, fb, &bars[st]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const u32 rgi = warp / lay.cg, cgi = warp - rgi * lay.cg;
+    const u32 il = rgi * 4 + (lane >> 3), s = lane & 7;
+    gl::Fq3Acc acc[PT];
+#pragma unroll
+    for (int p = 0; p < PT; ++p) acc[p].clear();
+
+    for (u32 t = 0; t < my_tiles; ++t) {
+        u32 st = t % stages, ph = (t / stages) & 1;
+        mbar_wait(&bars[st], ph);
+        const u64 *sa = reinterpret_cast<const u64 *>(smem_raw + (size_t)st * stage_bytes);
+        const u64 *sf = sa + lay.tile_elems();
+        for (u32 jj = cgi; jj < lay.tj; jj += lay.cg) {
+            const u64 *pa = sa + ((u64)(jj * 3) * lay.rb + il) * 8 + s;
+            u64 a0 = pa[0], a1 = pa[lay.rb * 8], a2 = pa[2 * lay.rb * 8];
+#pragma unroll
+            for (int p = 0; p < PT; ++p) {
+                const u64 *pf = sf + ((u64)p * lay.tj + jj) * ring::D + s * 3;
+                acc[p].mac(a0, a1, a2, pf[0], pf[1], pf[2]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[stages + st]);
+    }
+
+    // ===== epilogue: one reduction per output, canonical partial to the workspace =====
+    const u32 slot = blockIdx.x * lay.cg + cgi;
+    const u32 row = rbk * lay.rb + il;
+#pragma unroll
+    for (int p = 0; p < PT; ++p) {
+        u64 c0, c1, c2;
+        acc[p].finish(c0, c1, c2);
+        u64 *dst = ws + (((u64)slot * planes + (p0 + p)) * lay.kappa_pad + row) * ring::D + s * 3;
+        dst[0] = c0;
+        dst[1] = c1;
+        dst[2] = c2;
+    }
+}
+
+// cms[p][row][t] = sum over slots of the partials, mod q.  One block per (p, row); 240 threads = 10 x 24.
+__global__ void __launch_bounds__(256)
+mac_reduce_kernel(const u64 *__restrict__ ws, uint32_t nslots, uint32_t planes, uint32_t kappa, uint32_t kappa_pad,
+                  u64 *__restrict__ cms) {
+    __shared__ u64 part[10][ring::D];
+    const u32 p = blockIdx.x / kappa, row = blockIdx.x - p * kappa;
+    const u32 g = threadIdx.x / ring::D, t = threadIdx.x - g * ring::D;
+    if (g < 10) {
+        u64 lo = 0, hi = 0;
+        for (u32 sl = g; sl < nslots; sl += 10) {
+            u64 v = ws[(((u64)sl * planes + p) * kappa_pad + row) * ring::D + t];
+            lo += v;
+            hi += (lo < v);
+        }
+        part[g][t] = gl::reduce128(lo, hi);
+    }
+    __syncthreads();
+    if (threadIdx.x < ring::D) {
+        u64 acc = part[0][threadIdx.x];
+#pragma unroll
+        for (int k = 1; k < 10; ++k) acc = gl::add(acc, part[k][threadIdx.x]);
+        cms[((u64)p * kappa + row) * ring::D + threadIdx.x] = acc;
+    }
+}
+
+MacPlan plan_mac(const MatLayout &lay, uint32_t planes, int sm_count) {
+    MacPlan m{};
+    m.pt = (planes % 2 == 0) ? 2 : 1;
+    m.stages = MAX_STAGES;
+    size_t stage_bytes = lay.tile_elems() * 8 + (size_t)m.pt * lay.tj * ring::D * 8;
+    m.smem_bytes = m.stages * stage_bytes + 2 * m.stages * sizeof(u64);
+    // resident CTAs per SM by shared memory (227 KB usable, 1 KB reserved per CTA), capped by threads/registers
+    uint32_t occ = (uint32_t)((227 * 1024) / (m.smem_bytes + SM_RESERVED_SMEM));
+    uint32_t occ_cap = (m.pt == 1) ? 2 : 1;
+    if (occ > occ_cap) occ = occ_cap;
+    if (occ < 1) occ = 1;
+    uint32_t groups = planes / m.pt;
+    u64 want = (u64)sm_count * occ;
+    // plane groups and row blocks multiply the grid; keep the whole grid near one resident wave
+    u64 gx = want / ((u64)groups * lay.nrb);
+    if (gx < 1) gx = 1;
+    if (gx > lay.ntiles) gx = lay.ntiles;
+    m.grid_x = (uint32_t)gx;
+    m.nslots = m.grid_x * lay.cg;
+    m.ws_elems = (size_t)m.nslots * planes * lay.kappa_pad * ring::D;
+    return m;
+}
+
+void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *F, u64 f_stride, uint32_t planes, const MacPlan &plan,
+                u64 *workspace, u64 *cms, cudaStream_t stream) {
+    dim3 grid(plan.grid_x, lay.nrb, planes / plan.pt);
+    dim3 block((lay.rg * lay.cg + 1) * 32);
+    static bool attr_set[3] = {false, false, false};
+    if (plan.pt == 1) {
+        if (!attr_set[1]) {
+            cudaFuncSetAttribute(mac_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            attr_set[1] = true;
+        }
+        mac_kernel<1><<<grid, block, plan.smem_bytes, stream>>>(A_dev, lay, F, f_stride, planes, plan.stages, workspace);
+    } else {
+        if (!attr_set[2]) {
+            cudaFuncSetAttribute(mac_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            attr_set[2] = true;
+        }
+        mac_kernel<2><<<grid, block, plan.smem_bytes, stream>>>(A_dev, lay, F, f_stride, planes, plan.stages, workspace);
+    }
+    mac_reduce_kernel<<<planes * lay.kappa, 256, 0, stream>>>(workspace, plan.nslots, planes, lay.kappa, lay.kappa_pad, cms);
+}
+
+// cms[0] = cm - sum_{k>=1} 2^k cms[k]: Horner from the top plane, (acc + y_k) * 2.  decomposition.rs:189-197
+__global__ void __launch_bounds__(256)
+y0_kernel(const u64 *__restrict__ cm, u64 *__restrict__ cms, uint32_t K, uint32_t nwords) {
+    u32 i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= nwords) return;
+    u64 acc = 0;
+    for (uint32_t k = K - 1; k >= 1; --k) acc = gl::mul_pow2<1>(gl::add(acc, cms[(u64)k * nwords + i]));
+    cms[i] = gl::sub(cm[i], acc);
+}
+
+void launch_y0(const u64 *cm, u64 *cms, uint32_t K, uint32_t kappa, cudaStream_t stream) {
+    uint32_t nwords = kappa * ring::D;
+    y0_kernel<<<(nwords + 255) / 256, 256, 0, stream>>>(cm, cms, K, nwords);
+}
+
+}  // namespace lat
