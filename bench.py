@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- the Ajtai step-witness commit of Latticeum's zkVM on B200 (BASELINE.json configs[1]).
+
+A "step" is one pass of the hot path over one synthetic step witness at the zkVM's parameters
+(kappa = 32, w_len = 19 763, n = 98 815, B = 2^15, L = 5): Witness::from_w_ccs (iCRT -> base-2^15 gadget
+decomposition -> CRT) followed by Witness::commit (A * f), i.e. the reference's `commit()` call site
+zkvm/src/main.rs:348-367.  At N GPUs the witness is N times wider and column-sharded (one zkVM-sized column
+block per GPU, weak scaling) with one NCCL all-gather of the 6 KB partial commitments + a mod-q fold.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]                 our CUDA engine
+  python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  the CPU path (C restatement of the rayon path)
+
+Prints ONE JSON line (rank 0).  `value` = witness ring elements committed per second with inputs resident in HBM;
+`e2e` = the same through the host-buffer C ABI call with H2D/D2H copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+KAPPA, W_LEN, L_LIMBS, LOG2_B, K_PLANES = 32, 19763, 5, 15, 15
+N_COLS = W_LEN * L_LIMBS  # 98 815
+Q = 2**64 - 2**32 + 1
+ELEM_B = 192
+METRIC = "ajtai_commit_ring_elems_per_s"
+UNIT = "ring elems/s"
+
+
+# ---- synthetic inputs: independently random matrix, steady-state witness mix -----------------------------
+def uniform_fq(shape, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = rng.integers(0, 2**64, size=shape, dtype=np.uint64)
+    bad = out >= np.uint64(Q)
+    while bad.any():
+        out[bad] = rng.integers(0, 2**64, size=int(bad.sum()), dtype=np.uint64)
+        bad = out >= np.uint64(Q)
+    return out
+
+
+def matrix_row(rank, i):
+    return uniform_fq((N_COLS, 24), 1_000_003 * (rank + 1) + i)
+
+
+def steady_state_w(rank):
+    """~5.5 % scalar-embedded elements (all slots (v,0,0)), the rest dense uniform CRT-form elements."""
+    w = uniform_fq((W_LEN, 24), 77_000 + rank)
+    nsc = 1088
+    vals = uniform_fq((nsc,), 78_000 + rank)
+    w[:nsc] = 0
+    w[:nsc, 0::3] = vals[:, None]
+    return w
+
+
+# ---- clocks sampler (B200_PROFILING.md recipe) ----------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()  # exact PID we started
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for (_, l) in self.lines]
+        for l in rows:
+            p = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(p[0]))
+                mx = max(mx, float(p[1]))
+                for nme, v in zip(names, p[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy bandwidth)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture, if there is one."""
+    p = os.path.join(ROOT, "profiles", "mac_kernel_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ---- CPU arm: the C restatement of the reference's rayon path (oracle/), timed on the host cores ------------------------
+def cpu_step_inputs(sample_w):
+    A = np.empty((KAPPA, sample_w * L_LIMBS, 24), np.uint64)
+    for i in range(KAPPA):
+        A[i] = matrix_row(0, i)[: sample_w * L_LIMBS]
+    w = steady_state_w(0)[:sample_w]
+    return A, w
+
+
+def cpu_step(CO, A, w):
+    f_coeff, f = CO.witness_from_w_ccs(w, 1 << LOG2_B, L_LIMBS)
+    return CO.commit(A, f)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    from oracle import c_oracle as CO  # the CPU arm IS the oracle port (kind = "port": no Rust toolchain here)
+
+    cores = CO.num_threads()
+    # calibrate on a small sample, then bound every step so that the whole run ends within ~2 minutes
+    cal_w = 2000
+    A, w = cpu_step_inputs(cal_w)
+    t = time.perf_counter()
+    cpu_step(CO, A, w)
+    per_w = (time.perf_counter() - t) / cal_w
+    budget_s = 110.0
+    total_steps = args.steps + args.warmup
+    sample_w = int(min(W_LEN, max(500, budget_s / (total_steps * per_w))))
+    if sample_w != cal_w:
+        A, w = cpu_step_inputs(sample_w)
+    for _ in range(args.warmup):
+        cpu_step(CO, A, w)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(CO, A, w)
+    dt = time.perf_counter() - t0
+    ms = dt / args.steps * 1e3
+    value = sample_w * L_LIMBS * args.steps / dt
+    sample = (f"first {sample_w} of {W_LEN} w_ccs elements ({sample_w * L_LIMBS} of {N_COLS} columns), kappa={KAPPA}; "
+              "throughput is linear in columns")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "zkvm_step_witness_commit", "kappa": KAPPA, "w_len": W_LEN, "n": N_COLS, "d": 24,
+                   "B": 1 << LOG2_B, "L": L_LIMBS, "cpu_impl": "C restatement of the reference's rayon path (oracle/), OpenMP"},
+        "commitments_per_s": value / N_COLS,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- our arm -------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import latticeum_b200 as LB
+    from latticeum_b200 import _capi as capi
+    from latticeum_b200.device import DeviceScheme
+    from latticeum_b200.sharded import ShardedAjtaiScheme
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # -- build this rank's column block of the matrix and its block of the step witness ----------------------------------
+    scheme = LB.AjtaiCommitmentScheme(KAPPA, N_COLS, device=local_rank)
+    for i in range(KAPPA):
+        scheme.upload_rows(i, matrix_row(rank, i)[None])
+    eng = DeviceScheme(scheme)
+    sharded = ShardedAjtaiScheme(eng, world, rank)
+    w_host = steady_state_w(rank)
+    w_dev = eng.to_device(w_host)
+    partial = eng.new_commitment()
+
+    def step():
+        return sharded.witness_commit(w_dev, partial)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        cm_dev = step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    eng.set_profiling(True)
+    eng.mac_profile()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        cm_dev = step()
+    ev1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    mac_sum_ms, mac_launches = eng.mac_profile()
+    eng.set_profiling(False)
+    elapsed_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * N_COLS * args.steps / (elapsed_ms * 1e-3)
+
+    # -- e2e: the host-buffer C ABI call (pinned host memory), H2D of w_ccs and D2H of the commitment every step --------
+    e2e = None
+    if world == 1:
+        L = capi.lib()
+        hw, hcm = C.c_void_p(), C.c_void_p()
+        assert L.lat_host_alloc(C.byref(hw), W_LEN * ELEM_B) == 0 and L.lat_host_alloc(C.byref(hcm), KAPPA * ELEM_B) == 0
+        C.memmove(hw, w_host.ctypes.data, W_LEN * ELEM_B)
+        for _ in range(3):
+            st = L.lat_ajtai_witness_from_w_ccs(scheme._h, hw, W_LEN, None, None, hcm)
+            assert st == 0, capi.last_error()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            L.lat_ajtai_witness_from_w_ccs(scheme._h, hw, W_LEN, None, None, hcm)
+        t1 = time.perf_counter()
+        cm_e2e = np.ctypeslib.as_array(C.cast(hcm, C.POINTER(C.c_uint64)), shape=(KAPPA, 24)).copy()
+        e2e = {"value": N_COLS * args.steps / (t1 - t0), "unit": UNIT, "h2d_bytes_per_step": W_LEN * ELEM_B,
+               "d2h_bytes_per_step": KAPPA * ELEM_B + 4, "ms_per_step": (t1 - t0) / args.steps * 1e3,
+               "api": "lat_ajtai_witness_from_w_ccs(w_ccs_host_pinned) -> cm_host; witness stays device-resident"}
+        # the full drop-in (Witness with f and f_coeff materialised on the host, as the reference's struct holds them)
+        hf, hfc = C.c_void_p(), C.c_void_p()
+        L.lat_host_alloc(C.byref(hf), N_COLS * ELEM_B)
+        L.lat_host_alloc(C.byref(hfc), N_COLS * ELEM_B)
+        reps = max(3, min(args.steps, 20))
+        L.lat_ajtai_witness_from_w_ccs(scheme._h, hw, W_LEN, hfc, hf, hcm)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            L.lat_ajtai_witness_from_w_ccs(scheme._h, hw, W_LEN, hfc, hf, hcm)
+        t1 = time.perf_counter()
+        e2e["full_witness_to_host"] = {"value": N_COLS * reps / (t1 - t0), "ms_per_step": (t1 - t0) / reps * 1e3,
+                                       "d2h_bytes_per_step": 2 * N_COLS * ELEM_B + KAPPA * ELEM_B}
+        for p in (hw, hcm, hf, hfc):
+            L.lat_host_free(p)
+        eng.bind_stream()
+    else:
+        # N > 1: pinned host w_ccs -> device, sharded commit, commitment back to the host, every step
+        w_pin = torch.from_numpy(w_host.view(np.int64)).pin_memory()
+        cm_pin = torch.empty((KAPPA, 24), dtype=torch.int64).pin_memory()
+
+        def e2e_step():
+            w_dev.copy_(w_pin, non_blocking=True)
+            cm_pin.copy_(step(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * N_COLS * args.steps / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": W_LEN * ELEM_B, "d2h_bytes_per_step": KAPPA * ELEM_B,
+               "ms_per_step": float(dt.item()) / args.steps * 1e3,
+               "api": "per rank: pinned w_ccs -> ShardedAjtaiScheme.witness_commit -> pinned cm (bytes are per rank)"}
+    sampler.stop()
+    clocks = sampler.summary(t_wall0, t_wall1)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # -- roofline of the dominant kernel (mac_kernel): algorithmic bytes = 192 B of A per ring MAC x kappa*n ------------
+    peak, peak_src = measured_peaks()
+    alg_bytes = KAPPA * N_COLS * ELEM_B
+    mac_ms = mac_sum_ms / max(mac_launches, 1)
+    achieved = alg_bytes / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": ncu_traffic(), "kernel": "lat::mac_kernel<1>", "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel_ms": mac_ms, "kernel_share_of_step": mac_ms / ms_per_step if ms_per_step else None,
+                "launches_timed": int(mac_launches), "peak_source": peak_src}
+
+    # -- CPU baseline beside it (N = 1 only): the oracle port on the host cores, bounded sample ----------------------------
+    cpu_baseline, parity = None, None
+    if world == 1 and not args.no_cpu:
+        from oracle import c_oracle as CO  # checker / CPU arm only
+
+        A = np.empty((KAPPA, N_COLS, 24), np.uint64)
+        for i in range(KAPPA):
+            A[i] = matrix_row(0, i)
+        reps, t_cpu, cm_cpu = 0, 0.0, None
+        while reps < 3 or (t_cpu < 10.0 and reps < 40):
+            t0 = time.perf_counter()
+            cm_cpu = cpu_step(CO, A, w_host)
+            t_cpu += time.perf_counter() - t0
+            reps += 1
+        cpu_baseline = {"value": N_COLS * reps / t_cpu, "unit": UNIT, "cores": CO.num_threads(), "kind": "port",
+                        "sample": f"{reps} full steps (kappa={KAPPA}, n={N_COLS}), {t_cpu / reps * 1e3:.1f} ms each",
+                        "ms_per_step": t_cpu / reps * 1e3}
+        got = DeviceScheme.to_numpy(cm_dev)
+        parity = bool(np.array_equal(got, cm_cpu) and np.array_equal(cm_e2e, cm_cpu))
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic",
+        "config": {"workload": "zkvm_step_witness_commit", "kappa": KAPPA, "w_len": W_LEN, "n_per_gpu": N_COLS,
+                   "n_total": world * N_COLS, "d": 24, "B": 1 << LOG2_B, "L": L_LIMBS,
+                   "pipeline": "iCRT -> gadget_decompose(2^15,5) -> CRT -> A*f (Witness::from_w_ccs + commit)",
+                   "sharding": f"columns x{world}" + (", NCCL all-gather of 6 KB partials + mod-q fold" if world > 1 else ""),
+                   "l2": "inputs larger than L2 (607 MB matrix streamed every step)"},
+        "commitments_per_s": args.steps / (elapsed_ms * 1e-3),
+        "e2e": e2e, "gpu_launches": args.steps * (4 + (1 if world > 1 else 0)),
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_vs_cpu": parity,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

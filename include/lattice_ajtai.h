@@ -93,7 +93,8 @@ uint32_t lat_ajtai_kappa(const lat_ajtai *h);
 uint64_t lat_ajtai_width(const lat_ajtai *h);
 
 /* Use an existing CUDA stream (cudaStream_t) for all work of this handle, e.g. the caller's current
- * stream so that its own events bracket the kernels.  NULL restores the handle's own stream.            */
+ * stream so that its own events bracket the kernels.  NULL restores the handle's own stream; to name
+ * the legacy default stream pass cudaStreamLegacy ((void *)1).                                          */
 int lat_ajtai_set_stream(lat_ajtai *h, void *cuda_stream);
 /* Block until all work queued on the handle's stream has finished; returns the sticky asynchronous status
  * (LAT_E_DIGIT_OVERFLOW raised by a *_dev call, or LAT_OK) and clears it.                                 */
@@ -158,6 +159,23 @@ int lat_ring_icrt_dev(const uint64_t *ntt_dev, uint64_t count, uint64_t *coeff_d
  * RING/balanced_decomposition/mod.rs:163-175, coeff_form.rs:588-606.  out: count*L x 24.                   */
 int lat_ring_gadget_decompose(const uint64_t *in, uint64_t count, uint32_t log2_b, uint32_t L, uint64_t *out,
                               int repr, int device);
+
+/* ---- column-sharded commitments (multi-GPU) --------------------------------------------------------
+ * y = sum_j A_j f_j is a sum over columns: each GPU owns a contiguous column block (its own lat_ajtai handle of
+ * width n_g, uploaded with row_stride = full width) and produces a full kappa x 24 partial commitment; the
+ * partials are exchanged (NCCL all-gather over NVLink, done by the host layer) and summed mod q here.
+ * parts: count x words u64 (words = batch * kappa * 24), out: words u64.  Addition is representation-agnostic.   */
+int lat_commitment_sum_dev(const uint64_t *parts_dev, uint32_t count, uint64_t words, uint64_t *out_dev,
+                           void *cuda_stream);
+int lat_commitment_sum(const uint64_t *parts, uint32_t count, uint64_t words, uint64_t *out, int device);
+
+/* ---- diagnostics: CUDA-event timing of the dominant kernel (bench.py's roofline leg) ---------------------------
+ * While enabled, every mac_kernel launch (the matrix-vector kernel alone, not its tiny reduce) is bracketed by a
+ * pair of events on the handle's stream, taken from a pool so that nothing synchronises inside a timed loop.
+ * lat_ajtai_mac_profile waits for outstanding brackets and returns the summed duration and the launch count
+ * since profiling was enabled (or since the last call), then resets both.                                     */
+int lat_ajtai_set_profiling(lat_ajtai *h, int enabled);
+int lat_ajtai_mac_profile(lat_ajtai *h, double *sum_ms, uint64_t *launches);
 
 /* ---- pinned host memory for callers that want the fast copy path (optional) -------------------------------- */
 int lat_host_alloc(void **ptr, size_t bytes);

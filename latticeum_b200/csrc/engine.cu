@@ -82,9 +82,11 @@ struct lat_ajtai {
     DevBuf stage;        // upload staging (one row at a time)
     DevBuf in;           // host-call input staging (w_ccs / f / f_coeff)
     DevBuf f16;          // resident decomposed witness, int16 digits, n x 24
-    DevBuf f;            // CRT-form witness, n x 24 u64
+    DevBuf f;            // CRT-form witness, n x 24 u64 (only when a caller wants it on the host)
+    DevBuf fx;           // CRT-form witness(es) in the MAC kernel's extended layout, count x n x 48 u64
     DevBuf fcoeff64;     // f_coeff as u64 for host output
-    DevBuf planes;       // K x n x 24 CRT-form planes
+    DevBuf planes;       // K x n x 24 CRT-form planes (only when a caller wants them)
+    DevBuf planes_fx;    // K x n x 48 CRT-form planes, extended layout (MAC input)
     DevBuf planes_coeff; // K x n x 24 coefficient-form planes (host output only)
     DevBuf cms;          // up to max(K, batch) x kappa x 24
     DevBuf cm_in;        // kappa x 24
@@ -92,6 +94,25 @@ struct lat_ajtai {
     DevBuf flag;         // int
     int *h_flag = nullptr;  // pinned
     bool has_resident = false;
+    // profiling: pool of event pairs around mac_kernel launches, drained lazily
+    static constexpr int EV_POOL = 256;
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev0, ev1;
+    std::vector<uint8_t> ev_pending;
+    int ev_next = 0;
+    double prof_sum_ms = 0.0;
+    uint64_t prof_count = 0;
+
+    int drain_slot(int i) {
+        if (!ev_pending[i]) return LAT_OK;
+        float ms = 0.f;
+        CK(cudaEventSynchronize(ev1[i]));
+        CK(cudaEventElapsedTime(&ms, ev0[i], ev1[i]));
+        prof_sum_ms += ms;
+        prof_count++;
+        ev_pending[i] = 0;
+        return LAT_OK;
+    }
 
     int bind() {
         CK(cudaSetDevice(device));
@@ -107,14 +128,32 @@ struct lat_ajtai {
         return fail(LAT_E_WRONG_WITNESS_LENGTH, "Wrong length of the witness: " + std::to_string(got) +
                                                     ", expected: " + std::to_string(n));
     }
-    // mac + reduce into cms_dev for `count` witnesses laid out count x stride x 24
-    int mac(const u64 *F, u64 stride, uint32_t count, u64 *cms_dev) {
+    // mac + reduce into cms_dev for `count` witnesses in the extended layout, count x stride x 48
+    int mac_fx(const u64 *Fx, u64 stride, uint32_t count, u64 *cms_dev) {
         lat::MacPlan plan = lat::plan_mac(lay, count, sm_count);
         int st = ws.ensure(plan.ws_elems * sizeof(u64));
         if (st) return st;
-        lat::launch_mac(A.as<u64>(), lay, F, stride, count, plan, ws.as<u64>(), cms_dev, stream);
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (profiling) {
+            int i = ev_next;
+            ev_next = (ev_next + 1) % EV_POOL;
+            if ((st = drain_slot(i))) return st;  // only blocks if the pool wrapped onto unfinished work
+            e0 = ev0[i];
+            e1 = ev1[i];
+            ev_pending[i] = 1;
+        }
+        lat::launch_mac(A.as<u64>(), lay, Fx, stride, count, plan, ws.as<u64>(), cms_dev, stream, e0, e1);
         CK(cudaGetLastError());
         return LAT_OK;
+    }
+    // same for caller-supplied plain CRT-form witnesses (count x stride x 24): extend first
+    int mac(const u64 *F, u64 stride, uint32_t count, u64 *cms_dev) {
+        int st = fx.ensure((size_t)count * n * lat::FX_WORDS * sizeof(u64));
+        if (st) return st;
+        for (uint32_t p = 0; p < count; ++p)
+            lat::launch_fext(F + (size_t)p * stride * LAT_RING_DEGREE, n, fx.as<u64>() + (size_t)p * n * lat::FX_WORDS, stream);
+        CK(cudaGetLastError());
+        return mac_fx(fx.as<u64>(), n, count, cms_dev);
     }
     int clear_flag() {
         CK(cudaMemsetAsync(flag.p, 0, sizeof(int), stream));
@@ -185,7 +224,7 @@ int lat_ajtai_create(lat_ajtai **out, uint32_t kappa, uint64_t n, uint32_t log2_
         if ((st = h->flag.ensure(sizeof(int)))) break;
         if ((e = cudaMemsetAsync(h->flag.p, 0, sizeof(int), h->stream)) != cudaSuccess) break;
         if ((st = h->f16.ensure(n * LAT_RING_DEGREE * sizeof(int16_t)))) break;
-        if ((st = h->f.ensure(n * ELEM_BYTES))) break;
+        if ((st = h->fx.ensure(n * lat::FX_WORDS * sizeof(u64)))) break;
         if ((st = h->cms.ensure((size_t)K * kappa * ELEM_BYTES))) break;
         if ((st = h->cm_in.ensure((size_t)kappa * ELEM_BYTES))) break;
         if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) break;
@@ -203,10 +242,12 @@ void lat_ajtai_destroy(lat_ajtai *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
-    DevBuf *bufs[] = {&h->A, &h->stage, &h->in, &h->f16, &h->f, &h->fcoeff64, &h->planes, &h->planes_coeff,
-                      &h->cms, &h->cm_in, &h->ws, &h->flag};
+    DevBuf *bufs[] = {&h->A, &h->stage, &h->in, &h->f16, &h->f, &h->fx, &h->fcoeff64, &h->planes, &h->planes_fx,
+                      &h->planes_coeff, &h->cms, &h->cm_in, &h->ws, &h->flag};
     for (DevBuf *b : bufs) b->release();
     if (h->h_flag) cudaFreeHost(h->h_flag);
+    for (cudaEvent_t e : h->ev0) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev1) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -308,10 +349,9 @@ int lat_ajtai_commit_coeff(lat_ajtai *h, const uint64_t *f_coeff, uint64_t f_len
     size_t in_bytes = f_len * ELEM_BYTES;
     if ((st = h->in.ensure(in_bytes))) return st;
     CK(cudaMemcpyAsync(h->in.p, f_coeff, in_bytes, cudaMemcpyHostToDevice, h->stream));
-    lat::launch_crt(h->in.as<u64>(), h->f.as<u64>(), f_len, h->stream);
+    lat::launch_crt(h->in.as<u64>(), h->in.as<u64>(), f_len, h->stream);  // in place
     CK(cudaGetLastError());
-    h->has_resident = false;
-    if ((st = h->mac(h->f.as<u64>(), f_len, 1, h->cms.as<u64>()))) return st;
+    if ((st = h->mac(h->in.as<u64>(), f_len, 1, h->cms.as<u64>()))) return st;
     CK(cudaMemcpyAsync(cm, h->cms.p, (size_t)h->kappa * ELEM_BYTES, cudaMemcpyDeviceToHost, h->stream));
     return h->finish();
 }
@@ -322,11 +362,11 @@ static int witness_core(lat_ajtai *h, const u64 *w_dev, u64 w_len, bool in_coeff
     lat::launch_icrt_decompose(w_dev, w_len, (int)h->log2_B, (int)h->L, h->mont, in_coeff, h->f16.as<int16_t>(),
                                f_coeff_dev, h->flag.as<int>(), h->stream);
     CK(cudaGetLastError());
-    u64 *f_target = f_dev ? f_dev : h->f.as<u64>();
-    lat::launch_crt_small(h->f16.as<int16_t>(), h->n, h->mont, f_target, h->stream);
+    // the CRT kernel writes the extended layout for the MAC directly; the plain layout only if the caller wants f
+    lat::launch_crt_small(h->f16.as<int16_t>(), h->n, h->mont, f_dev, cm_dev ? h->fx.as<u64>() : nullptr, h->stream);
     CK(cudaGetLastError());
     h->has_resident = true;
-    if (cm_dev) return h->mac(f_target, h->n, 1, cm_dev);
+    if (cm_dev) return h->mac_fx(h->fx.as<u64>(), h->n, 1, cm_dev);
     return LAT_OK;
 }
 
@@ -350,9 +390,10 @@ static int witness_host(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool in
     size_t in_bytes = w_len * ELEM_BYTES, n_bytes = h->n * ELEM_BYTES;
     if ((st = h->in.ensure(in_bytes))) return st;
     if (f_coeff && (st = h->fcoeff64.ensure(n_bytes))) return st;
+    if (f && (st = h->f.ensure(n_bytes))) return st;
     CK(cudaMemcpyAsync(h->in.p, w, in_bytes, cudaMemcpyHostToDevice, h->stream));
-    st = witness_core(h, h->in.as<u64>(), w_len, in_coeff, f_coeff ? h->fcoeff64.as<u64>() : nullptr, nullptr,
-                      cm ? h->cms.as<u64>() : nullptr);
+    st = witness_core(h, h->in.as<u64>(), w_len, in_coeff, f_coeff ? h->fcoeff64.as<u64>() : nullptr,
+                      f ? h->f.as<u64>() : nullptr, cm ? h->cms.as<u64>() : nullptr);
     if (st) return st;
     if (cm) CK(cudaMemcpyAsync(cm, h->cms.p, (size_t)h->kappa * ELEM_BYTES, cudaMemcpyDeviceToHost, h->stream));
     if (f_coeff) CK(cudaMemcpyAsync(f_coeff, h->fcoeff64.p, n_bytes, cudaMemcpyDeviceToHost, h->stream));
@@ -377,18 +418,18 @@ int lat_ajtai_decompose_and_commit_coeff(lat_ajtai *h, const uint64_t *w_coeff, 
 // f16 already holds the coefficients; produce planes (to caller buffers or internal), K-1 commits and y_0.
 static int planes_core(lat_ajtai *h, const u64 *cm_dev, u64 *planes_coeff_dev, u64 *planes_f_dev, u64 *cms_dev) {
     int st;
-    u64 *pf = planes_f_dev;
-    if (!pf && cms_dev) {
-        if ((st = h->planes.ensure((size_t)h->K * h->n * ELEM_BYTES))) return st;
-        pf = h->planes.as<u64>();
+    u64 *pfx = nullptr;
+    if (cms_dev && h->K > 1) {
+        if ((st = h->planes_fx.ensure((size_t)h->K * h->n * lat::FX_WORDS * sizeof(u64)))) return st;
+        pfx = h->planes_fx.as<u64>();
     }
-    if (pf || planes_coeff_dev) {
-        lat::launch_planes(h->f16.as<int16_t>(), h->n, (int)h->K, h->mont, pf, h->n, planes_coeff_dev, h->stream);
+    if (pfx || planes_f_dev || planes_coeff_dev) {
+        lat::launch_planes(h->f16.as<int16_t>(), h->n, (int)h->K, h->mont, planes_f_dev, pfx, planes_coeff_dev, h->stream);
         CK(cudaGetLastError());
     }
     if (cms_dev) {
         if (h->K > 1) {
-            st = h->mac(pf + h->n * LAT_RING_DEGREE, h->n, h->K - 1, cms_dev + (size_t)h->kappa * LAT_RING_DEGREE);
+            st = h->mac_fx(pfx + h->n * lat::FX_WORDS, h->n, h->K - 1, cms_dev + (size_t)h->kappa * LAT_RING_DEGREE);
             if (st) return st;
         }
         lat::launch_y0(cm_dev, cms_dev, h->K, h->kappa, h->stream);
@@ -421,9 +462,9 @@ static int planes_host(lat_ajtai *h, const uint64_t *cm, uint64_t *planes_coeff,
         CK(cudaMemcpyAsync(h->cm_in.p, cm, cm_bytes, cudaMemcpyHostToDevice, h->stream));
     }
     if (planes_coeff && (st = h->planes_coeff.ensure(plane_bytes))) return st;
-    if ((planes_f || cms) && (st = h->planes.ensure(plane_bytes))) return st;
+    if (planes_f && (st = h->planes.ensure(plane_bytes))) return st;
     st = planes_core(h, h->cm_in.as<u64>(), planes_coeff ? h->planes_coeff.as<u64>() : nullptr,
-                     (planes_f || cms) ? h->planes.as<u64>() : nullptr, cms ? h->cms.as<u64>() : nullptr);
+                     planes_f ? h->planes.as<u64>() : nullptr, cms ? h->cms.as<u64>() : nullptr);
     if (st) return st;
     if (cms) CK(cudaMemcpyAsync(cms, h->cms.p, (size_t)h->K * cm_bytes, cudaMemcpyDeviceToHost, h->stream));
     if (planes_f) CK(cudaMemcpyAsync(planes_f, h->planes.p, plane_bytes, cudaMemcpyDeviceToHost, h->stream));
@@ -527,6 +568,63 @@ int lat_ring_gadget_decompose(const uint64_t *in, uint64_t count, uint32_t log2_
     if (st) return st;
     if (e != cudaSuccess) return fail_cuda(e, "lat_ring_gadget_decompose", __LINE__);
     if (h_flag) return fail(LAT_E_DIGIT_OVERFLOW, "a coefficient needs more than L digits");
+    return LAT_OK;
+}
+
+int lat_ajtai_set_profiling(lat_ajtai *h, int enabled) {
+    if (!h) return fail(LAT_E_INVALID_ARGUMENT, "NULL handle");
+    int st = h->bind();
+    if (st) return st;
+    if (enabled && h->ev0.empty()) {
+        h->ev0.resize(lat_ajtai::EV_POOL);
+        h->ev1.resize(lat_ajtai::EV_POOL);
+        h->ev_pending.assign(lat_ajtai::EV_POOL, 0);
+        for (int i = 0; i < lat_ajtai::EV_POOL; ++i) {
+            CK(cudaEventCreate(&h->ev0[i]));
+            CK(cudaEventCreate(&h->ev1[i]));
+        }
+    }
+    h->profiling = enabled != 0;
+    return LAT_OK;
+}
+int lat_ajtai_mac_profile(lat_ajtai *h, double *sum_ms, uint64_t *launches) {
+    if (!h || !sum_ms || !launches) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    int st = h->bind();
+    if (st) return st;
+    for (size_t i = 0; i < h->ev_pending.size(); ++i)
+        if ((st = h->drain_slot((int)i))) return st;
+    *sum_ms = h->prof_sum_ms;
+    *launches = h->prof_count;
+    h->prof_sum_ms = 0.0;
+    h->prof_count = 0;
+    return LAT_OK;
+}
+
+int lat_commitment_sum_dev(const uint64_t *parts_dev, uint32_t count, uint64_t words, uint64_t *out_dev,
+                           void *cuda_stream) {
+    if (words && (!parts_dev || !out_dev)) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    lat::launch_commitment_sum((const u64 *)parts_dev, count, words, (u64 *)out_dev, (cudaStream_t)cuda_stream);
+    CK(cudaGetLastError());
+    return LAT_OK;
+}
+int lat_commitment_sum(const uint64_t *parts, uint32_t count, uint64_t words, uint64_t *out, int device) {
+    if (words == 0) return LAT_OK;
+    if (!parts || !out) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    CK(cudaSetDevice(device));
+    DevBuf din, dout;
+    int st;
+    if ((st = din.ensure((size_t)count * words * 8)) || (st = dout.ensure(words * 8))) {
+        din.release(); dout.release();
+        return st;
+    }
+    cudaError_t e = cudaMemcpy(din.p, parts, (size_t)count * words * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        lat::launch_commitment_sum(din.as<u64>(), count, words, dout.as<u64>(), nullptr);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout.p, words * 8, cudaMemcpyDeviceToHost);
+    din.release(); dout.release();
+    if (e != cudaSuccess) return fail_cuda(e, "lat_commitment_sum", __LINE__);
     return LAT_OK;
 }
 

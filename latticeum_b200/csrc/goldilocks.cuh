@@ -84,23 +84,31 @@ __device__ __forceinline__ u64 from_small(int d) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Lazy multiply-accumulate: sum of up to 2^20 64x64-bit products kept as three 32-bit-column accumulators
-// (weights 2^0, 2^32, 2^64), each 64 bits + a 32-bit overflow word.  One product = 4 IMAD.WIDE.U32 with
-// carry-out, the carries absorbed pairwise by IADD3.X (checked in SASS).  Reduced once at the end.
+// Lazy multiply-accumulate: a sum of up to 2^31 64x64-bit products kept as three 32-bit-column accumulators
+// (weights 2^0, 2^32, 2^64), each a 64-bit register pair + a 32-bit overflow word.  One 32x32 partial product is
+// `mul.wide.u32 + add.cc.u64 + addc.u32`, which ptxas fuses into ONE IMAD.WIDE.U32 with carry-out predicate
+// plus half an IADD3.X (two carries are absorbed per IADD3.X) -- checked in SASS; keeping the accumulator a
+// 64-bit PTX register is what avoids per-iteration IMAD.MOV copies of loop-carried halves.
+// IMAD.WIDE.U32 issues at half the IMAD rate on sm_100a (measured 31.5 /clk/SM, tools/imad_peak.cu), so the
+// multiply count is what bounds the MAC: hence Karatsuba in Fq3 below (6 base products instead of 9).
 // ---------------------------------------------------------------------------------------------------------
 struct Col {
-    u32 lo, hi, ov;
+    u64 acc;
+    u32 ov;
 };
 __device__ __forceinline__ void col_mac(Col &c, u32 x, u32 y) {
-    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
-        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
-        "addc.u32 %2, %2, 0;"
-        : "+r"(c.lo), "+r"(c.hi), "+r"(c.ov)
+    asm("{\n\t"
+        ".reg .u64 p;\n\t"
+        "mul.wide.u32 p, %2, %3;\n\t"
+        "add.cc.u64 %0, %0, p;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "+l"(c.acc), "+r"(c.ov)
         : "r"(x), "r"(y));
 }
 struct WideAcc {
     Col c0, c1, c2;
-    __device__ __forceinline__ void clear() { c0 = c1 = c2 = Col{0u, 0u, 0u}; }
+    __device__ __forceinline__ void clear() { c0 = c1 = c2 = Col{0ull, 0u}; }
     __device__ __forceinline__ void mac(u64 a, u64 b) {
         u32 al = (u32)a, ah = (u32)(a >> 32), bl = (u32)b, bh = (u32)(b >> 32);
         col_mac(c0, al, bl);
@@ -110,43 +118,69 @@ struct WideAcc {
     }
     // value = c0 + c1 * 2^32 + c2 * 2^64 (each column < 2^96)  ->  canonical
     __device__ __forceinline__ u64 reduce() const {
-        // words w0..w5 of the 192-bit sum
         u64 t;
-        u32 w0 = c0.lo;
-        t = (u64)c0.hi + c1.lo;
+        u32 w0 = (u32)c0.acc;
+        t = (c0.acc >> 32) + (u32)c1.acc;
         u32 w1 = (u32)t;
-        t = (t >> 32) + c0.ov + c1.hi + c2.lo;
+        t = (t >> 32) + c0.ov + (c1.acc >> 32) + (u32)c2.acc;
         u32 w2 = (u32)t;
-        t = (t >> 32) + c1.ov + c2.hi;
+        t = (t >> 32) + c1.ov + (c2.acc >> 32);
         u32 w3 = (u32)t;
         t = (t >> 32) + c2.ov;
-        u32 w4 = (u32)t;  // t < 2^33 only if a column overflowed 2^96, which n <= 2^20 excludes; w5 = 0
+        u32 w4 = (u32)t;  // no sixth word: every column is < 2^96
         // 2^128 = -2^32 :  x = (w0 + w1 2^32 + w2 2^64 + w3 2^96) - w4 * 2^32
         u64 lo = ((u64)w1 << 32) | w0, hi = ((u64)w3 << 32) | w2;
         return sub(reduce128(lo, hi), (u64)w4 << 32);
     }
 };
 
-// Accumulators of one Fq3 output: sum_j a_j * b_j in Fq[u]/(u^3 - 2^40)
-//   c0 = S00 + NR * S12,  c1 = S01 + NR * S22,  c2 = S02
-//   S00 = sum a0 b0, S12 = sum a1 b2 + a2 b1, S01 = sum a0 b1 + a1 b0, S22 = sum a2 b2,
-//   S02 = sum a0 b2 + a1 b1 + a2 b0.
+// a + b as SOME 64-bit representative of (a + b) mod q, for canonical a, b: on carry add 2^64 = 2^32 - 1 (mod q);
+// a, b < q makes a second carry impossible.  Products tolerate non-canonical operands, so this is all the
+// Karatsuba pre-additions need.
+__device__ __forceinline__ u64 add_lazy(u64 a, u64 b) {
+    u64 s;
+    // carry chain instead of a 64-bit compare: c = carry(a + b); s = a + b + (c ? 2^32 - 1 : 0)
+    asm("{\n\t"
+        ".reg .u32 al, ah, bl, bh, c;\n\t"
+        "mov.b64 {al, ah}, %1;\n\t"
+        "mov.b64 {bl, bh}, %2;\n\t"
+        "add.cc.u32 al, al, bl;\n\t"
+        "addc.cc.u32 ah, ah, bh;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "neg.s32 c, c;\n\t"          // 0 or 0xFFFFFFFF
+        "add.cc.u32 al, al, c;\n\t"
+        "addc.u32 ah, ah, 0;\n\t"
+        "mov.b64 %0, {al, ah};\n\t"
+        "}"
+        : "=l"(s)
+        : "l"(a), "l"(b));
+    return s;
+}
+
+// Accumulators of one Fq3 output, Karatsuba form: for x = (x0,x1,x2), y = (y0,y1,y2) in Fq[u]/(u^3 - 2^40),
+// with x01 = x0+x1 etc. (any representative mod q):
+//   P0 = sum x0 y0, P1 = sum x1 y1, P2 = sum x2 y2, P01 = sum x01 y01, P02 = sum x02 y02, P12 = sum x12 y12
+//   c0 = P0 + NR (P12 - P1 - P2),  c1 = (P01 - P0 - P1) + NR P2,  c2 = (P02 - P0 - P2) + P1,  NR = 2^40.
 struct Fq3Acc {
-    WideAcc s00, s12, s01, s22, s02;
+    WideAcc p0, p1, p2, p01, p02, p12;
     __device__ __forceinline__ void clear() {
-        s00.clear(); s12.clear(); s01.clear(); s22.clear(); s02.clear();
+        p0.clear(); p1.clear(); p2.clear(); p01.clear(); p02.clear(); p12.clear();
     }
-    __device__ __forceinline__ void mac(u64 a0, u64 a1, u64 a2, u64 b0, u64 b1, u64 b2) {
-        s00.mac(a0, b0);
-        s12.mac(a1, b2); s12.mac(a2, b1);
-        s01.mac(a0, b1); s01.mac(a1, b0);
-        s22.mac(a2, b2);
-        s02.mac(a0, b2); s02.mac(a1, b1); s02.mac(a2, b0);
+    __device__ __forceinline__ void mac(u64 a0, u64 a1, u64 a2, u64 a01, u64 a02, u64 a12, u64 b0, u64 b1, u64 b2,
+                                        u64 b01, u64 b02, u64 b12) {
+        p0.mac(a0, b0);
+        p1.mac(a1, b1);
+        p2.mac(a2, b2);
+        p01.mac(a01, b01);
+        p02.mac(a02, b02);
+        p12.mac(a12, b12);
     }
     __device__ __forceinline__ void finish(u64 &c0, u64 &c1, u64 &c2) const {
-        c0 = add(s00.reduce(), mul_pow2<40>(s12.reduce()));
-        c1 = add(s01.reduce(), mul_pow2<40>(s22.reduce()));
-        c2 = s02.reduce();
+        u64 r0 = p0.reduce(), r1 = p1.reduce(), r2 = p2.reduce();
+        u64 r01 = p01.reduce(), r02 = p02.reduce(), r12 = p12.reduce();
+        c0 = add(r0, mul_pow2<40>(sub(sub(r12, r1), r2)));
+        c1 = add(sub(sub(r01, r0), r1), mul_pow2<40>(r2));
+        c2 = add(sub(sub(r02, r0), r2), r1);
     }
 };
 

@@ -21,13 +21,14 @@ void launch_icrt(const u64 *in, u64 *out, u64 count, cudaStream_t stream);
 void launch_icrt_decompose(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool in_coeff, int16_t *f16,
                            u64 *f_coeff, int *flag, cudaStream_t stream);
 
-// int16 digits -> CRT-form elements.  out has `count` elements.
-void launch_crt_small(const int16_t *f16, u64 count, bool mont, u64 *out, cudaStream_t stream);
+// int16 digits -> CRT-form elements: out (count x 24, may be nullptr) and/or fx (count x 48 extended, may be nullptr).
+void launch_crt_small(const int16_t *f16, u64 count, bool mont, u64 *out, u64 *fx, cudaStream_t stream);
 
 // int16 coefficients -> K base-2 digit planes: plane k of element j = sign * bit_k(|c|).
-//   planes_f     : K x plane_stride x 24 CRT form (plane_stride >= n, in elements), or nullptr
+//   planes_f     : K x n x 24 CRT form, or nullptr
+//   planes_fx    : K x n x 48 CRT form in the extended layout, or nullptr
 //   planes_coeff : K x n x 24 coefficient form, or nullptr
-void launch_planes(const int16_t *f16, u64 n, int K, bool mont, u64 *planes_f, u64 plane_stride, u64 *planes_coeff,
+void launch_planes(const int16_t *f16, u64 n, int K, bool mont, u64 *planes_f, u64 *planes_fx, u64 *planes_coeff,
                    cudaStream_t stream);
 
 // u64 coefficient-form elements (caller's representation) -> int16, flag |= 1 unless |c| < 2^bits for all c.
@@ -67,11 +68,21 @@ struct MacPlan {
 };
 MacPlan plan_mac(const MatLayout &lay, uint32_t planes, int sm_count);
 
-// cms[p][i][24] = sum_j A[i][j] * F[p][j]   for p < planes;  F: planes x f_stride x 24 (f_stride >= n; no padding needed).
-void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *F, u64 f_stride, uint32_t planes, const MacPlan &plan,
-                u64 *workspace, u64 *cms, cudaStream_t stream);
+// Extended witness layout consumed by the MAC kernel: per element 8 slots x 6 u64 = (f0, f1, f2, f0+f1, f0+f2, f1+f2).
+constexpr int FX_WORDS = 48;
+// f (count x 24, CRT form, any representation) -> fx (count x 48)
+void launch_fext(const u64 *f, u64 count, u64 *fx, cudaStream_t stream);
+
+// cms[p][i][24] = sum_j A[i][j] * F[p][j]   for p < planes;  Fx: planes x f_stride x 48 in the extended layout
+// (f_stride >= n in elements; no padding needed).
+void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes, const MacPlan &plan,
+                u64 *workspace, u64 *cms, cudaStream_t stream, cudaEvent_t ev_begin = nullptr,
+                cudaEvent_t ev_end = nullptr);
 
 // cms[0] = cm - sum_{k=1..K-1} 2^k cms[k]      (LF/nifs/decomposition.rs:189-197)
 void launch_y0(const u64 *cm, u64 *cms, uint32_t K, uint32_t kappa, cudaStream_t stream);
+
+// out[i] = sum_{p < count} parts[p * words + i] mod q
+void launch_commitment_sum(const u64 *parts, uint32_t count, u64 words, u64 *out, cudaStream_t stream);
 
 }  // namespace lat

@@ -8,10 +8,16 @@
 //    (canonical form), so that a tile is one contiguous run of bytes in HBM and a warp's shared-memory read of
 //    (jj, c) is 32 consecutive u64 (conflict-free).  Tiles are streamed with TMA bulk copies (cp.async.bulk ->
 //    UBLKCP) into a multi-stage shared-memory ring guarded by mbarriers; one producer warp, RG*CG consumer warps.
+//  * The witness side comes in the "extended" layout [element][slot][6] = (f0, f1, f2, f0+f1, f0+f2, f1+f2): the
+//    Karatsuba pre-additions of the witness are done once by whoever produces it (the CRT kernels, or fext_kernel
+//    for a caller-supplied witness), not once per matrix row.  The matrix-side pre-additions are 3 lazy adds per
+//    thread per column on the ALU pipe, which is otherwise idle.
 //  * Split-K over columns: every CTA owns a contiguous range of tiles and keeps, per thread, the UNREDUCED
-//    accumulators of one output (row, slot) for PT witnesses ("planes"): 5 sums x 3 columns x (64+32) bits
-//    (gl::Fq3Acc).  One 64x64 product = 4 IMAD.WIDE.U32 with carry-out + 2 IADD3.X; a single special-form
-//    reduction per output at the end.  No tensor cores: this is exact 64-bit modular integer work.
+//    accumulators of one output (row, slot) for PT witnesses ("planes"): 6 sums x 3 columns x (64+32) bits
+//    (gl::Fq3Acc).  One 64x64 product = 4 IMAD.WIDE.U32 with carry-out + 2 IADD3.X; 6 products per Fq3 MAC
+//    (Karatsuba) = 24 IMAD.WIDE.U32; a single special-form reduction per output at the end.  IMAD.WIDE.U32 runs at
+//    31.5 /clk/SM (measured), so this multiply count, not HBM, is what the batched (PT > 1) case is bound by.
+//    No tensor cores: this is exact 64-bit modular integer work.
 //  * Per-CTA partial results (canonical u64) go to a small workspace; mac_reduce_kernel sums them mod q.
 //  * A is canonical and F is in the caller's representation, so canonical(A) * repr(F) = repr(A*F): the
 //    commitment comes out in the caller's representation without any conversion (the map is Fq-linear).
@@ -24,7 +30,11 @@ namespace lat {
 using gl::u32;
 
 constexpr int SM_RESERVED_SMEM = 1024;
-constexpr int MAX_STAGES = 4;
+constexpr int FX = 48;  // u64 per element in the extended witness layout (8 slots x 6)
+
+// Compile-time geometry per row-group count RG (rows per block RB = 4 RG <= 32).
+__host__ __device__ constexpr int geo_cg(int rg) { return rg == 1 ? 8 : rg == 2 ? 4 : rg <= 4 ? 2 : 1; }
+__host__ __device__ constexpr int geo_tj(int rg) { return ((128 / (4 * rg)) / geo_cg(rg)) * geo_cg(rg); }
 
 MatLayout make_layout(uint32_t kappa, u64 n) {
     MatLayout l{};
@@ -40,17 +50,11 @@ MatLayout make_layout(uint32_t kappa, u64 n) {
     }
     l.nrb = l.kappa_pad / l.rb;
     l.rg = l.rb / 4;
-    l.cg = 8 / l.rg;
-    if (l.cg < 1) l.cg = 1;
-    // ~12 KB tiles: tj * rb * 192 B
-    uint32_t tj = 64 / l.rb;
-    if (tj < 2) tj = 2;
-    tj = (tj / l.cg) * l.cg;
-    if (tj < l.cg) tj = l.cg;
-    l.tj = tj;
-    l.ntiles = (n + tj - 1) / tj;
+    l.cg = geo_cg((int)l.rg);
+    l.tj = geo_tj((int)l.rg);  // ~24 KB tiles: tj * rb * 192 B
+    l.ntiles = (n + l.tj - 1) / l.tj;
     if (l.ntiles == 0) l.ntiles = 1;
-    l.n_pad = l.ntiles * tj;
+    l.n_pad = l.ntiles * l.tj;
     return l;
 }
 
@@ -121,22 +125,51 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                  : "memory");
 }
 
+// ---- witness -> extended layout (only for caller-supplied CRT-form witnesses; the CRT kernels emit it directly) -----
+__global__ void __launch_bounds__(256)
+fext_kernel(const u64 *__restrict__ f, u64 count_slots, u64 *__restrict__ fx) {
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;  // (element, slot)
+    if (i >= count_slots) return;
+    u64 f0 = f[i * 3], f1 = f[i * 3 + 1], f2 = f[i * 3 + 2];
+    f0 = gl::reduce128(f0, 0); f1 = gl::reduce128(f1, 0); f2 = gl::reduce128(f2, 0);
+    ulonglong2 *o = reinterpret_cast<ulonglong2 *>(fx + i * 6);
+    o[0] = make_ulonglong2(f0, f1);
+    o[1] = make_ulonglong2(f2, gl::add(f0, f1));
+    o[2] = make_ulonglong2(gl::add(f0, f2), gl::add(f1, f2));
+}
+void launch_fext(const u64 *f, u64 count, u64 *fx, cudaStream_t stream) {
+    u64 slots = count * ring::NSLOT;
+    if (!slots) return;
+    fext_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(f, slots, fx);
+}
+
 // ---- the MAC kernel --------------------------------------------------------------------------------------------
 // grid = (column chunks, row blocks, plane groups); block = (RG*CG consumer warps + 1 producer warp) * 32.
-// Shared memory: stages x { A tile | PT x tj x 24 u64 of F } + 2*stages mbarriers.
+// Shared memory: STAGES x { A tile | PT x TJ x 48 u64 of extended witness } + 2*STAGES mbarriers.
 // Partials layout: ws[((slot * planes + p) * kappa_pad + row) * 24 + s*3 + c], slot = blockIdx.x * CG + cg.
-template <int PT>
-__global__ void __launch_bounds__(288, (PT == 1) ? 2 : 1)
-mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__ F, u64 f_stride, uint32_t planes,
+template <int PT, int RG>
+struct MacGeo {
+    static constexpr int RB = 4 * RG, CG = geo_cg(RG), TJ = geo_tj(RG);
+    static constexpr int NCONS = RG * CG, THREADS = (NCONS + 1) * 32;
+    static constexpr u32 TILE_ELEMS = TJ * 3 * RB * 8;
+    static constexpr u32 TILE_BYTES = TILE_ELEMS * 8;
+    static constexpr u32 F_BYTES = TJ * FX * 8;  // per plane per tile
+    static constexpr u32 STAGE_BYTES = TILE_BYTES + PT * F_BYTES;
+    static constexpr int MIN_CTAS = PT == 1 ? 2 : 1;
+    // register budget for MIN_CTAS resident CTAs: 64K regs / (CTAs * warps * 32), rounded down to a multiple of 8
+    static constexpr int MAX_REGS_RAW = (65536 / (MIN_CTAS * THREADS)) / 8 * 8;
+    static constexpr int MAX_REGS = MAX_REGS_RAW > 232 ? 232 : MAX_REGS_RAW;
+};
+
+template <int PT, int RG>
+__global__ void __launch_bounds__(MacGeo<PT, RG>::THREADS) __maxnreg__((MacGeo<PT, RG>::MAX_REGS))
+mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__ Fx, u64 f_stride, uint32_t planes,
            uint32_t stages, u64 *__restrict__ ws) {
+    using G = MacGeo<PT, RG>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const u32 tile_bytes = (u32)(lay.tile_elems() * 8);
-    const u32 f_bytes = lay.tj * ring::D * 8;  // per plane per tile
-    const u32 stage_bytes = tile_bytes + PT * f_bytes;
-    u64 *bars = reinterpret_cast<u64 *>(smem_raw + (size_t)stages * stage_bytes);  // [full x stages][empty x stages]
+    u64 *bars = reinterpret_cast<u64 *>(smem_raw + (size_t)stages * G::STAGE_BYTES);  // [full x stages][empty x stages]
 
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const u32 n_cons = lay.rg * lay.cg;  // consumer warps; warp n_cons is the producer
     const u32 rbk = blockIdx.y;
     const u32 p0 = blockIdx.z * PT;
 
@@ -147,33 +180,33 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
 
     if (threadIdx.x == 0) {
         for (u32 st = 0; st < stages; ++st) {
-            mbar_init(&bars[st], 1);                // full: one arrive (producer) + tx bytes
-            mbar_init(&bars[stages + st], n_cons);  // empty: one arrive per consumer warp
+            mbar_init(&bars[st], 1);                   // full: one arrive (producer) + tx bytes
+            mbar_init(&bars[stages + st], G::NCONS);   // empty: one arrive per consumer warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == n_cons) {
+    if (warp == G::NCONS) {
         // ===== producer: one elected lane streams tiles with TMA bulk copies =====
         if (lane == 0) {
-            const u64 *a_src = A_dev + ((u64)rbk * lay.ntiles + t_begin) * lay.tile_elems();
+            const u64 *a_src = A_dev + ((u64)rbk * lay.ntiles + t_begin) * G::TILE_ELEMS;
             for (u32 t = 0; t < my_tiles; ++t) {
                 u32 st = t % stages, ph = (t / stages) & 1;
                 if (t >= stages) mbar_wait(&bars[stages + st], ph ^ 1);
-                unsigned char *dst = smem_raw + (size_t)st * stage_bytes;
+                unsigned char *dst = smem_raw + (size_t)st * G::STAGE_BYTES;
                 // The last tile may hang over the end of F (columns >= n): copy only the valid columns.  The
                 // matching matrix columns are zero padding, so whatever the stale tail of the stage holds
                 // contributes 0 (exact integer arithmetic, no NaNs to worry about).
-                u64 col0 = (t_begin + t) * lay.tj;
-                u32 fcols = (u32)min((u64)lay.tj, lay.n - col0);
-                u32 fb = fcols * ring::D * 8;
-                mbar_arrive_expect_tx(&bars[st], tile_bytes + PT * fb);
-                tma_bulk_g2s(dst, a_src + (u64)t * lay.tile_elems(), tile_bytes, &bars[st]);
+                u64 col0 = (t_begin + t) * G::TJ;
+                u32 fcols = (u32)min((u64)G::TJ, lay.n - col0);
+                u32 fb = fcols * FX * 8;
+                mbar_arrive_expect_tx(&bars[st], G::TILE_BYTES + PT * fb);
+                tma_bulk_g2s(dst, a_src + (u64)t * G::TILE_ELEMS, G::TILE_BYTES, &bars[st]);
 #pragma unroll
                 for (int p = 0; p < PT; ++p) {
-                    const u64 *f_src = F + ((u64)(p0 + p) * f_stride + col0) * ring::D;
-                    tma_bulk_g2s(dst + tile_bytes + p * f_bytes, f_src, fb, &bars[st]);
+                    const u64 *f_src = Fx + ((u64)(p0 + p) * f_stride + col0) * FX;
+                    tma_bulk_g2s(dst + G::TILE_BYTES + p * G::F_BYTES, f_src, fb, &bars[st]);
                 }
             }
         }
@@ -181,7 +214,7 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
     }
 
     // ===== consumers =====
-    const u32 rgi = warp / lay.cg, cgi = warp - rgi * lay.cg;
+    const u32 rgi = warp / G::CG, cgi = warp % G::CG;
     const u32 il = rgi * 4 + (lane >> 3), s = lane & 7;
     gl::Fq3Acc acc[PT];
 #pragma unroll
@@ -190,15 +223,20 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
     for (u32 t = 0; t < my_tiles; ++t) {
         u32 st = t % stages, ph = (t / stages) & 1;
         mbar_wait(&bars[st], ph);
-        const u64 *sa = reinterpret_cast<const u64 *>(smem_raw + (size_t)st * stage_bytes);
-        const u64 *sf = sa + lay.tile_elems();
-        for (u32 jj = cgi; jj < lay.tj; jj += lay.cg) {
-            const u64 *pa = sa + ((u64)(jj * 3) * lay.rb + il) * 8 + s;
-            u64 a0 = pa[0], a1 = pa[lay.rb * 8], a2 = pa[2 * lay.rb * 8];
+        const u64 *sa = reinterpret_cast<const u64 *>(smem_raw + (size_t)st * G::STAGE_BYTES) + il * 8 + s;
+        const ulonglong2 *sf =
+            reinterpret_cast<const ulonglong2 *>(smem_raw + (size_t)st * G::STAGE_BYTES + G::TILE_BYTES) + s * 3;
+#pragma unroll
+        for (int q = 0; q < G::TJ / G::CG; ++q) {
+            const u32 jj = cgi + q * G::CG;
+            const u64 *pa = sa + jj * (3 * G::RB * 8);
+            u64 a0 = pa[0], a1 = pa[G::RB * 8], a2 = pa[2 * G::RB * 8];
+            u64 a01 = gl::add_lazy(a0, a1), a02 = gl::add_lazy(a0, a2), a12 = gl::add_lazy(a1, a2);
 #pragma unroll
             for (int p = 0; p < PT; ++p) {
-                const u64 *pf = sf + ((u64)p * lay.tj + jj) * ring::D + s * 3;
-                acc[p].mac(a0, a1, a2, pf[0], pf[1], pf[2]);
+                const ulonglong2 *pf = sf + (p * G::TJ + jj) * (FX / 2);
+                ulonglong2 x = pf[0], y = pf[1], z = pf[2];
+                acc[p].mac(a0, a1, a2, a01, a02, a12, x.x, x.y, y.x, y.y, z.x, z.y);
             }
         }
         __syncwarp();
@@ -206,8 +244,8 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
     }
 
     // ===== epilogue: one reduction per output, canonical partial to the workspace =====
-    const u32 slot = blockIdx.x * lay.cg + cgi;
-    const u32 row = rbk * lay.rb + il;
+    const u32 slot = blockIdx.x * G::CG + cgi;
+    const u32 row = rbk * G::RB + il;
 #pragma unroll
     for (int p = 0; p < PT; ++p) {
         u64 c0, c1, c2;
@@ -244,19 +282,28 @@ mac_reduce_kernel(const u64 *__restrict__ ws, uint32_t nslots, uint32_t planes, 
     }
 }
 
+template <int PT, int RG>
+static size_t mac_stage_bytes() { return MacGeo<PT, RG>::STAGE_BYTES; }
+
+static size_t stage_bytes_for(uint32_t pt, uint32_t rg) {
+    size_t tile = (size_t)geo_tj((int)rg) * 3 * (4 * rg) * 64;
+    return tile + (size_t)pt * geo_tj((int)rg) * FX * 8;
+}
+
 MacPlan plan_mac(const MatLayout &lay, uint32_t planes, int sm_count) {
     MacPlan m{};
     m.pt = (planes % 2 == 0) ? 2 : 1;
-    m.stages = MAX_STAGES;
-    size_t stage_bytes = lay.tile_elems() * 8 + (size_t)m.pt * lay.tj * ring::D * 8;
-    m.smem_bytes = m.stages * stage_bytes + 2 * m.stages * sizeof(u64);
-    // resident CTAs per SM by shared memory (227 KB usable, 1 KB reserved per CTA), capped by threads/registers
-    uint32_t occ = (uint32_t)((227 * 1024) / (m.smem_bytes + SM_RESERVED_SMEM));
+    size_t stage_bytes = stage_bytes_for(m.pt, lay.rg);
     uint32_t occ_cap = (m.pt == 1) ? 2 : 1;
-    if (occ > occ_cap) occ = occ_cap;
-    if (occ < 1) occ = 1;
+    // as many stages as fit next to occ_cap resident CTAs (227 KB usable, 1 KB reserved per CTA), at most 6
+    size_t per_cta = (227 * 1024) / occ_cap - SM_RESERVED_SMEM - 2 * 8 * sizeof(u64);
+    uint32_t stages = (uint32_t)(per_cta / stage_bytes);
+    if (stages > 6) stages = 6;
+    if (stages < 2) stages = 2;
+    m.stages = stages;
+    m.smem_bytes = m.stages * stage_bytes + 2 * m.stages * sizeof(u64);
     uint32_t groups = planes / m.pt;
-    u64 want = (u64)sm_count * occ;
+    u64 want = (u64)sm_count * occ_cap;
     // plane groups and row blocks multiply the grid; keep the whole grid near one resident wave
     u64 gx = want / ((u64)groups * lay.nrb);
     if (gx < 1) gx = 1;
@@ -267,24 +314,40 @@ MacPlan plan_mac(const MatLayout &lay, uint32_t planes, int sm_count) {
     return m;
 }
 
-void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *F, u64 f_stride, uint32_t planes, const MacPlan &plan,
-                u64 *workspace, u64 *cms, cudaStream_t stream) {
-    dim3 grid(plan.grid_x, lay.nrb, planes / plan.pt);
-    dim3 block((lay.rg * lay.cg + 1) * 32);
-    static bool attr_set[3] = {false, false, false};
-    if (plan.pt == 1) {
-        if (!attr_set[1]) {
-            cudaFuncSetAttribute(mac_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            attr_set[1] = true;
-        }
-        mac_kernel<1><<<grid, block, plan.smem_bytes, stream>>>(A_dev, lay, F, f_stride, planes, plan.stages, workspace);
-    } else {
-        if (!attr_set[2]) {
-            cudaFuncSetAttribute(mac_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            attr_set[2] = true;
-        }
-        mac_kernel<2><<<grid, block, plan.smem_bytes, stream>>>(A_dev, lay, F, f_stride, planes, plan.stages, workspace);
+template <int PT, int RG>
+static void launch_mac_t(dim3 grid, const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes,
+                         const MacPlan &plan, u64 *workspace, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(mac_kernel<PT, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_set = true;
     }
+    mac_kernel<PT, RG><<<grid, MacGeo<PT, RG>::THREADS, plan.smem_bytes, stream>>>(A_dev, lay, Fx, f_stride, planes,
+                                                                                    plan.stages, workspace);
+}
+
+template <int PT>
+static void launch_mac_pt(dim3 grid, const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes,
+                          const MacPlan &plan, u64 *workspace, cudaStream_t stream) {
+    switch (lay.rg) {
+        case 1: launch_mac_t<PT, 1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream); break;
+        case 2: launch_mac_t<PT, 2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream); break;
+        case 3: launch_mac_t<PT, 3>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream); break;
+        case 4: launch_mac_t<PT, 4>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream); break;
+        case 5: launch_mac_t<PT, 5>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream); break;
+        case 6: launch_mac_t<PT, 6>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream); break;
+        case 7: launch_mac_t<PT, 7>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream); break;
+        default: launch_mac_t<PT, 8>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream); break;
+    }
+}
+
+void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes, const MacPlan &plan,
+                u64 *workspace, u64 *cms, cudaStream_t stream, cudaEvent_t ev_begin, cudaEvent_t ev_end) {
+    dim3 grid(plan.grid_x, lay.nrb, planes / plan.pt);
+    if (ev_begin) cudaEventRecord(ev_begin, stream);
+    if (plan.pt == 1) launch_mac_pt<1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream);
+    else launch_mac_pt<2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream);
+    if (ev_end) cudaEventRecord(ev_end, stream);
     mac_reduce_kernel<<<planes * lay.kappa, 256, 0, stream>>>(workspace, plan.nslots, planes, lay.kappa, lay.kappa_pad, cms);
 }
 
@@ -301,6 +364,24 @@ y0_kernel(const u64 *__restrict__ cm, u64 *__restrict__ cms, uint32_t K, uint32_
 void launch_y0(const u64 *cm, u64 *cms, uint32_t K, uint32_t kappa, cudaStream_t stream) {
     uint32_t nwords = kappa * ring::D;
     y0_kernel<<<(nwords + 255) / 256, 256, 0, stream>>>(cm, cms, K, nwords);
+}
+
+// Sum of `count` partial commitments mod q (column-sharded multi-GPU exchange).
+__global__ void __launch_bounds__(256)
+commitment_sum_kernel(const u64 *__restrict__ parts, uint32_t count, u64 words, u64 *__restrict__ out) {
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i >= words) return;
+    u64 lo = 0, hi = 0;
+    for (uint32_t p = 0; p < count; ++p) {
+        u64 v = parts[(u64)p * words + i];
+        lo += v;
+        hi += (lo < v);
+    }
+    out[i] = gl::reduce128(lo, hi);
+}
+void launch_commitment_sum(const u64 *parts, uint32_t count, u64 words, u64 *out, cudaStream_t stream) {
+    if (!words) return;
+    commitment_sum_kernel<<<(unsigned)((words + 255) / 256), 256, 0, stream>>>(parts, count, words, out);
 }
 
 }  // namespace lat

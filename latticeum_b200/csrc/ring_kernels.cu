@@ -37,6 +37,45 @@ __device__ __forceinline__ void stage_out(u64 *__restrict__ g, u64 e0, u64 count
     u64 *dst = g + e0 * ring::D;
     for (u32 i = threadIdx.x; i < nwords; i += EPB) dst[i] = s[(i / ring::D) * PITCH + (i % ring::D)];
 }
+__device__ __forceinline__ void row_store(u64 *s, const u64 (&c)[ring::D]);
+// Extended witness layout for the MAC kernel (kernels.h FX_WORDS): per slot (f0, f1, f2, f0+f1, f0+f2, f1+f2).
+// Staged in two halves of 4 slots (24 words each) through the same padded tile.
+__device__ __forceinline__ void row_store_fx_half(u64 *s, const u64 (&c)[ring::D], int half) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int sl = half * 4 + q;
+        u64 f0 = c[3 * sl], f1 = c[3 * sl + 1], f2 = c[3 * sl + 2];
+        u64 *r = s + threadIdx.x * PITCH + q * 6;
+        r[0] = f0; r[1] = f1; r[2] = f2;
+        r[3] = gl::add(f0, f1); r[4] = gl::add(f0, f2); r[5] = gl::add(f1, f2);
+    }
+}
+__device__ __forceinline__ void stage_out_fx_half(u64 *__restrict__ fx, u64 e0, u64 count, const u64 *s, int half) {
+    u32 nelem = (u32)min((u64)EPB, count - e0);
+    u32 nwords = nelem * ring::D;
+    u64 *dst = fx + e0 * FX_WORDS + half * ring::D;
+    for (u32 i = threadIdx.x; i < nwords; i += EPB) dst[(i / ring::D) * FX_WORDS + (i % ring::D)] = s[(i / ring::D) * PITCH + (i % ring::D)];
+}
+// block-wide: write the CRT-form element held by each active thread to out (plain) and/or fx (extended)
+__device__ __forceinline__ void emit_element(u64 *s, const u64 (&c)[ring::D], bool active, u64 e0, u64 count,
+                                             u64 *__restrict__ out, u64 *__restrict__ fx) {
+    if (out) {
+        if (active) row_store(s, c);
+        __syncthreads();
+        stage_out(out, e0, count, s);
+        __syncthreads();
+    }
+    if (fx) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            if (active) row_store_fx_half(s, c, half);
+            __syncthreads();
+            stage_out_fx_half(fx, e0, count, s, half);
+            __syncthreads();
+        }
+    }
+}
+
 __device__ __forceinline__ void row_load(const u64 *s, u64 (&c)[ring::D]) {
 #pragma unroll
     for (int k = 0; k < ring::D; ++k) c[k] = s[threadIdx.x * PITCH + k];
@@ -161,34 +200,33 @@ __device__ __forceinline__ void load_i16x24(const int16_t *__restrict__ p, int (
 
 template <bool MONT>
 __global__ void __launch_bounds__(EPB)
-crt_small_kernel(const int16_t *__restrict__ f16, u64 count, u64 *__restrict__ out) {
+crt_small_kernel(const int16_t *__restrict__ f16, u64 count, u64 *__restrict__ out, u64 *__restrict__ fx) {
     __shared__ u64 s[EPB * PITCH];
     u64 e0 = (u64)blockIdx.x * EPB;
     u64 e = e0 + threadIdx.x;
-    if (e < count) {
+    bool active = e < count;
+    u64 c[ring::D];
+    if (active) {
         int d[ring::D];
         load_i16x24(f16 + e * ring::D, d);
-        u64 c[ring::D];
 #pragma unroll
         for (int k = 0; k < ring::D; ++k) c[k] = gl::from_small<MONT>(d[k]);
         ring::crt24(c);
-        row_store(s, c);
     }
-    __syncthreads();
-    stage_out(out, e0, count, s);
+    emit_element(s, c, active, e0, count, out, fx);
 }
 
-void launch_crt_small(const int16_t *f16, u64 count, bool mont, u64 *out, cudaStream_t stream) {
+void launch_crt_small(const int16_t *f16, u64 count, bool mont, u64 *out, u64 *fx, cudaStream_t stream) {
     if (!count) return;
     unsigned grid = (unsigned)((count + EPB - 1) / EPB);
-    if (mont) crt_small_kernel<true><<<grid, EPB, 0, stream>>>(f16, count, out);
-    else crt_small_kernel<false><<<grid, EPB, 0, stream>>>(f16, count, out);
+    if (mont) crt_small_kernel<true><<<grid, EPB, 0, stream>>>(f16, count, out, fx);
+    else crt_small_kernel<false><<<grid, EPB, 0, stream>>>(f16, count, out, fx);
 }
 
 // ---- int16 coefficients -> K sign*bit planes, each CRT'd ---------------------------------------------------
 template <bool MONT>
 __global__ void __launch_bounds__(EPB)
-planes_kernel(const int16_t *__restrict__ f16, u64 n, int K, u64 *__restrict__ planes_f, u64 plane_stride,
+planes_kernel(const int16_t *__restrict__ f16, u64 n, int K, u64 *__restrict__ planes_f, u64 *__restrict__ planes_fx,
               u64 *__restrict__ planes_coeff) {
     __shared__ u64 s[EPB * PITCH];
     u64 e0 = (u64)blockIdx.x * EPB;
@@ -205,31 +243,22 @@ planes_kernel(const int16_t *__restrict__ f16, u64 n, int K, u64 *__restrict__ p
                 int bit = (a >> k) & 1;
                 c[t] = gl::from_small<MONT>(d[t] < 0 ? -bit : bit);  // digit k base 2 = sign * bit_k(|c|)
             }
-            row_store(s, c);
         }
-        if (planes_coeff) {
-            __syncthreads();
-            stage_out(planes_coeff + (u64)k * n * ring::D, e0, n, s);
-            __syncthreads();
-        }
-        if (planes_f) {
-            if (active) {
-                ring::crt24(c);
-                row_store(s, c);
-            }
-            __syncthreads();
-            stage_out(planes_f + (u64)k * plane_stride * ring::D, e0, n, s);
-            __syncthreads();
+        if (planes_coeff) emit_element(s, c, active, e0, n, planes_coeff + (u64)k * n * ring::D, nullptr);
+        if (planes_f || planes_fx) {
+            if (active) ring::crt24(c);
+            emit_element(s, c, active, e0, n, planes_f ? planes_f + (u64)k * n * ring::D : nullptr,
+                         planes_fx ? planes_fx + (u64)k * n * FX_WORDS : nullptr);
         }
     }
 }
 
-void launch_planes(const int16_t *f16, u64 n, int K, bool mont, u64 *planes_f, u64 plane_stride, u64 *planes_coeff,
+void launch_planes(const int16_t *f16, u64 n, int K, bool mont, u64 *planes_f, u64 *planes_fx, u64 *planes_coeff,
                    cudaStream_t stream) {
     if (!n) return;
     unsigned grid = (unsigned)((n + EPB - 1) / EPB);
-    if (mont) planes_kernel<true><<<grid, EPB, 0, stream>>>(f16, n, K, planes_f, plane_stride, planes_coeff);
-    else planes_kernel<false><<<grid, EPB, 0, stream>>>(f16, n, K, planes_f, plane_stride, planes_coeff);
+    if (mont) planes_kernel<true><<<grid, EPB, 0, stream>>>(f16, n, K, planes_f, planes_fx, planes_coeff);
+    else planes_kernel<false><<<grid, EPB, 0, stream>>>(f16, n, K, planes_f, planes_fx, planes_coeff);
 }
 
 // ---- u64 coefficients -> int16 with range check ---------------------------------------------------------------
