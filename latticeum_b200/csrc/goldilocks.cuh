@@ -134,46 +134,60 @@ struct WideAcc {
     }
 };
 
-// a + b as SOME 64-bit representative of (a + b) mod q, for canonical a, b: on carry add 2^64 = 2^32 - 1 (mod q);
-// a, b < q makes a second carry impossible.  Products tolerate non-canonical operands, so this is all the
-// Karatsuba pre-additions need.
-__device__ __forceinline__ u64 add_lazy(u64 a, u64 b) {
-    u64 s;
-    // carry chain instead of a 64-bit compare: c = carry(a + b); s = a + b + (c ? 2^32 - 1 : 0)
+// Karatsuba pre-addition on the matrix side: the exact 65-bit sum a + b = s + c * 2^64 (c = carry).  The carry is NOT
+// folded back into s (that costs IMAD-pipe instructions, measured); instead mac65 below adds c * y * 2^64 straight
+// into the accumulator's weight-2^64 column with carry-chain adds, which ptxas must keep on the ALU pipe.
+__device__ __forceinline__ void add65(u64 a, u64 b, u64 &s, u32 &c) {
     asm("{\n\t"
-        ".reg .u32 al, ah, bl, bh, c;\n\t"
-        "mov.b64 {al, ah}, %1;\n\t"
-        "mov.b64 {bl, bh}, %2;\n\t"
+        ".reg .u32 al, ah, bl, bh;\n\t"
+        "mov.b64 {al, ah}, %2;\n\t"
+        "mov.b64 {bl, bh}, %3;\n\t"
         "add.cc.u32 al, al, bl;\n\t"
         "addc.cc.u32 ah, ah, bh;\n\t"
-        "addc.u32 c, 0, 0;\n\t"
-        "neg.s32 c, c;\n\t"          // 0 or 0xFFFFFFFF
-        "add.cc.u32 al, al, c;\n\t"
-        "addc.u32 ah, ah, 0;\n\t"
+        "addc.u32 %1, 0, 0;\n\t"
         "mov.b64 %0, {al, ah};\n\t"
         "}"
-        : "=l"(s)
+        : "=l"(s), "=r"(c)
         : "l"(a), "l"(b));
-    return s;
+}
+// acc += (s + c * 2^64) * y,  c in {0, 1}
+__device__ __forceinline__ void mac65(WideAcc &A, u64 s, u32 c, u64 y) {
+    A.mac(s, y);
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u64 ym;\n\t"
+        "setp.ne.u32 p, %2, 0;\n\t"
+        "selp.b64 ym, %3, 0, p;\n\t"
+        "add.cc.u64 %0, %0, ym;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "+l"(A.c2.acc), "+r"(A.c2.ov)
+        : "r"(c), "l"(y));
 }
 
 // Accumulators of one Fq3 output, Karatsuba form: for x = (x0,x1,x2), y = (y0,y1,y2) in Fq[u]/(u^3 - 2^40),
-// with x01 = x0+x1 etc. (any representative mod q):
+// with x01 = x0+x1 etc.:
 //   P0 = sum x0 y0, P1 = sum x1 y1, P2 = sum x2 y2, P01 = sum x01 y01, P02 = sum x02 y02, P12 = sum x12 y12
 //   c0 = P0 + NR (P12 - P1 - P2),  c1 = (P01 - P0 - P1) + NR P2,  c2 = (P02 - P0 - P2) + P1,  NR = 2^40.
+// The x side (matrix) is summed on the fly as exact 65-bit values; the y side (witness) arrives pre-summed mod q.
+// Column bounds: c2 gets at most 2 additions < 2^64 per MAC, so 2^31 MACs still fit its 96 bits.
 struct Fq3Acc {
     WideAcc p0, p1, p2, p01, p02, p12;
     __device__ __forceinline__ void clear() {
         p0.clear(); p1.clear(); p2.clear(); p01.clear(); p02.clear(); p12.clear();
     }
-    __device__ __forceinline__ void mac(u64 a0, u64 a1, u64 a2, u64 a01, u64 a02, u64 a12, u64 b0, u64 b1, u64 b2,
-                                        u64 b01, u64 b02, u64 b12) {
+    __device__ __forceinline__ void mac(u64 a0, u64 a1, u64 a2, u64 b0, u64 b1, u64 b2, u64 b01, u64 b02, u64 b12) {
+        u64 s01, s02, s12;
+        u32 k01, k02, k12;
+        add65(a0, a1, s01, k01);
+        add65(a0, a2, s02, k02);
+        add65(a1, a2, s12, k12);
         p0.mac(a0, b0);
         p1.mac(a1, b1);
         p2.mac(a2, b2);
-        p01.mac(a01, b01);
-        p02.mac(a02, b02);
-        p12.mac(a12, b12);
+        mac65(p01, s01, k01, b01);
+        mac65(p02, s02, k02, b02);
+        mac65(p12, s12, k12, b12);
     }
     __device__ __forceinline__ void finish(u64 &c0, u64 &c1, u64 &c2) const {
         u64 r0 = p0.reduce(), r1 = p1.reduce(), r2 = p2.reduce();

@@ -22,6 +22,7 @@
 //  * A is canonical and F is in the caller's representation, so canonical(A) * repr(F) = repr(A*F): the
 //    commitment comes out in the caller's representation without any conversion (the map is Fq-linear).
 #include <cstdio>
+#include <cstdlib>
 
 #include "kernels.h"
 #include "ring24.cuh"
@@ -118,6 +119,19 @@ __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
             : "memory");
     } while (!done);
 }
+__device__ __forceinline__ bool mbar_test(u64 *bar, u32 parity) {  // non-blocking
+    u32 done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst_smem)),
@@ -150,24 +164,25 @@ void launch_fext(const u64 *f, u64 count, u64 *fx, cudaStream_t stream) {
 template <int PT, int RG>
 struct MacGeo {
     static constexpr int RB = 4 * RG, CG = geo_cg(RG), TJ = geo_tj(RG);
-    static constexpr int NCONS = RG * CG, THREADS = (NCONS + 1) * 32;
+    // RG*CG warps, all consumers; lane 0 of warp 0 also issues the TMA copies.  (A dedicated 9th producer warp
+    // halves the occupancy: warp slots are handed out four at a time -- measured with the occupancy API.)
+    static constexpr int NCONS = RG * CG, THREADS = NCONS * 32;
     static constexpr u32 TILE_ELEMS = TJ * 3 * RB * 8;
     static constexpr u32 TILE_BYTES = TILE_ELEMS * 8;
     static constexpr u32 F_BYTES = TJ * FX * 8;  // per plane per tile
     static constexpr u32 STAGE_BYTES = TILE_BYTES + PT * F_BYTES;
     static constexpr int MIN_CTAS = PT == 1 ? 2 : 1;
-    // register budget for MIN_CTAS resident CTAs: 64K regs / (CTAs * warps * 32), rounded down to a multiple of 8
-    static constexpr int MAX_REGS_RAW = (65536 / (MIN_CTAS * THREADS)) / 8 * 8;
-    static constexpr int MAX_REGS = MAX_REGS_RAW > 232 ? 232 : MAX_REGS_RAW;
 };
 
 template <int PT, int RG>
-__global__ void __launch_bounds__(MacGeo<PT, RG>::THREADS) __maxnreg__((MacGeo<PT, RG>::MAX_REGS))
+__global__ void __launch_bounds__(MacGeo<PT, RG>::THREADS, MacGeo<PT, RG>::MIN_CTAS)
 mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__ Fx, u64 f_stride, uint32_t planes,
            uint32_t stages, u64 *__restrict__ ws) {
     using G = MacGeo<PT, RG>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    u64 *bars = reinterpret_cast<u64 *>(smem_raw + (size_t)stages * G::STAGE_BYTES);  // [full x stages][empty x stages]
+    // after the stages: [full mbarrier x stages][release counter x stages]
+    u64 *bars = reinterpret_cast<u64 *>(smem_raw + (size_t)stages * G::STAGE_BYTES);
+    u32 *released = reinterpret_cast<u32 *>(bars + stages);
 
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u32 rbk = blockIdx.y;
@@ -177,70 +192,81 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
     const u64 t_begin = lay.ntiles * blockIdx.x / gridDim.x;
     const u64 t_end = lay.ntiles * (blockIdx.x + 1) / gridDim.x;
     const u32 my_tiles = (u32)(t_end - t_begin);
+    const u64 *a_src = A_dev + ((u64)rbk * lay.ntiles + t_begin) * G::TILE_ELEMS;
+
+    // Stream tile `nt` into stage `st` with TMA bulk copies (one thread).  There is no producer role: the warp that
+    // is LAST to release a stage refills it at once (release counters below), so no warp ever waits for another
+    // except through the data itself, and `stages` tiles are in flight or being consumed at all times.
+    auto issue_tile = [&](u32 nt, u32 st) {
+        unsigned char *dst = smem_raw + (size_t)st * G::STAGE_BYTES;
+        // The last tile may hang over the end of F (columns >= n): copy only the valid columns.  The matching
+        // matrix columns are zero padding, so whatever the stale tail of the stage holds contributes 0
+        // (exact integer arithmetic, no NaNs to worry about).
+        const u64 col0 = (t_begin + nt) * G::TJ;
+        const u32 fcols = (u32)min((u64)G::TJ, lay.n - col0);
+        const u32 fb = fcols * FX * 8;
+        mbar_arrive_expect_tx(&bars[st], G::TILE_BYTES + PT * fb);
+        tma_bulk_g2s(dst, a_src + (u64)nt * G::TILE_ELEMS, G::TILE_BYTES, &bars[st]);
+#pragma unroll
+        for (int p = 0; p < PT; ++p) {
+            const u64 *f_src = Fx + ((u64)(p0 + p) * f_stride + col0) * FX;
+            tma_bulk_g2s(dst + G::TILE_BYTES + p * G::F_BYTES, f_src, fb, &bars[st]);
+        }
+    };
 
     if (threadIdx.x == 0) {
         for (u32 st = 0; st < stages; ++st) {
-            mbar_init(&bars[st], 1);                   // full: one arrive (producer) + tx bytes
-            mbar_init(&bars[stages + st], G::NCONS);   // empty: one arrive per consumer warp
+            mbar_init(&bars[st], 1);  // full: one arrive (whoever issues the copies) + tx bytes
+            released[st] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const u32 pre = min(stages, my_tiles);
+        for (u32 nt = 0; nt < pre; ++nt) issue_tile(nt, nt);
     }
     __syncthreads();
 
-    if (warp == G::NCONS) {
-        // ===== producer: one elected lane streams tiles with TMA bulk copies =====
-        if (lane == 0) {
-            const u64 *a_src = A_dev + ((u64)rbk * lay.ntiles + t_begin) * G::TILE_ELEMS;
-            for (u32 t = 0; t < my_tiles; ++t) {
-                u32 st = t % stages, ph = (t / stages) & 1;
-                if (t >= stages) mbar_wait(&bars[stages + st], ph ^ 1);
-                unsigned char *dst = smem_raw + (size_t)st * G::STAGE_BYTES;
-                // The last tile may hang over the end of F (columns >= n): copy only the valid columns.  The
-                // matching matrix columns are zero padding, so whatever the stale tail of the stage holds
-                // contributes 0 (exact integer arithmetic, no NaNs to worry about).
-                u64 col0 = (t_begin + t) * G::TJ;
-                u32 fcols = (u32)min((u64)G::TJ, lay.n - col0);
-                u32 fb = fcols * FX * 8;
-                mbar_arrive_expect_tx(&bars[st], G::TILE_BYTES + PT * fb);
-                tma_bulk_g2s(dst, a_src + (u64)t * G::TILE_ELEMS, G::TILE_BYTES, &bars[st]);
-#pragma unroll
-                for (int p = 0; p < PT; ++p) {
-                    const u64 *f_src = Fx + ((u64)(p0 + p) * f_stride + col0) * FX;
-                    tma_bulk_g2s(dst + G::TILE_BYTES + p * G::F_BYTES, f_src, fb, &bars[st]);
-                }
-            }
-        }
-        return;
-    }
-
-    // ===== consumers =====
     const u32 rgi = warp / G::CG, cgi = warp % G::CG;
     const u32 il = rgi * 4 + (lane >> 3), s = lane & 7;
     gl::Fq3Acc acc[PT];
 #pragma unroll
     for (int p = 0; p < PT; ++p) acc[p].clear();
 
+    u32 st = 0, ph = 0;  // stage and phase parity of tile t (no runtime division in the loop)
+    bool ready = false;  // result of the early, non-blocking poll of this tile's barrier
     for (u32 t = 0; t < my_tiles; ++t) {
-        u32 st = t % stages, ph = (t / stages) & 1;
-        mbar_wait(&bars[st], ph);
+        if (!ready) mbar_wait(&bars[st], ph);
         const u64 *sa = reinterpret_cast<const u64 *>(smem_raw + (size_t)st * G::STAGE_BYTES) + il * 8 + s;
         const ulonglong2 *sf =
             reinterpret_cast<const ulonglong2 *>(smem_raw + (size_t)st * G::STAGE_BYTES + G::TILE_BYTES) + s * 3;
+        // poll the NEXT tile's barrier now, so that its latency hides under this tile's arithmetic
+        u32 st_n = st + 1, ph_n = ph;
+        if (st_n == stages) {
+            st_n = 0;
+            ph_n ^= 1;
+        }
+        ready = (t + 1 < my_tiles) && mbar_test(&bars[st_n], ph_n);
 #pragma unroll
         for (int q = 0; q < G::TJ / G::CG; ++q) {
             const u32 jj = cgi + q * G::CG;
             const u64 *pa = sa + jj * (3 * G::RB * 8);
             u64 a0 = pa[0], a1 = pa[G::RB * 8], a2 = pa[2 * G::RB * 8];
-            u64 a01 = gl::add_lazy(a0, a1), a02 = gl::add_lazy(a0, a2), a12 = gl::add_lazy(a1, a2);
 #pragma unroll
             for (int p = 0; p < PT; ++p) {
                 const ulonglong2 *pf = sf + (p * G::TJ + jj) * (FX / 2);
                 ulonglong2 x = pf[0], y = pf[1], z = pf[2];
-                acc[p].mac(a0, a1, a2, a01, a02, a12, x.x, x.y, y.x, y.y, z.x, z.y);
+                acc[p].mac(a0, a1, a2, x.x, x.y, y.x, y.y, z.x, z.y);
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[stages + st]);
+        // release the stage; the last warp to do so refills it with tile t + stages
+        if (lane == 0) {
+            if (atomicAdd(&released[st], 1u) == G::NCONS - 1) {
+                released[st] = 0;
+                if (t + stages < my_tiles) issue_tile(t + stages, st);
+            }
+        }
+        st = st_n;
+        ph = ph_n;
     }
 
     // ===== epilogue: one reduction per output, canonical partial to the workspace =====
@@ -296,10 +322,12 @@ MacPlan plan_mac(const MatLayout &lay, uint32_t planes, int sm_count) {
     size_t stage_bytes = stage_bytes_for(m.pt, lay.rg);
     uint32_t occ_cap = (m.pt == 1) ? 2 : 1;
     // as many stages as fit next to occ_cap resident CTAs (227 KB usable, 1 KB reserved per CTA), at most 6
-    size_t per_cta = (227 * 1024) / occ_cap - SM_RESERVED_SMEM - 2 * 8 * sizeof(u64);
+    size_t per_cta = (227 * 1024) / occ_cap - SM_RESERVED_SMEM - 2 * 8 * sizeof(u64);  // 16 B of sync state per stage
     uint32_t stages = (uint32_t)(per_cta / stage_bytes);
     if (stages > 6) stages = 6;
     if (stages < 2) stages = 2;
+    if (const char *e = getenv("LAT_MAC_STAGES")) stages = (uint32_t)atoi(e);  // tuning hooks (tools/tune_mac.py)
+    if (const char *e = getenv("LAT_MAC_OCC")) occ_cap = (uint32_t)atoi(e);
     m.stages = stages;
     m.smem_bytes = m.stages * stage_bytes + 2 * m.stages * sizeof(u64);
     uint32_t groups = planes / m.pt;
@@ -307,6 +335,7 @@ MacPlan plan_mac(const MatLayout &lay, uint32_t planes, int sm_count) {
     // plane groups and row blocks multiply the grid; keep the whole grid near one resident wave
     u64 gx = want / ((u64)groups * lay.nrb);
     if (gx < 1) gx = 1;
+    if (const char *e = getenv("LAT_MAC_GRIDX")) gx = (u64)atoll(e);
     if (gx > lay.ntiles) gx = lay.ntiles;
     m.grid_x = (uint32_t)gx;
     m.nslots = m.grid_x * lay.cg;
@@ -319,8 +348,18 @@ static void launch_mac_t(dim3 grid, const u64 *A_dev, const MatLayout &lay, cons
                          const MacPlan &plan, u64 *workspace, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(mac_kernel<PT, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(mac_kernel<PT, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) fprintf(stderr, "lattice_ajtai: cudaFuncSetAttribute(mac_kernel<%d,%d>): %s\n", PT, RG, cudaGetErrorString(e));
         attr_set = true;
+    }
+    if (getenv("LAT_DEBUG")) {
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, mac_kernel<PT, RG>);
+        int occ = -1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mac_kernel<PT, RG>, MacGeo<PT, RG>::THREADS, plan.smem_bytes);
+        fprintf(stderr, "mac_kernel<%d,%d>: grid=(%u,%u,%u) block=%d smem=%zu stages=%u regs=%d maxDyn=%d static=%zu occ=%d maxThreads=%d\n",
+                PT, RG, grid.x, grid.y, grid.z, MacGeo<PT, RG>::THREADS, plan.smem_bytes, plan.stages, fa.numRegs,
+                fa.maxDynamicSharedSizeBytes, fa.sharedSizeBytes, occ, fa.maxThreadsPerBlock);
     }
     mac_kernel<PT, RG><<<grid, MacGeo<PT, RG>::THREADS, plan.smem_bytes, stream>>>(A_dev, lay, Fx, f_stride, planes,
                                                                                     plan.stages, workspace);
