@@ -357,7 +357,7 @@ def run_ours(args):
                    "sharding": f"columns x{world}" + (", NCCL all-gather of 6 KB partials + mod-q fold" if world > 1 else ""),
                    "l2": "inputs larger than L2 (607 MB matrix streamed every step)"},
         "commitments_per_s": args.steps / (elapsed_ms * 1e-3),
-        "e2e": e2e, "gpu_launches": args.steps * (4 + (1 if world > 1 else 0)),
+        "e2e": e2e, "gpu_launches": args.steps * (2 + (1 if world > 1 else 0)),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_vs_cpu": parity,
     }
     print(json.dumps(line), flush=True)

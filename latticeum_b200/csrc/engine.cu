@@ -131,8 +131,10 @@ struct lat_ajtai {
     // mac + reduce into cms_dev for `count` witnesses in the extended layout, count x stride x 48
     int mac_fx(const u64 *Fx, u64 stride, uint32_t count, u64 *cms_dev) {
         lat::MacPlan plan = lat::plan_mac(lay, count, sm_count);
+        size_t had = ws.bytes;
         int st = ws.ensure(plan.ws_elems * sizeof(u64));
         if (st) return st;
+        if (ws.bytes != had) CK(cudaMemsetAsync(ws.p, 0, ws.bytes, stream));  // the kernel keeps it zero afterwards
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (profiling) {
             int i = ev_next;
@@ -359,11 +361,9 @@ int lat_ajtai_commit_coeff(lat_ajtai *h, const uint64_t *f_coeff, uint64_t f_len
 // shared by from_w_ccs and decompose_and_commit_*: device input -> digits -> CRT -> (commit)
 static int witness_core(lat_ajtai *h, const u64 *w_dev, u64 w_len, bool in_coeff, u64 *f_coeff_dev, u64 *f_dev,
                         u64 *cm_dev) {
-    lat::launch_icrt_decompose(w_dev, w_len, (int)h->log2_B, (int)h->L, h->mont, in_coeff, h->f16.as<int16_t>(),
-                               f_coeff_dev, h->flag.as<int>(), h->stream);
-    CK(cudaGetLastError());
-    // the CRT kernel writes the extended layout for the MAC directly; the plain layout only if the caller wants f
-    lat::launch_crt_small(h->f16.as<int16_t>(), h->n, h->mont, f_dev, cm_dev ? h->fx.as<u64>() : nullptr, h->stream);
+    // one kernel: iCRT -> digits -> CRT; the extended layout feeds the MAC, the plain layout only if the caller wants f
+    lat::launch_witness(w_dev, w_len, (int)h->log2_B, (int)h->L, h->mont, in_coeff, h->f16.as<int16_t>(), f_coeff_dev,
+                        f_dev, cm_dev ? h->fx.as<u64>() : nullptr, h->flag.as<int>(), h->stream);
     CK(cudaGetLastError());
     h->has_resident = true;
     if (cm_dev) return h->mac_fx(h->fx.as<u64>(), h->n, 1, cm_dev);
@@ -558,8 +558,8 @@ int lat_ring_gadget_decompose(const uint64_t *in, uint64_t count, uint32_t log2_
             break;
         if ((e = cudaMemset(dflag.p, 0, sizeof(int))) != cudaSuccess) break;
         if ((e = cudaMemcpy(din.p, in, count * ELEM_BYTES, cudaMemcpyHostToDevice)) != cudaSuccess) break;
-        lat::launch_icrt_decompose(din.as<u64>(), count, (int)log2_b, (int)L, repr == LAT_REPR_MONTGOMERY, true,
-                                   d16.as<int16_t>(), dout.as<u64>(), dflag.as<int>(), nullptr);
+        lat::launch_witness(din.as<u64>(), count, (int)log2_b, (int)L, repr == LAT_REPR_MONTGOMERY, true,
+                            d16.as<int16_t>(), dout.as<u64>(), nullptr, nullptr, dflag.as<int>(), nullptr);
         if ((e = cudaGetLastError()) != cudaSuccess) break;
         if ((e = cudaMemcpy(out, dout.p, count * L * ELEM_BYTES, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
         if ((e = cudaMemcpy(&h_flag, dflag.p, sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) break;

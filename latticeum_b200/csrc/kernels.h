@@ -13,16 +13,15 @@ typedef unsigned long long u64;
 void launch_crt(const u64 *in, u64 *out, u64 count, cudaStream_t stream);
 void launch_icrt(const u64 *in, u64 *out, u64 count, cudaStream_t stream);
 
-// w (CRT form, `mont` says which representation) -> iCRT -> balanced digits base 2^log2b, L limbs.
+// Witness::from_w_ccs fused: w (CRT form unless in_coeff; `mont` says which representation) -> iCRT -> balanced
+// digits base 2^log2b, L limbs -> CRT of every limb.
 //   f16      : w_len*L x 24 int16 digits, element-major / limb-minor (always written)
-//   f_coeff  : same as u64 field elements in the caller's representation, or nullptr
-//   in_coeff : if true the input is already in coefficient form (skip the iCRT)
+//   f_coeff  : the digits as u64 field elements in the caller's representation, or nullptr
+//   f_plain  : CRT form, w_len*L x 24, or nullptr
+//   fx       : CRT form in the MAC kernel's extended layout, w_len*L x 48, or nullptr
 //   flag     : device int, OR-ed with 1 when a coefficient does not fit in L digits
-void launch_icrt_decompose(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool in_coeff, int16_t *f16,
-                           u64 *f_coeff, int *flag, cudaStream_t stream);
-
-// int16 digits -> CRT-form elements: out (count x 24, may be nullptr) and/or fx (count x 48 extended, may be nullptr).
-void launch_crt_small(const int16_t *f16, u64 count, bool mont, u64 *out, u64 *fx, cudaStream_t stream);
+void launch_witness(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool in_coeff, int16_t *f16, u64 *f_coeff,
+                    u64 *f_plain, u64 *fx, int *flag, cudaStream_t stream);
 
 // int16 coefficients -> K base-2 digit planes: plane k of element j = sign * bit_k(|c|).
 //   planes_f     : K x n x 24 CRT form, or nullptr
@@ -61,8 +60,8 @@ void launch_relayout(const u64 *rows, uint32_t row0, uint32_t nrows, u64 row_str
 struct MacPlan {
     uint32_t pt;        // planes per thread
     uint32_t grid_x;    // column-chunk CTAs
-    uint32_t nslots;    // partial slots per (plane, row)
-    size_t ws_elems;    // u64 of workspace
+    uint32_t nslots;    // partial sums per output (= CTAs x column groups contributing to it)
+    size_t ws_elems;    // u64 of workspace (must be zeroed once; launches leave it zeroed)
     size_t smem_bytes;
     uint32_t stages;
 };

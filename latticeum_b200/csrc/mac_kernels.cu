@@ -18,7 +18,8 @@
 //    (Karatsuba) = 24 IMAD.WIDE.U32; a single special-form reduction per output at the end.  IMAD.WIDE.U32 runs at
 //    31.5 /clk/SM (measured), so this multiply count, not HBM, is what the batched (PT > 1) case is bound by.
 //    No tensor cores: this is exact 64-bit modular integer work.
-//  * Per-CTA partial results (canonical u64) go to a small workspace; mac_reduce_kernel sums them mod q.
+//  * Cross-CTA sum inside the same kernel: canonical partials are added as 32-bit halves with 64-bit REDs into a
+//    (zeroed, self-cleaning) workspace and the last CTA folds them mod q into the commitment.
 //  * A is canonical and F is in the caller's representation, so canonical(A) * repr(F) = repr(A*F): the
 //    commitment comes out in the caller's representation without any conversion (the map is Fq-linear).
 #include <cstdio>
@@ -160,7 +161,8 @@ void launch_fext(const u64 *f, u64 count, u64 *fx, cudaStream_t stream) {
 // ---- the MAC kernel --------------------------------------------------------------------------------------------
 // grid = (column chunks, row blocks, plane groups); block = (RG*CG consumer warps + 1 producer warp) * 32.
 // Shared memory: STAGES x { A tile | PT x TJ x 48 u64 of extended witness } + 2*STAGES mbarriers.
-// Partials layout: ws[((slot * planes + p) * kappa_pad + row) * 24 + s*3 + c], slot = blockIdx.x * CG + cg.
+// Workspace: ws[2*i], ws[2*i+1] = sums of the low / high 32-bit halves of output i = (p * kappa + row) * 24 + s*3 + c;
+// ws[2 * nout] = finished-CTA counter.  Must be zero before the first launch; every launch leaves it zero again.
 template <int PT, int RG>
 struct MacGeo {
     static constexpr int RB = 4 * RG, CG = geo_cg(RG), TJ = geo_tj(RG);
@@ -177,7 +179,7 @@ struct MacGeo {
 template <int PT, int RG>
 __global__ void __launch_bounds__(MacGeo<PT, RG>::THREADS, MacGeo<PT, RG>::MIN_CTAS)
 mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__ Fx, u64 f_stride, uint32_t planes,
-           uint32_t stages, u64 *__restrict__ ws) {
+           uint32_t stages, u64 *__restrict__ ws, u64 *__restrict__ cms) {
     using G = MacGeo<PT, RG>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // after the stages: [full mbarrier x stages][release counter x stages]
@@ -269,42 +271,46 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
         ph = ph_n;
     }
 
-    // ===== epilogue: one reduction per output, canonical partial to the workspace =====
-    const u32 slot = blockIdx.x * G::CG + cgi;
+    // ===== epilogue ============================================================================================
+    // One special-form reduction per output, then the cross-CTA sum: every partial (canonical, < 2^64) is split into
+    // its 32-bit halves and added with two 64-bit REDs into ws[2*idx], ws[2*idx+1] (a few hundred addends cannot
+    // overflow); the last CTA to finish folds lo + 2^32 hi mod q into cms and leaves the workspace zeroed for the
+    // next launch.  No second kernel, no partials round trip.
     const u32 row = rbk * G::RB + il;
+    if (row < lay.kappa) {
 #pragma unroll
-    for (int p = 0; p < PT; ++p) {
-        u64 c0, c1, c2;
-        acc[p].finish(c0, c1, c2);
-        u64 *dst = ws + (((u64)slot * planes + (p0 + p)) * lay.kappa_pad + row) * ring::D + s * 3;
-        dst[0] = c0;
-        dst[1] = c1;
-        dst[2] = c2;
-    }
-}
-
-// cms[p][row][t] = sum over slots of the partials, mod q.  One block per (p, row); 240 threads = 10 x 24.
-__global__ void __launch_bounds__(256)
-mac_reduce_kernel(const u64 *__restrict__ ws, uint32_t nslots, uint32_t planes, uint32_t kappa, uint32_t kappa_pad,
-                  u64 *__restrict__ cms) {
-    __shared__ u64 part[10][ring::D];
-    const u32 p = blockIdx.x / kappa, row = blockIdx.x - p * kappa;
-    const u32 g = threadIdx.x / ring::D, t = threadIdx.x - g * ring::D;
-    if (g < 10) {
-        u64 lo = 0, hi = 0;
-        for (u32 sl = g; sl < nslots; sl += 10) {
-            u64 v = ws[(((u64)sl * planes + p) * kappa_pad + row) * ring::D + t];
-            lo += v;
-            hi += (lo < v);
+        for (int p = 0; p < PT; ++p) {
+            u64 c[3];
+            acc[p].finish(c[0], c[1], c[2]);
+            u64 *dst = ws + 2 * ((((u64)(p0 + p)) * lay.kappa + row) * ring::D + s * 3);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                atomicAdd(reinterpret_cast<unsigned long long *>(dst + 2 * k), c[k] & 0xFFFFFFFFull);
+                atomicAdd(reinterpret_cast<unsigned long long *>(dst + 2 * k + 1), c[k] >> 32);
+            }
         }
-        part[g][t] = gl::reduce128(lo, hi);
+    }
+    __shared__ u32 s_last;
+    const u64 nout = (u64)planes * lay.kappa * ring::D;
+    u64 *counter = ws + 2 * nout;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const u32 total = gridDim.x * gridDim.y * gridDim.z;
+        s_last = (atomicAdd(reinterpret_cast<unsigned long long *>(counter), 1ull) == total - 1) ? 1u : 0u;
     }
     __syncthreads();
-    if (threadIdx.x < ring::D) {
-        u64 acc = part[0][threadIdx.x];
-#pragma unroll
-        for (int k = 1; k < 10; ++k) acc = gl::add(acc, part[k][threadIdx.x]);
-        cms[((u64)p * kappa + row) * ring::D + threadIdx.x] = acc;
+    if (s_last) {
+        __threadfence();
+        for (u64 i = threadIdx.x; i < nout; i += blockDim.x) {
+            u64 lo = __ldcg(ws + 2 * i), hi = __ldcg(ws + 2 * i + 1);   // sums of low / high halves
+            u64 v_lo = lo + (hi << 32);
+            u64 v_hi = (hi >> 32) + (v_lo < lo ? 1ull : 0ull);
+            cms[i] = gl::reduce128(v_lo, v_hi);
+            ws[2 * i] = 0;
+            ws[2 * i + 1] = 0;
+        }
+        if (threadIdx.x == 0) *counter = 0;
     }
 }
 
@@ -322,7 +328,7 @@ MacPlan plan_mac(const MatLayout &lay, uint32_t planes, int sm_count) {
     size_t stage_bytes = stage_bytes_for(m.pt, lay.rg);
     uint32_t occ_cap = (m.pt == 1) ? 2 : 1;
     // as many stages as fit next to occ_cap resident CTAs (227 KB usable, 1 KB reserved per CTA), at most 6
-    size_t per_cta = (227 * 1024) / occ_cap - SM_RESERVED_SMEM - 2 * 8 * sizeof(u64);  // 16 B of sync state per stage
+    size_t per_cta = (227 * 1024) / occ_cap - SM_RESERVED_SMEM - 1024;  // 16 B of sync state per stage
     uint32_t stages = (uint32_t)(per_cta / stage_bytes);
     if (stages > 6) stages = 6;
     if (stages < 2) stages = 2;
@@ -339,16 +345,16 @@ MacPlan plan_mac(const MatLayout &lay, uint32_t planes, int sm_count) {
     if (gx > lay.ntiles) gx = lay.ntiles;
     m.grid_x = (uint32_t)gx;
     m.nslots = m.grid_x * lay.cg;
-    m.ws_elems = (size_t)m.nslots * planes * lay.kappa_pad * ring::D;
+    m.ws_elems = (size_t)planes * lay.kappa * ring::D * 2 + 2;  // (lo, hi) sums per output + the CTA counter
     return m;
 }
 
 template <int PT, int RG>
 static void launch_mac_t(dim3 grid, const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes,
-                         const MacPlan &plan, u64 *workspace, cudaStream_t stream) {
+                         const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mac_kernel<PT, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(mac_kernel<PT, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // minus the static bytes
         if (e != cudaSuccess) fprintf(stderr, "lattice_ajtai: cudaFuncSetAttribute(mac_kernel<%d,%d>): %s\n", PT, RG, cudaGetErrorString(e));
         attr_set = true;
     }
@@ -362,21 +368,21 @@ static void launch_mac_t(dim3 grid, const u64 *A_dev, const MatLayout &lay, cons
                 fa.maxDynamicSharedSizeBytes, fa.sharedSizeBytes, occ, fa.maxThreadsPerBlock);
     }
     mac_kernel<PT, RG><<<grid, MacGeo<PT, RG>::THREADS, plan.smem_bytes, stream>>>(A_dev, lay, Fx, f_stride, planes,
-                                                                                    plan.stages, workspace);
+                                                                                    plan.stages, workspace, cms);
 }
 
 template <int PT>
 static void launch_mac_pt(dim3 grid, const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes,
-                          const MacPlan &plan, u64 *workspace, cudaStream_t stream) {
+                          const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream) {
     switch (lay.rg) {
-        case 1: launch_mac_t<PT, 1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream); break;
-        case 2: launch_mac_t<PT, 2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream); break;
-        case 3: launch_mac_t<PT, 3>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream); break;
-        case 4: launch_mac_t<PT, 4>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream); break;
-        case 5: launch_mac_t<PT, 5>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream); break;
-        case 6: launch_mac_t<PT, 6>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream); break;
-        case 7: launch_mac_t<PT, 7>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream); break;
-        default: launch_mac_t<PT, 8>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream); break;
+        case 1: launch_mac_t<PT, 1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream); break;
+        case 2: launch_mac_t<PT, 2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream); break;
+        case 3: launch_mac_t<PT, 3>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream); break;
+        case 4: launch_mac_t<PT, 4>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream); break;
+        case 5: launch_mac_t<PT, 5>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream); break;
+        case 6: launch_mac_t<PT, 6>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream); break;
+        case 7: launch_mac_t<PT, 7>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream); break;
+        default: launch_mac_t<PT, 8>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream); break;
     }
 }
 
@@ -384,10 +390,9 @@ void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_str
                 u64 *workspace, u64 *cms, cudaStream_t stream, cudaEvent_t ev_begin, cudaEvent_t ev_end) {
     dim3 grid(plan.grid_x, lay.nrb, planes / plan.pt);
     if (ev_begin) cudaEventRecord(ev_begin, stream);
-    if (plan.pt == 1) launch_mac_pt<1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream);
-    else launch_mac_pt<2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, stream);
+    if (plan.pt == 1) launch_mac_pt<1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream);
+    else launch_mac_pt<2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream);
     if (ev_end) cudaEventRecord(ev_end, stream);
-    mac_reduce_kernel<<<planes * lay.kappa, 256, 0, stream>>>(workspace, plan.nslots, planes, lay.kappa, lay.kappa_pad, cms);
 }
 
 // cms[0] = cm - sum_{k>=1} 2^k cms[k]: Horner from the top plane, (acc + y_k) * 2.  decomposition.rs:189-197

@@ -43,7 +43,8 @@ class ShardedAjtaiScheme:
             return partial
         if self._gather is None or self._gather.shape[1:] != partial.shape or self._gather.device != partial.device:
             self._gather = torch.empty((self.world,) + tuple(partial.shape), dtype=partial.dtype, device=partial.device)
-        dist.all_gather_into_tensor(self._gather, partial, group=self.group)
+        # flat views: gloo's all-gather wants a 1-D output of world * numel; NCCL accepts the same
+        dist.all_gather_into_tensor(self._gather.view(-1), partial.contiguous().view(-1), group=self.group)
         out = torch.empty_like(partial)
         return self.engine.fold_partials(self._gather, out)
 
