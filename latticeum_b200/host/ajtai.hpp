@@ -1,0 +1,102 @@
+// Header-only C++ mirror of the reference's commitment API over the C ABI (include/lattice_ajtai.h), for C++ hosts.
+// Names follow latticefold/src/commitment/commitment_scheme.rs:38-140 and homomorphic_commitment.rs:12-80.
+// Ring elements are 24 contiguous uint64_t (CRT form: slot*3 + component).  No CPU fallback: construction throws
+// without a CUDA device.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/lattice_ajtai.h"
+
+namespace lat {
+
+using RingElem = uint64_t[LAT_RING_DEGREE];
+
+// latticefold/src/commitment.rs:13-26
+struct CommitmentError : std::runtime_error {
+    int status;
+    size_t got, expected;
+    CommitmentError(int st, size_t g, size_t e, const std::string &msg) : std::runtime_error(msg), status(st), got(g), expected(e) {}
+};
+inline void check(int st, size_t got = 0, size_t expected = 0) {
+    if (st == LAT_OK) return;
+    if (st == LAT_E_WRONG_WITNESS_LENGTH)
+        throw CommitmentError(st, got, expected,
+                              "Wrong length of the witness: " + std::to_string(got) + ", expected: " + std::to_string(expected));
+    throw CommitmentError(st, got, expected, std::string(lat_strerror(st)) + ": " + lat_last_error());
+}
+
+// Commitment<R>: kappa ring elements (homomorphic_commitment.rs:12-14)
+struct Commitment {
+    std::vector<uint64_t> val;  // kappa * 24
+    size_t len() const { return val.size() / LAT_RING_DEGREE; }
+    bool operator==(const Commitment &o) const { return val == o.val; }
+};
+
+struct DecompositionParams {  // decomposition_parameters.rs:11-20; zkvm/src/ccs.rs:26-34
+    uint32_t log2_B = 15, L = 5, K = 15;
+};
+
+class AjtaiCommitmentScheme {
+   public:
+    // AjtaiCommitmentScheme::new: rows[i] points at n ring elements (the host matrix is a vector of rows)
+    AjtaiCommitmentScheme(const std::vector<const uint64_t *> &rows, uint64_t n, DecompositionParams p = {},
+                          lat_repr repr = LAT_REPR_CANONICAL, int device = 0)
+        : kappa_((uint32_t)rows.size()), n_(n), p_(p) {
+        check(lat_ajtai_create(&h_, kappa_, n, p.log2_B, p.L, p.K, repr, device));
+        for (uint32_t i = 0; i < kappa_; ++i) check(lat_ajtai_upload_rows(h_, i, 1, rows[i], n));
+    }
+    ~AjtaiCommitmentScheme() { lat_ajtai_destroy(h_); }
+    AjtaiCommitmentScheme(const AjtaiCommitmentScheme &) = delete;
+    AjtaiCommitmentScheme &operator=(const AjtaiCommitmentScheme &) = delete;
+
+    size_t kappa() const { return kappa_; }  // :85
+    size_t width() const { return n_; }      // :92
+
+    // commit / commit_ntt (:63-80, :101-103)
+    Commitment commit_ntt(const uint64_t *f, size_t f_len) const {
+        Commitment cm{std::vector<uint64_t>((size_t)kappa_ * LAT_RING_DEGREE)};
+        check(lat_ajtai_commit_ntt(h_, f, f_len, cm.val.data()), f_len, n_);
+        return cm;
+    }
+    Commitment commit(const uint64_t *f, size_t f_len) const { return commit_ntt(f, f_len); }
+    // commit_coeff (:107-112)
+    Commitment commit_coeff(const uint64_t *f_coeff, size_t f_len) const {
+        Commitment cm{std::vector<uint64_t>((size_t)kappa_ * LAT_RING_DEGREE)};
+        check(lat_ajtai_commit_coeff(h_, f_coeff, f_len, cm.val.data()), f_len, n_);
+        return cm;
+    }
+    // decompose_and_commit_ntt (:132-139)
+    Commitment decompose_and_commit_ntt(const uint64_t *w, size_t w_len) const {
+        Commitment cm{std::vector<uint64_t>((size_t)kappa_ * LAT_RING_DEGREE)};
+        check(lat_ajtai_decompose_and_commit_ntt(h_, w, w_len, cm.val.data()), w_len * p_.L, n_);
+        return cm;
+    }
+    // Witness::from_w_ccs + Witness::commit (arith.rs:230-248, 357-362); f_coeff / f may be null
+    Commitment witness_from_w_ccs(const uint64_t *w_ccs, size_t w_len, uint64_t *f_coeff, uint64_t *f) const {
+        Commitment cm{std::vector<uint64_t>((size_t)kappa_ * LAT_RING_DEGREE)};
+        check(lat_ajtai_witness_from_w_ccs(h_, w_ccs, w_len, f_coeff, f, cm.val.data()), w_len * p_.L, n_);
+        return cm;
+    }
+    // decompose_witness + commit_witnesses (nifs/decomposition.rs:162-201): K commitments, y_0 by homomorphism
+    std::vector<Commitment> decompose_commit(const uint64_t *f_coeff, size_t n, const Commitment &cm, uint64_t *planes_coeff = nullptr,
+                                             uint64_t *planes_f = nullptr) const {
+        std::vector<uint64_t> cms((size_t)p_.K * kappa_ * LAT_RING_DEGREE);
+        check(lat_ajtai_decompose_commit(h_, f_coeff, n, cm.val.data(), planes_coeff, planes_f, cms.data()), n, n_);
+        std::vector<Commitment> out(p_.K);
+        for (uint32_t k = 0; k < p_.K; ++k)
+            out[k].val.assign(cms.begin() + (size_t)k * kappa_ * LAT_RING_DEGREE, cms.begin() + (size_t)(k + 1) * kappa_ * LAT_RING_DEGREE);
+        return out;
+    }
+    lat_ajtai *handle() const { return h_; }
+
+   private:
+    lat_ajtai *h_ = nullptr;
+    uint32_t kappa_;
+    uint64_t n_;
+    DecompositionParams p_;
+};
+
+}  // namespace lat

@@ -366,3 +366,15 @@ def test_zkvm_fold_step_properties(zkvm):
     f2 = CO.fill_uniform((LB.N, 24), 81)
     s = ((wit.f.astype(object) + f2.astype(object)) % Q).astype(np.uint64)
     assert scheme.commit(s) == scheme.commit(wit.f) + scheme.commit(f2)
+
+
+def test_cpp_host_mirror_example():
+    # latticeum_b200/host/ajtai.hpp: the C++ mirror of the reference API, on the reference's closed-form commit test
+    import subprocess
+
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "latticeum_b200", "host", "example")
+    if not os.path.exists(exe):
+        pytest.skip("example not built (run __graft_entry__.build())")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "example ok" in out.stdout
