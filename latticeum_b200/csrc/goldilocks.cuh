@@ -134,6 +134,14 @@ struct WideAcc {
     }
 };
 
+// a + b as SOME 64-bit representative of (a + b) mod q, for canonical a, b: on carry add 2^64 = 2^32 - 1 (mod q);
+// a, b < q makes a second carry impossible.  Used for the witness-side Karatsuba sums of the extended layout: the
+// MAC only multiplies by them, and products tolerate non-canonical operands.
+__device__ __forceinline__ u64 add_lazy(u64 a, u64 b) {
+    u64 s = a + b;
+    return s + ((s < a) ? EPS : 0ull);
+}
+
 // Karatsuba pre-addition on the matrix side: the exact 65-bit sum a + b = s + c * 2^64 (c = carry).  The carry is NOT
 // folded back into s (that costs IMAD-pipe instructions, measured); instead mac65 below adds c * y * 2^64 straight
 // into the accumulator's weight-2^64 column with carry-chain adds, which ptxas must keep on the ALU pipe.

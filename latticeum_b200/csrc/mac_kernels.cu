@@ -149,8 +149,8 @@ fext_kernel(const u64 *__restrict__ f, u64 count_slots, u64 *__restrict__ fx) {
     f0 = gl::reduce128(f0, 0); f1 = gl::reduce128(f1, 0); f2 = gl::reduce128(f2, 0);
     ulonglong2 *o = reinterpret_cast<ulonglong2 *>(fx + i * 6);
     o[0] = make_ulonglong2(f0, f1);
-    o[1] = make_ulonglong2(f2, gl::add(f0, f1));
-    o[2] = make_ulonglong2(gl::add(f0, f2), gl::add(f1, f2));
+    o[1] = make_ulonglong2(f2, gl::add_lazy(f0, f1));
+    o[2] = make_ulonglong2(gl::add_lazy(f0, f2), gl::add_lazy(f1, f2));
 }
 void launch_fext(const u64 *f, u64 count, u64 *fx, cudaStream_t stream) {
     u64 slots = count * ring::NSLOT;

@@ -83,6 +83,43 @@ __device__ __forceinline__ void crt24(u64 (&c)[D]) {
     homogenize(c);
 }
 
+// Forward CRT of an element whose coefficients are SMALL signed integers (|d| < 2^15: base-B limbs, bit planes).
+// Layer 1 uses zeta = w^4 = 2^160 = -2^64 = -(2^32 - 1) (mod q), so zeta*b = b - (b << 32) is an exact 48-bit
+// signed integer and the whole first layer is plain int64 arithmetic (no modular reduction); the results
+// (|x| < 2^48) are mapped into the field once, then layers 2 and 3 and the twist run as in crt24.
+// Same values as crt24(from_small(d)): the maps are Fq-linear and the integers are exact.
+template <bool MONT>
+__device__ __forceinline__ void crt24_small(const int (&d)[D], u64 (&c)[D]) {
+    long long x[D];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {  // ntt.rs:146-152 with zb = zeta * b
+        long long a = d[i], b = d[12 + i];
+        long long zb = b - (b << 32);
+        x[i] = a + zb;
+        x[12 + i] = a + b - zb;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        // signed |x| < 2^48 -> field element (canonical), then to Montgomery form if the caller uses it
+        u64 m = (u64)(x[i] < 0 ? -x[i] : x[i]);
+        u64 v = (x[i] < 0 && m) ? gl::Q - m : m;
+        c[i] = MONT ? gl::to_mont(v) : v;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {  // ntt.rs:160-179
+        bf_fwd<2>(c[i], c[6 + i]);
+        bf_fwd<10>(c[12 + i], c[18 + i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {  // ntt.rs:186-225
+        bf_fwd<1>(c[i], c[3 + i]);
+        bf_fwd<7>(c[6 + i], c[9 + i]);
+        bf_fwd<5>(c[12 + i], c[15 + i]);
+        bf_fwd<11>(c[18 + i], c[21 + i]);
+    }
+    homogenize(c);
+}
+
 // 8 x Fq3 -> 24 coefficients, in place.
 __device__ __forceinline__ void icrt24(u64 (&c)[D]) {
     dehomogenize(c);

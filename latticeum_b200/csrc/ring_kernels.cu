@@ -20,8 +20,8 @@
 namespace lat {
 using gl::u32;
 
-constexpr int OPB = 32;            // octets (ring elements) per block
-constexpr int THREADS = OPB * 8;   // 256
+constexpr int OPB = 16;            // octets (ring elements) per block
+constexpr int THREADS = OPB * 8;   // 128
 
 struct Octet {
     u64 e;       // element index (clamped into range so that every lane can take part in the shuffles)
@@ -48,8 +48,8 @@ __device__ __forceinline__ void store3(u64 *__restrict__ base, u64 elem, u32 sl,
 __device__ __forceinline__ void store_fx(u64 *__restrict__ fx, u64 elem, u32 sl, const u64 (&c)[3]) {
     ulonglong2 *p = reinterpret_cast<ulonglong2 *>(fx + (elem * ring::NSLOT + sl) * 6);
     p[0] = make_ulonglong2(c[0], c[1]);
-    p[1] = make_ulonglong2(c[2], gl::add(c[0], c[1]));
-    p[2] = make_ulonglong2(gl::add(c[0], c[2]), gl::add(c[1], c[2]));
+    p[1] = make_ulonglong2(c[2], gl::add_lazy(c[0], c[1]));
+    p[2] = make_ulonglong2(gl::add_lazy(c[0], c[2]), gl::add_lazy(c[1], c[2]));
 }
 
 // ---- batched CRT / iCRT ------------------------------------------------------------------------------------
@@ -100,8 +100,8 @@ __device__ __forceinline__ void store_elem_fx(u64 *__restrict__ fx, u64 elem, co
     for (int sl = 0; sl < ring::NSLOT; ++sl) {
         u64 f0 = c[3 * sl], f1 = c[3 * sl + 1], f2 = c[3 * sl + 2];
         p[3 * sl] = make_ulonglong2(f0, f1);
-        p[3 * sl + 1] = make_ulonglong2(f2, gl::add(f0, f1));
-        p[3 * sl + 2] = make_ulonglong2(gl::add(f0, f2), gl::add(f1, f2));
+        p[3 * sl + 1] = make_ulonglong2(f2, gl::add_lazy(f0, f1));
+        p[3 * sl + 2] = make_ulonglong2(gl::add_lazy(f0, f2), gl::add_lazy(f1, f2));
     }
 }
 
@@ -114,7 +114,7 @@ __device__ __forceinline__ void store_elem_fx(u64 *__restrict__ fx, u64 elem, co
 // (98 815 limb elements) gets the cheap transform.
 constexpr int WIT_MAX_L = 8;
 template <bool MONT>
-__global__ void __launch_bounds__(THREADS, 3)
+__global__ void __launch_bounds__(THREADS, 6)
 witness_kernel(const u64 *__restrict__ w, u64 w_len, int log2b, int L, bool in_coeff, int16_t *__restrict__ f16,
                u64 *__restrict__ f_coeff, u64 *__restrict__ f_plain, u64 *__restrict__ fx, int *__restrict__ flag) {
     __shared__ __align__(16) int16_t tile[OPB * WIT_MAX_L * ring::D];  // [octet][limb][24] = 12 KB
@@ -163,9 +163,7 @@ witness_kernel(const u64 *__restrict__ w, u64 w_len, int log2b, int L, bool in_c
         int d[ring::D];
         load_i16x24(tile + idx * ring::D, d);
         u64 c[ring::D];
-#pragma unroll
-        for (int k = 0; k < ring::D; ++k) c[k] = gl::from_small<MONT>(d[k]);
-        ring::crt24(c);
+        ring::crt24_small<MONT>(d, c);
         const u64 elem = e0 * (u64)L + idx;
         if (f_plain) store_elem(f_plain, elem, c);
         if (fx) store_elem_fx(fx, elem, c);
@@ -197,16 +195,21 @@ planes_kernel(const int16_t *__restrict__ f16, u64 n, int K, u64 *__restrict__ p
     load_i16x24(f16 + e * ring::D, d);
     for (int k = 0; k < K; ++k) {
         u64 c[ring::D];
+        int pd[ring::D];
 #pragma unroll
         for (int t = 0; t < ring::D; ++t) {
             int a = d[t] < 0 ? -d[t] : d[t];
             int bit = (a >> k) & 1;
-            c[t] = gl::from_small<MONT>(d[t] < 0 ? -bit : bit);
+            pd[t] = d[t] < 0 ? -bit : bit;  // digit k base 2 = sign * bit_k(|c|)
         }
         const u64 elem = (u64)k * n + e;
-        if (planes_coeff) store_elem(planes_coeff, elem, c);
+        if (planes_coeff) {
+#pragma unroll
+            for (int t = 0; t < ring::D; ++t) c[t] = gl::from_small<MONT>(pd[t]);
+            store_elem(planes_coeff, elem, c);
+        }
         if (planes_f || planes_fx) {
-            ring::crt24(c);
+            ring::crt24_small<MONT>(pd, c);
             if (planes_f) store_elem(planes_f, elem, c);
             if (planes_fx) store_elem_fx(planes_fx, elem, c);
         }

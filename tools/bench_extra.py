@@ -1,0 +1,85 @@
+"""Secondary measurements (BASELINE.json configs[2], configs[3]): the fold-step batch (decompose + 14 commits per side)
+and the standalone CRT/iCRT sweep, device-resident, CUDA-event timed.  Writes gpurun_out/extra.json."""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import latticeum_b200 as LB
+from latticeum_b200 import _capi as capi
+from latticeum_b200.device import DeviceScheme
+
+KAPPA, N, K = 32, 98815, 15
+rng = np.random.default_rng(0)
+out = {}
+
+
+def timeit(fn, reps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+# ---- transform sweep (config 3) -------------------------------------------------------------------------------------
+L = capi.lib()
+stream = C.c_void_p(torch.cuda.current_stream().cuda_stream or 1)
+sweep = []
+for lg in range(10, 23, 2):
+    cnt = 1 << lg
+    x = torch.from_numpy(rng.integers(0, 2**63, size=(cnt, 24), dtype=np.int64)).cuda()
+    y = torch.empty_like(x)
+    t_crt = timeit(lambda: L.lat_ring_crt_dev(x.data_ptr(), cnt, y.data_ptr(), stream))
+    t_icrt = timeit(lambda: L.lat_ring_icrt_dev(x.data_ptr(), cnt, y.data_ptr(), stream))
+    sweep.append({"log2_count": lg, "crt_us": t_crt * 1e3, "icrt_us": t_icrt * 1e3,
+                  "crt_GBps": cnt * 384 / t_crt / 1e6, "icrt_GBps": cnt * 384 / t_icrt / 1e6})
+    print(sweep[-1], flush=True)
+    del x, y
+out["transform_sweep"] = sweep
+
+# ---- fold-step batch (config 2) ---------------------------------------------------------------------------------------
+scheme = LB.AjtaiCommitmentScheme(KAPPA, N)
+for i in range(KAPPA):
+    scheme.upload_rows(i, rng.integers(0, 2**63, size=(1, N, 24), dtype=np.uint64))
+eng = DeviceScheme(scheme)
+v = rng.integers(-(2**14), 2**14 + 1, size=(N, 24), dtype=np.int64)           # dense: every bit-plane about half full
+fc = np.where(v < 0, np.uint64(LB.scheme.Q) - (-v).astype(np.uint64), v.astype(np.uint64)).astype(np.uint64)
+fc_dev = eng.to_device(fc)
+cm = eng.new_commitment()
+cms = torch.empty((K, KAPPA, 24), dtype=torch.int64, device="cuda")
+eng.commit_ntt(eng.to_device(rng.integers(0, 2**63, size=(N, 24), dtype=np.uint64)), cm)
+eng.set_profiling(True)
+eng.mac_profile()
+t_side = timeit(lambda: eng.decompose_commit(fc_dev, cm, cms), reps=10)
+mac_ms, mac_n = eng.mac_profile()
+eng.set_profiling(False)
+eng.synchronize()
+wide = 14 * KAPPA * N * 8 * 24
+out["fold_side"] = {"what": "decompose_witness + commit_witnesses for one side: 15 planes, 14 matrix commits, y_0",
+                    "ms": t_side, "mac_kernel_ms": mac_ms / mac_n, "commitments_per_s": 14 / (t_side * 1e-3),
+                    "ring_elems_per_s": 14 * N / (t_side * 1e-3),
+                    "imad_wide_per_s": wide / (mac_ms / mac_n * 1e-3), "imad_wide_peak_per_s": 9.154e12,
+                    "imad_pipe_frac": wide / (mac_ms / mac_n * 1e-3) / 9.154e12}
+print(out["fold_side"], flush=True)
+# 28-witness batch through commit_ntt_batch (both sides in one launch)
+fs = torch.from_numpy(rng.integers(0, 2**63, size=(28, N, 24), dtype=np.int64)).cuda()
+cms28 = torch.empty((28, KAPPA, 24), dtype=torch.int64, device="cuda")
+eng.set_profiling(True)
+eng.mac_profile()
+t28 = timeit(lambda: eng.commit_ntt(fs, cms28), reps=5)
+mac_ms, mac_n = eng.mac_profile()
+wide28 = 28 * KAPPA * N * 8 * 24
+out["batch28"] = {"ms": t28, "mac_kernel_ms": mac_ms / mac_n, "imad_pipe_frac": wide28 / (mac_ms / mac_n * 1e-3) / 9.154e12}
+print(out["batch28"], flush=True)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/extra.json", "w"), indent=1)
