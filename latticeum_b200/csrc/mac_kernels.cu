@@ -32,11 +32,14 @@ namespace lat {
 using gl::u32;
 
 constexpr int SM_RESERVED_SMEM = 1024;
+#ifndef LAT_TJ_BYTES
+#define LAT_TJ_BYTES 256
+#endif
 constexpr int FX = 48;  // u64 per element in the extended witness layout (8 slots x 6)
 
 // Compile-time geometry per row-group count RG (rows per block RB = 4 RG <= 32).
 __host__ __device__ constexpr int geo_cg(int rg) { return rg == 1 ? 8 : rg == 2 ? 4 : rg <= 4 ? 2 : 1; }
-__host__ __device__ constexpr int geo_tj(int rg) { return ((128 / (4 * rg)) / geo_cg(rg)) * geo_cg(rg); }
+__host__ __device__ constexpr int geo_tj(int rg) { return ((LAT_TJ_BYTES / (4 * rg)) / geo_cg(rg)) * geo_cg(rg) < geo_cg(rg) ? geo_cg(rg) : ((LAT_TJ_BYTES / (4 * rg)) / geo_cg(rg)) * geo_cg(rg); }
 
 MatLayout make_layout(uint32_t kappa, u64 n) {
     MatLayout l{};
@@ -53,7 +56,7 @@ MatLayout make_layout(uint32_t kappa, u64 n) {
     l.nrb = l.kappa_pad / l.rb;
     l.rg = l.rb / 4;
     l.cg = geo_cg((int)l.rg);
-    l.tj = geo_tj((int)l.rg);  // ~24 KB tiles: tj * rb * 192 B
+    l.tj = geo_tj((int)l.rg);  // ~48 KB tiles (tj * rb * 192 B): per-tile barrier/refill costs favour large tiles
     l.ntiles = (n + l.tj - 1) / l.tj;
     if (l.ntiles == 0) l.ntiles = 1;
     l.n_pad = l.ntiles * l.tj;
