@@ -87,15 +87,21 @@ __device__ __forceinline__ void load_i16x24(const int16_t *p, int (&d)[ring::D])
     }
 }
 
-// Whole-element stores for the one-thread-per-element phases.  Each thread writes one contiguous 192 B / 384 B run
-// with 16-byte stores; the half-filled sectors of one instruction are completed by the next and merge in L2.
-__device__ __forceinline__ void store_elem(u64 *__restrict__ out, u64 elem, const u64 (&c)[ring::D]) {
-    ulonglong2 *p = reinterpret_cast<ulonglong2 *>(out + elem * ring::D);  // 192 B per element: 16-B aligned
+// ---- coalesced row output for the one-thread-per-element phases -------------------------------------------------
+// A thread that owns a whole element would write one private 192 B / 384 B run: every store instruction of the warp
+// then touches 32 different sectors with 16 B each, and L2 has to read-merge the half-written sectors (measured on
+// the first planes kernel: 206 MB of DRAM reads and 699 MB of writes for 569 MB of payload, 547 us).  Instead each
+// thread drops its row into a padded shared-memory tile and the block copies the tile out as one contiguous run.
+// Rows are in 16-byte units; the pitch is ROW_UNITS + 1 units so that quarter-warps hit distinct banks.
+constexpr int PLAIN_UNITS = ring::D / 2;  // 12 x 16 B = 192 B
+constexpr int FX_UNITS = FX_WORDS / 2;    // 24 x 16 B = 384 B
+__device__ __forceinline__ void row_put(ulonglong2 *tile, int row, const u64 (&c)[ring::D]) {
+    ulonglong2 *p = tile + row * (PLAIN_UNITS + 1);
 #pragma unroll
-    for (int k = 0; k < ring::D / 2; ++k) p[k] = make_ulonglong2(c[2 * k], c[2 * k + 1]);
+    for (int k = 0; k < PLAIN_UNITS; ++k) p[k] = make_ulonglong2(c[2 * k], c[2 * k + 1]);
 }
-__device__ __forceinline__ void store_elem_fx(u64 *__restrict__ fx, u64 elem, const u64 (&c)[ring::D]) {
-    ulonglong2 *p = reinterpret_cast<ulonglong2 *>(fx + elem * FX_WORDS);
+__device__ __forceinline__ void row_put_fx(ulonglong2 *tile, int row, const u64 (&c)[ring::D]) {
+    ulonglong2 *p = tile + row * (FX_UNITS + 1);
 #pragma unroll
     for (int sl = 0; sl < ring::NSLOT; ++sl) {
         u64 f0 = c[3 * sl], f1 = c[3 * sl + 1], f2 = c[3 * sl + 2];
@@ -104,21 +110,36 @@ __device__ __forceinline__ void store_elem_fx(u64 *__restrict__ fx, u64 elem, co
         p[3 * sl + 2] = make_ulonglong2(gl::add_lazy(f0, f2), gl::add_lazy(f1, f2));
     }
 }
+// block-wide: copy `nrows` rows of ROW_UNITS units from the padded tile to the contiguous global run at `dst`
+template <int ROW_UNITS>
+__device__ __forceinline__ void rows_out(const ulonglong2 *tile, u64 *__restrict__ dst, u32 nrows) {
+    __syncthreads();
+    ulonglong2 *g = reinterpret_cast<ulonglong2 *>(dst);
+    for (u32 u = threadIdx.x; u < nrows * ROW_UNITS; u += blockDim.x) {
+        u32 r = u / ROW_UNITS, c = u - r * ROW_UNITS;
+        g[u] = tile[r * (ROW_UNITS + 1) + c];
+    }
+    __syncthreads();
+}
 
 // ---- Witness::from_w_ccs in one kernel: iCRT -> balanced digits base 2^log2b -> CRT of every limb -------------
-// Phase A (8 lanes per w_ccs element, 32 elements per block): iCRT by warp shuffles, then the digit loop on the
+// Phase A (8 lanes per w_ccs element, OPB elements per block): iCRT by warp shuffles, then the digit loop on the
 // lane's three coefficients; digits go to the device-resident int16 witness and to a shared-memory tile.
-// Phase B (one thread per LIMB element, 32*L of them per block): forward CRT with compile-time shift twiddles
+// Phase B (one thread per LIMB element, OPB*L of them per block): forward CRT with compile-time shift twiddles
 // (ring24.cuh: no general multiplies) straight from the tile, written in the plain and/or the MAC kernel's
-// extended layout.  The small vector (19 763 elements) gets the 8x parallelism where it needs it, the large one
-// (98 815 limb elements) gets the cheap transform.
+// extended layout through the coalescing tile.  The small vector (19 763 elements) gets the 8x parallelism where
+// it needs it, the large one (98 815 limb elements) gets the cheap transform.
+// Dynamic shared memory: OPB*L rows x (FX_UNITS + 1) x 16 B for the output tile.
 constexpr int WIT_MAX_L = 8;
 template <bool MONT>
-__global__ void __launch_bounds__(THREADS, 6)
+__global__ void __launch_bounds__(THREADS, 4)
 witness_kernel(const u64 *__restrict__ w, u64 w_len, int log2b, int L, bool in_coeff, int16_t *__restrict__ f16,
                u64 *__restrict__ f_coeff, u64 *__restrict__ f_plain, u64 *__restrict__ fx, int *__restrict__ flag) {
-    __shared__ __align__(16) int16_t tile[OPB * WIT_MAX_L * ring::D];  // [octet][limb][24] = 12 KB
+    __shared__ __align__(16) int16_t tile[OPB * WIT_MAX_L * ring::D];  // [octet][limb][24] = 6 KB
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    ulonglong2 *otile = reinterpret_cast<ulonglong2 *>(dyn_smem);
     const Octet o = octet_of(w_len);
+    const bool tiled = L <= WIT_MAX_L;  // the engine's L is <= 8; only lat_ring_gadget_decompose allows more
     {
         const ring8::Twiddles tw = ring8::make_twiddles(o.sl);
         u64 c[3];
@@ -145,28 +166,40 @@ witness_kernel(const u64 *__restrict__ w, u64 w_len, int log2b, int L, bool in_c
                     m[k] += 1;
                 }
                 if (negative[k]) dg = -dg;
-                trow[l * ring::D + k] = (int16_t)dg;
-                if (o.valid) {
-                    f16[elem * ring::D + 3 * o.sl + k] = (int16_t)dg;
-                    if (f_coeff) f_coeff[elem * ring::D + 3 * o.sl + k] = gl::from_small<MONT>(dg);
-                }
+                if (tiled) trow[l * ring::D + k] = (int16_t)dg;
+                else if (o.valid) f16[elem * ring::D + 3 * o.sl + k] = (int16_t)dg;  // standalone decompositions with L > 8
+                if (o.valid && f_coeff) f_coeff[elem * ring::D + 3 * o.sl + k] = gl::from_small<MONT>(dg);
             }
         }
         // the reference would index out of bounds (mod.rs:80) if a value needed more than L digits
         if (o.valid && (m[0] | m[1] | m[2])) atomicOr(flag, 1);
     }
-    if (!f_plain && !fx) return;
+    if (!tiled) return;
     __syncthreads();
     const u64 e0 = (u64)blockIdx.x * OPB;
     const u32 nvalid = (u32)min((u64)OPB, w_len - e0);
-    for (u32 idx = threadIdx.x; idx < nvalid * (u32)L; idx += THREADS) {  // tile rows are already in limb-element order
+    const u32 nrows = nvalid * (u32)L;  // tile rows are already in limb-element order
+    {   // the int16 witness: one contiguous run per block, copied with 16-byte stores
+        const uint4 *src = reinterpret_cast<const uint4 *>(tile);
+        uint4 *dst = reinterpret_cast<uint4 *>(f16 + e0 * (u64)L * ring::D);
+        for (u32 u = threadIdx.x; u < nrows * 3; u += THREADS) dst[u] = src[u];
+    }
+    if (!f_plain && !fx) return;
+    u64 c[ring::D];
+    const bool active = threadIdx.x < nrows;  // L <= 8 and OPB = 16: at most 128 rows = one per thread
+    if (active) {
         int d[ring::D];
-        load_i16x24(tile + idx * ring::D, d);
-        u64 c[ring::D];
+        load_i16x24(tile + threadIdx.x * ring::D, d);
         ring::crt24_small<MONT>(d, c);
-        const u64 elem = e0 * (u64)L + idx;
-        if (f_plain) store_elem(f_plain, elem, c);
-        if (fx) store_elem_fx(fx, elem, c);
+    }
+    const u64 elem0 = e0 * (u64)L;
+    if (f_plain) {
+        if (active) row_put(otile, threadIdx.x, c);
+        rows_out<PLAIN_UNITS>(otile, f_plain + elem0 * ring::D, nrows);
+    }
+    if (fx) {
+        if (active) row_put_fx(otile, threadIdx.x, c);
+        rows_out<FX_UNITS>(otile, fx + elem0 * FX_WORDS, nrows);
     }
 }
 
@@ -174,44 +207,64 @@ void launch_witness(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool i
                     u64 *f_plain, u64 *fx, int *flag, cudaStream_t stream) {
     if (!w_len) return;
     unsigned grid = (unsigned)((w_len + OPB - 1) / OPB);
+    size_t smem = (f_plain || fx) ? (size_t)OPB * L * (FX_UNITS + 1) * 16 : 0;  // 32 KB at L = 5
+    if (smem + sizeof(int16_t) * OPB * WIT_MAX_L * ring::D > 48 * 1024) {
+        cudaFuncSetAttribute(witness_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(witness_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
     if (mont)
-        witness_kernel<true><<<grid, THREADS, 0, stream>>>(w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag);
+        witness_kernel<true><<<grid, THREADS, smem, stream>>>(w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag);
     else
-        witness_kernel<false><<<grid, THREADS, 0, stream>>>(w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag);
+        witness_kernel<false><<<grid, THREADS, smem, stream>>>(w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag);
 }
 
 // ---- int16 coefficients -> K sign*bit planes, each CRT'd ---------------------------------------------------
 // decompose_B_vec_into_k_vec (latticefold/src/nifs/decomposition/utils.rs:45-49) + the CRT of Witness::from_f_coeff
 // (latticefold/src/arith.rs:327).  One thread per element (there are n = 98 815 of them, times K planes of work
-// each): plane k of it = sign * bit_k(|c|), transformed with the compile-time shift twiddles.
-constexpr int PLANE_THREADS = 128;
+// each): plane k of it = sign * bit_k(|c|), transformed with the compile-time shift twiddles; every output goes
+// through the coalescing tile.
+constexpr int PLANE_THREADS = 64;
 template <bool MONT>
 __global__ void __launch_bounds__(PLANE_THREADS)
 planes_kernel(const int16_t *__restrict__ f16, u64 n, int K, u64 *__restrict__ planes_f, u64 *__restrict__ planes_fx,
               u64 *__restrict__ planes_coeff) {
-    const u64 e = (u64)blockIdx.x * PLANE_THREADS + threadIdx.x;
-    if (e >= n) return;
+    __shared__ __align__(16) ulonglong2 otile[PLANE_THREADS * (FX_UNITS + 1)];  // 25.6 KB
+    const u64 e0 = (u64)blockIdx.x * PLANE_THREADS;
+    const u64 e = e0 + threadIdx.x;
+    const bool active = e < n;
+    const u32 nrows = (u32)min((u64)PLANE_THREADS, n - e0);
     int d[ring::D];
-    load_i16x24(f16 + e * ring::D, d);
+    if (active) load_i16x24(f16 + e * ring::D, d);
     for (int k = 0; k < K; ++k) {
         u64 c[ring::D];
         int pd[ring::D];
+        if (active) {
 #pragma unroll
-        for (int t = 0; t < ring::D; ++t) {
-            int a = d[t] < 0 ? -d[t] : d[t];
-            int bit = (a >> k) & 1;
-            pd[t] = d[t] < 0 ? -bit : bit;  // digit k base 2 = sign * bit_k(|c|)
+            for (int t = 0; t < ring::D; ++t) {
+                int a = d[t] < 0 ? -d[t] : d[t];
+                int bit = (a >> k) & 1;
+                pd[t] = d[t] < 0 ? -bit : bit;  // digit k base 2 = sign * bit_k(|c|)
+            }
         }
-        const u64 elem = (u64)k * n + e;
+        const u64 elem0 = (u64)k * n + e0;
         if (planes_coeff) {
+            if (active) {
 #pragma unroll
-            for (int t = 0; t < ring::D; ++t) c[t] = gl::from_small<MONT>(pd[t]);
-            store_elem(planes_coeff, elem, c);
+                for (int t = 0; t < ring::D; ++t) c[t] = gl::from_small<MONT>(pd[t]);
+                row_put(otile, threadIdx.x, c);
+            }
+            rows_out<PLAIN_UNITS>(otile, planes_coeff + elem0 * ring::D, nrows);
         }
         if (planes_f || planes_fx) {
-            ring::crt24_small<MONT>(pd, c);
-            if (planes_f) store_elem(planes_f, elem, c);
-            if (planes_fx) store_elem_fx(planes_fx, elem, c);
+            if (active) ring::crt24_small<MONT>(pd, c);
+            if (planes_f) {
+                if (active) row_put(otile, threadIdx.x, c);
+                rows_out<PLAIN_UNITS>(otile, planes_f + elem0 * ring::D, nrows);
+            }
+            if (planes_fx) {
+                if (active) row_put_fx(otile, threadIdx.x, c);
+                rows_out<FX_UNITS>(otile, planes_fx + elem0 * FX_WORDS, nrows);
+            }
         }
     }
 }
