@@ -38,6 +38,15 @@ METRIC = "ajtai_commit_ring_elems_per_s"
 UNIT = "ring elems/s"
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 # ---- synthetic inputs: independently random matrix, steady-state witness mix -----------------------------
 def uniform_fq(shape, seed):
     rng = np.random.Generator(np.random.PCG64(seed))
@@ -182,7 +191,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---- our arm -------------------------------------------------------------------------------------------------------------
@@ -360,13 +369,19 @@ def run_ours(args):
         "e2e": e2e, "gpu_launches": args.steps * (2 + (1 if world > 1 else 0)),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_vs_cpu": parity,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
+    # stdout carries exactly ONE line (the JSON): libraries that chat on fd 1 (NCCL prints its version there) are
+    # diverted to stderr for the whole run and the line is written to the saved descriptor at the end.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -148,6 +148,24 @@ int lat_ajtai_decompose_commit_dev(lat_ajtai *h, const uint64_t *f_coeff_dev, ui
 int lat_ajtai_decompose_commit_resident(lat_ajtai *h, const uint64_t *cm, uint64_t *planes_coeff,
                                         uint64_t *planes_f, uint64_t *cms);
 
+/* ---- LFFoldingProver::compute_f_0 + Witness::from_f      LF/nifs/folding.rs:110,121,258-268; LF/arith.rs:299-313
+ * (SURVEY 8 f1).  A fold step decomposes two witnesses (accumulator side, step side) into K planes each; the
+ * folded witness is f_0[j] = sum_{i < 2K} rho_i * f_i[j] over those 2K planes in CRT form, followed by
+ * f_0_coeff = iCRT(f_0).  The engine keeps the planes of the last decomposition of EACH side resident:
+ * lat_ajtai_select_side chooses which side (0 = first / accumulator, 1 = second / step witness) the following
+ * lat_ajtai_decompose_commit* calls fill.  rho: 2K ring elements in CRT form (rho_0..rho_{K-1} for side 0, then
+ * side 1).  Outputs f0 (n x 24, CRT form) and f0_coeff (n x 24, coefficient form); either may be NULL.
+ * Fails with LAT_E_INVALID_ARGUMENT until both sides have been decomposed.                                   */
+int lat_ajtai_select_side(lat_ajtai *h, int side);
+int lat_ajtai_fold_witness(lat_ajtai *h, const uint64_t *rho, uint64_t *f0, uint64_t *f0_coeff);
+int lat_ajtai_fold_witness_dev(lat_ajtai *h, const uint64_t *rho_dev, uint64_t *f0_dev, uint64_t *f0_coeff_dev);
+
+/* GadgetRecompose for &[R] in CRT form: out[i] = sum_l B^l * f[i*L + l]   (Witness::from_f / from_f_coeff rebuild
+ * w_ccs this way, LF/arith.rs:305,330; RING/balanced_decomposition/mod.rs:105-117,177-190).
+ * f: count*L elements, out: count elements.                                                                  */
+int lat_ring_gadget_recompose(const uint64_t *f, uint64_t count, uint32_t log2_b, uint32_t L, uint64_t *out, int repr,
+                              int device);
+
 /* ---- standalone batched ring transforms (no handle; run on `device`, synchronous) ----------------------------
  * CRT::elementwise_crt / ICRT::elementwise_icrt      RING/cyclotomic_ring/crt.rs:10-49 -> GOLD/ntt.rs:135-319
  * `count` ring elements; in-place allowed (in == out).  Both maps are linear, so `repr` does not matter.   */

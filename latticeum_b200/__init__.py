@@ -15,6 +15,7 @@ from .scheme import (  # noqa: F401
     GoldiLocksDP,
     KAPPA,
     LFDecompositionProver,
+    LFFoldingProver,
     N,
     W_SIZE,
     Witness,
@@ -22,6 +23,7 @@ from .scheme import (  # noqa: F401
     WrongCommitmentLength,
     WrongWitnessLength,
     from_mont,
+    gadget_recompose,
     get_fhat,
     ntt_from_scalar,
     to_mont,
@@ -29,6 +31,6 @@ from .scheme import (  # noqa: F401
 
 __all__ = [
     "AjtaiCommitmentScheme", "Commitment", "CommitmentError", "DecompositionParams", "DigitOverflow", "EngineError",
-    "GoldiLocksDP", "KAPPA", "LFDecompositionProver", "N", "W_SIZE", "Witness", "WrongAjtaiMatrixDimensions",
+    "GoldiLocksDP", "KAPPA", "LFDecompositionProver", "LFFoldingProver", "gadget_recompose", "N", "W_SIZE", "Witness", "WrongAjtaiMatrixDimensions",
     "WrongCommitmentLength", "WrongWitnessLength", "from_mont", "get_fhat", "ntt_from_scalar", "to_mont",
 ]

@@ -52,6 +52,10 @@ SIGNATURES = {
     "lat_ajtai_decompose_commit": (C.c_int, [_H, _u64p, C.c_uint64, _u64p, _u64p, _u64p, _u64p]),
     "lat_ajtai_decompose_commit_dev": (C.c_int, [_H, _u64p, C.c_uint64, _u64p, _u64p, _u64p, _u64p]),
     "lat_ajtai_decompose_commit_resident": (C.c_int, [_H, _u64p, _u64p, _u64p, _u64p]),
+    "lat_ajtai_select_side": (C.c_int, [_H, C.c_int]),
+    "lat_ajtai_fold_witness": (C.c_int, [_H, _u64p, _u64p, _u64p]),
+    "lat_ajtai_fold_witness_dev": (C.c_int, [_H, _u64p, _u64p, _u64p]),
+    "lat_ring_gadget_recompose": (C.c_int, [_u64p, C.c_uint64, C.c_uint32, C.c_uint32, _u64p, C.c_int, C.c_int]),
     "lat_ring_crt": (C.c_int, [_u64p, C.c_uint64, _u64p, C.c_int]),
     "lat_ring_icrt": (C.c_int, [_u64p, C.c_uint64, _u64p, C.c_int]),
     "lat_ring_crt_dev": (C.c_int, [_u64p, C.c_uint64, _u64p, C.c_void_p]),

@@ -86,7 +86,11 @@ struct lat_ajtai {
     DevBuf fx;           // CRT-form witness(es) in the MAC kernel's extended layout, count x n x 48 u64
     DevBuf fcoeff64;     // f_coeff as u64 for host output
     DevBuf planes;       // K x n x 24 CRT-form planes (only when a caller wants them)
-    DevBuf planes_fx;    // K x n x 48 CRT-form planes, extended layout (MAC input)
+    DevBuf planes_fx[2]; // K x n x 48 CRT-form planes, extended layout (MAC input), one buffer per fold side
+    bool side_ready[2] = {false, false};
+    int cur_side = 0;
+    DevBuf rho;          // 2K x 24
+    DevBuf f0;           // n x 24, folded witness (host-call staging)
     DevBuf planes_coeff; // K x n x 24 coefficient-form planes (host output only)
     DevBuf cms;          // up to max(K, batch) x kappa x 24
     DevBuf cm_in;        // kappa x 24
@@ -244,8 +248,8 @@ void lat_ajtai_destroy(lat_ajtai *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
-    DevBuf *bufs[] = {&h->A, &h->stage, &h->in, &h->f16, &h->f, &h->fx, &h->fcoeff64, &h->planes, &h->planes_fx,
-                      &h->planes_coeff, &h->cms, &h->cm_in, &h->ws, &h->flag};
+    DevBuf *bufs[] = {&h->A, &h->stage, &h->in, &h->f16, &h->f, &h->fx, &h->fcoeff64, &h->planes, &h->planes_fx[0], &h->planes_fx[1],
+                      &h->rho, &h->f0, &h->planes_coeff, &h->cms, &h->cm_in, &h->ws, &h->flag};
     for (DevBuf *b : bufs) b->release();
     if (h->h_flag) cudaFreeHost(h->h_flag);
     for (cudaEvent_t e : h->ev0) cudaEventDestroy(e);
@@ -419,9 +423,11 @@ int lat_ajtai_decompose_and_commit_coeff(lat_ajtai *h, const uint64_t *w_coeff, 
 static int planes_core(lat_ajtai *h, const u64 *cm_dev, u64 *planes_coeff_dev, u64 *planes_f_dev, u64 *cms_dev) {
     int st;
     u64 *pfx = nullptr;
-    if (cms_dev && h->K > 1) {
-        if ((st = h->planes_fx.ensure((size_t)h->K * h->n * lat::FX_WORDS * sizeof(u64)))) return st;
-        pfx = h->planes_fx.as<u64>();
+    {   // the extended-layout planes of this side stay resident for lat_ajtai_fold_witness
+        DevBuf &buf = h->planes_fx[h->cur_side];
+        if ((st = buf.ensure((size_t)h->K * h->n * lat::FX_WORDS * sizeof(u64)))) return st;
+        pfx = buf.as<u64>();
+        h->side_ready[h->cur_side] = true;
     }
     if (pfx || planes_f_dev || planes_coeff_dev) {
         lat::launch_planes(h->f16.as<int16_t>(), h->n, (int)h->K, h->mont, planes_f_dev, pfx, planes_coeff_dev, h->stream);
@@ -501,6 +507,73 @@ int lat_ajtai_decompose_commit_resident(lat_ajtai *h, const uint64_t *cm, uint64
         return fail(LAT_E_INVALID_ARGUMENT, "resident limbs may exceed 2^K (log2_B > K): use lat_ajtai_decompose_commit");
     }
     return planes_host(h, cm, planes_coeff, planes_f, cms);
+}
+
+// ---- compute_f_0 + Witness::from_f --------------------------------------------------------------------------------------
+int lat_ajtai_select_side(lat_ajtai *h, int side) {
+    if (!h || (side != 0 && side != 1)) return fail(LAT_E_INVALID_ARGUMENT, "side must be 0 or 1");
+    h->cur_side = side;
+    return LAT_OK;
+}
+
+int lat_ajtai_fold_witness_dev(lat_ajtai *h, const uint64_t *rho_dev, uint64_t *f0_dev, uint64_t *f0_coeff_dev) {
+    if (!h || !rho_dev) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (!h->side_ready[0] || !h->side_ready[1])
+        return fail(LAT_E_INVALID_ARGUMENT, "both sides must be decomposed first (lat_ajtai_select_side + lat_ajtai_decompose_commit)");
+    int st = h->bind();
+    if (st) return st;
+    u64 *f0 = (u64 *)f0_dev;
+    if (!f0) {
+        if ((st = h->f0.ensure(h->n * ELEM_BYTES))) return st;
+        f0 = h->f0.as<u64>();
+    }
+    const u64 *sides[2] = {h->planes_fx[0].as<u64>(), h->planes_fx[1].as<u64>()};
+    lat::launch_fold(sides, 2, (int)h->K, h->n, (const u64 *)rho_dev, h->mont, f0, h->stream);
+    CK(cudaGetLastError());
+    if (f0_coeff_dev) {
+        lat::launch_icrt(f0, (u64 *)f0_coeff_dev, h->n, h->stream);
+        CK(cudaGetLastError());
+    }
+    return LAT_OK;
+}
+
+int lat_ajtai_fold_witness(lat_ajtai *h, const uint64_t *rho, uint64_t *f0, uint64_t *f0_coeff) {
+    if (!h || !rho) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    int st = h->bind();
+    if (st) return st;
+    size_t n_bytes = h->n * ELEM_BYTES, rho_bytes = (size_t)2 * h->K * ELEM_BYTES;
+    if ((st = h->rho.ensure(rho_bytes)) || (st = h->f0.ensure(n_bytes))) return st;
+    if (f0_coeff && (st = h->in.ensure(n_bytes))) return st;
+    CK(cudaMemcpyAsync(h->rho.p, rho, rho_bytes, cudaMemcpyHostToDevice, h->stream));
+    st = lat_ajtai_fold_witness_dev(h, h->rho.as<uint64_t>(), h->f0.as<uint64_t>(), f0_coeff ? h->in.as<uint64_t>() : nullptr);
+    if (st) return st;
+    if (f0) CK(cudaMemcpyAsync(f0, h->f0.p, n_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (f0_coeff) CK(cudaMemcpyAsync(f0_coeff, h->in.p, n_bytes, cudaMemcpyDeviceToHost, h->stream));
+    return h->finish();
+}
+
+int lat_ring_gadget_recompose(const uint64_t *f, uint64_t count, uint32_t log2_b, uint32_t L, uint64_t *out, int repr,
+                              int device) {
+    (void)repr;  // a scalar multiple and sums: the same in either representation
+    if (count == 0) return LAT_OK;
+    if (!f || !out) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (log2_b < 1 || log2_b > 62 || L < 1) return fail(LAT_E_INVALID_ARGUMENT, "need 1<=log2_b<=62, L>=1");
+    CK(cudaSetDevice(device));
+    DevBuf din, dout;
+    int st;
+    if ((st = din.ensure(count * L * ELEM_BYTES)) || (st = dout.ensure(count * ELEM_BYTES))) {
+        din.release(); dout.release();
+        return st;
+    }
+    cudaError_t e = cudaMemcpy(din.p, f, count * L * ELEM_BYTES, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        lat::launch_recompose(din.as<u64>(), count, (int)log2_b, (int)L, dout.as<u64>(), nullptr);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout.p, count * ELEM_BYTES, cudaMemcpyDeviceToHost);
+    din.release(); dout.release();
+    if (e != cudaSuccess) return fail_cuda(e, "lat_ring_gadget_recompose", __LINE__);
+    return LAT_OK;
 }
 
 // ---- standalone transforms ---------------------------------------------------------------------------------------

@@ -81,6 +81,14 @@ void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_str
 // cms[0] = cm - sum_{k=1..K-1} 2^k cms[k]      (LF/nifs/decomposition.rs:189-197)
 void launch_y0(const u64 *cm, u64 *cms, uint32_t K, uint32_t kappa, cudaStream_t stream);
 
+// f0[j] = sum_{i < nplanes} rho[i] (*) planes[i][j]  (slot-wise Fq3), planes given as `nsides` extended-layout
+// buffers of planes_per_side x n x 48 each.  rho: nplanes x 24 in the caller's representation.  f0: n x 24.
+void launch_fold(const u64 *const *sides_fx, int nsides, int planes_per_side, u64 n, const u64 *rho, bool mont, u64 *f0,
+                 cudaStream_t stream);
+
+// out[i] = sum_l (2^log2b)^l * f[i*L + l], CRT form (scalar multiples, so any representation)
+void launch_recompose(const u64 *f, u64 count, int log2b, int L, u64 *out, cudaStream_t stream);
+
 // out[i] = sum_{p < count} parts[p * words + i] mod q
 void launch_commitment_sum(const u64 *parts, uint32_t count, u64 words, u64 *out, cudaStream_t stream);
 

@@ -413,6 +413,66 @@ void launch_y0(const u64 *cm, u64 *cms, uint32_t K, uint32_t kappa, cudaStream_t
     y0_kernel<<<(nwords + 255) / 256, 256, 0, stream>>>(cm, cms, K, nwords);
 }
 
+// ---- compute_f_0: f0[j] = sum_i rho_i (*) f_i[j] over the 2K resident planes (LF/nifs/folding.rs:258-268) --------------
+// One thread per (element, slot): it walks the planes (a 48-byte extended-layout slot each, consecutive threads read
+// consecutive slots), multiplies by rho_i's slot from shared memory and accumulates lazily with the same Karatsuba
+// accumulators as the MAC; one reduction at the end.  HBM-bound on reading the planes once (2K x n x 384 B).
+constexpr int FOLD_MAX_PLANES = 64;
+template <bool MONT>
+__global__ void __launch_bounds__(256)
+fold_kernel(const u64 *__restrict__ s0, const u64 *__restrict__ s1, int nsides, int pps, u64 n, const u64 *__restrict__ rho,
+            u64 *__restrict__ f0) {
+    __shared__ u64 s_rho[FOLD_MAX_PLANES * ring::D];
+    const int nplanes = nsides * pps;
+    for (int i = threadIdx.x; i < nplanes * ring::D; i += blockDim.x) {
+        u64 v = rho[i];
+        s_rho[i] = MONT ? gl::from_mont(v) : gl::reduce128(v, 0);  // canonical(rho) * repr(f) = repr(rho * f)
+    }
+    __syncthreads();
+    const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;  // (element, slot)
+    if (idx >= n * ring::NSLOT) return;
+    const u32 sl = (u32)(idx & 7);
+    gl::Fq3Acc acc;
+    acc.clear();
+    for (int side = 0; side < nsides; ++side) {
+        const u64 *base = (side == 0 ? s0 : s1) + idx * 6;
+        for (int k = 0; k < pps; ++k) {
+            const ulonglong2 *pf = reinterpret_cast<const ulonglong2 *>(base + (u64)k * n * FX);
+            ulonglong2 x = __ldg(pf), y = __ldg(pf + 1), z = __ldg(pf + 2);
+            const u64 *r = s_rho + (side * pps + k) * ring::D + 3 * sl;
+            acc.mac(r[0], r[1], r[2], x.x, x.y, y.x, y.y, z.x, z.y);
+        }
+    }
+    u64 c0, c1, c2;
+    acc.finish(c0, c1, c2);
+    u64 *o = f0 + idx * 3;  // element * 24 + slot * 3
+    o[0] = c0; o[1] = c1; o[2] = c2;
+}
+void launch_fold(const u64 *const *sides_fx, int nsides, int planes_per_side, u64 n, const u64 *rho, bool mont, u64 *f0,
+                 cudaStream_t stream) {
+    if (!n) return;
+    unsigned grid = (unsigned)((n * ring::NSLOT + 255) / 256);
+    const u64 *a = sides_fx[0], *b = nsides > 1 ? sides_fx[1] : nullptr;
+    if (mont) fold_kernel<true><<<grid, 256, 0, stream>>>(a, b, nsides, planes_per_side, n, rho, f0);
+    else fold_kernel<false><<<grid, 256, 0, stream>>>(a, b, nsides, planes_per_side, n, rho, f0);
+}
+
+// ---- gadget_recompose in CRT form: Horner from the top limb, result = result * B + v_l ---------------------------------
+__global__ void __launch_bounds__(256)
+recompose_kernel(const u64 *__restrict__ f, u64 nwords, int L, u64 bq, u64 *__restrict__ out) {
+    const u64 i = (u64)blockIdx.x * 256 + threadIdx.x;  // (element, word)
+    if (i >= nwords) return;
+    const u64 e = i / ring::D, t = i - e * ring::D;
+    u64 acc = 0;
+    for (int l = L - 1; l >= 0; --l) acc = gl::add(gl::mul(acc, bq), gl::reduce128(f[(e * L + l) * ring::D + t], 0));
+    out[i] = acc;
+}
+void launch_recompose(const u64 *f, u64 count, int log2b, int L, u64 *out, cudaStream_t stream) {
+    u64 nwords = count * ring::D;
+    if (!nwords) return;
+    recompose_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, stream>>>(f, nwords, L, 1ull << log2b, out);
+}
+
 // Sum of `count` partial commitments mod q (column-sharded multi-GPU exchange).
 __global__ void __launch_bounds__(256)
 commitment_sum_kernel(const u64 *__restrict__ parts, uint32_t count, u64 words, u64 *__restrict__ out) {

@@ -386,9 +386,13 @@ class LFDecompositionProver:
     """The two private helpers of latticefold/src/nifs/decomposition.rs the engine replaces."""
 
     @staticmethod
-    def decompose_and_commit(scheme: AjtaiCommitmentScheme, wit_f_coeff, cm: Commitment, want_planes: bool = True):
+    def decompose_and_commit(scheme: AjtaiCommitmentScheme, wit_f_coeff, cm: Commitment, want_planes: bool = True,
+                             side: int = 0):
         """decompose_witness (:162-167) + commit_witnesses (:178-201) in one engine call.
-        Returns (wit_s, y_s): K witnesses (or None) and K commitments, y_0 by homomorphism."""
+        Returns (wit_s, y_s): K witnesses (or None) and K commitments, y_0 by homomorphism.
+        `side` (0 = accumulator, 1 = step witness; zk_latticefold.rs:60-71) says which resident plane buffer the
+        engine fills, for LFFoldingProver.compute_f_0 later."""
+        _raise(capi.lib().lat_ajtai_select_side(scheme._h, side))
         fc = _as_u64(wit_f_coeff, "f_coeff").reshape(-1, D)
         K, n, kappa = scheme.params.K, fc.shape[0], scheme._kappa
         pc = np.empty((K, n, D), np.uint64) if want_planes else None
@@ -421,6 +425,33 @@ class LFDecompositionProver:
         for y in reversed(ys):
             acc = (acc + y) * b
         return [cm - acc] + ys
+
+
+class LFFoldingProver:
+    """The witness-side tail of latticefold/src/nifs/folding.rs the engine replaces."""
+
+    @staticmethod
+    def compute_f_0(scheme: AjtaiCommitmentScheme, rho_s, want_f_coeff: bool = True) -> Witness:
+        """compute_f_0 (:258-268): f_0 = sum_i rho_i * f_i over the 2K planes left resident by the two
+        decompose_and_commit calls (side 0 then side 1), followed by Witness::from_f's iCRT (arith.rs:299-313).
+        rho_s: (2K, 24) CRT-form challenges.  Returns a Witness with f = f_0 and f_coeff = iCRT(f_0)."""
+        rho = _as_u64(rho_s, "rho_s").reshape(-1, D)
+        if rho.shape[0] != 2 * scheme.params.K:
+            raise ValueError("need 2K challenges")
+        f0 = np.empty((scheme._n, D), np.uint64)
+        fc = np.empty((scheme._n, D), np.uint64) if want_f_coeff else None
+        _raise(capi.lib().lat_ajtai_fold_witness(scheme._h, _ptr(rho), _ptr(f0), _ptr(fc)))
+        return Witness(None, f0, fc, scheme.mont)
+
+
+def gadget_recompose(f, params: DecompositionParams = GoldiLocksDP, device: int = 0) -> np.ndarray:
+    """GadgetRecompose for &[R] in CRT form (balanced_decomposition/mod.rs:177-190): rebuilds w_ccs from f
+    (Witness::from_f / from_f_coeff, arith.rs:305,330)."""
+    f = _as_u64(f, "f").reshape(-1, D)
+    count = f.shape[0] // params.L
+    out = np.empty((count, D), np.uint64)
+    _raise(capi.lib().lat_ring_gadget_recompose(_ptr(f), count, params.log2_B, params.L, _ptr(out), 0, device))
+    return out
 
 
 # ---- helpers ----------------------------------------------------------------------------------------------------------------

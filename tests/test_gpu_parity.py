@@ -368,6 +368,41 @@ def test_zkvm_fold_step_properties(zkvm):
     assert scheme.commit(s) == scheme.commit(wit.f) + scheme.commit(f2)
 
 
+@pytest.mark.parametrize("mont", [False, True], ids=["canonical", "montgomery"])
+def test_fold_witness_compute_f0_vs_oracle(mont):
+    # LF/nifs/folding.rs:258-268 (compute_f_0) + LF/arith.rs:299-313 (Witness::from_f) on the resident planes
+    kappa, n = 8, 1500
+    A = CO.fill_uniform((kappa, n, 24), 91)
+    scheme = make_scheme(A, mont)
+    sides, planes = [], []
+    for side in (0, 1):
+        fc, _ = small_coeffs(n, 92 + side, 2**15 - 1)
+        cm = CO.commit(A, CO.crt(fc))
+        LB.LFDecompositionProver.decompose_and_commit(scheme, maybe_mont(fc, mont), LB.Commitment(maybe_mont(cm, mont), mont),
+                                                      want_planes=False, side=side)
+        planes += list(CO.decompose_commit(A, fc, cm, 2, DP.K)[1])
+    rho = CO.fill_uniform((2 * DP.K, 24), 95)
+    wit = LB.LFFoldingProver.compute_f_0(scheme, maybe_mont(rho, mont))
+    exp_f0 = CO.compute_f0(rho, planes)
+    assert np.array_equal(unmont(wit.f, mont), exp_f0)
+    assert np.array_equal(unmont(wit.f_coeff, mont), CO.icrt(exp_f0))
+    scheme.close()
+    # needs both sides
+    s2 = make_scheme(A)
+    with pytest.raises(LB.EngineError):
+        LB.LFFoldingProver.compute_f_0(s2, rho)
+    s2.close()
+
+
+def test_gadget_recompose_vs_oracle():
+    # RING/balanced_decomposition/mod.rs:177-190 in CRT form: recompose(from_w_ccs(w).f) == w  (LF/arith.rs:516-548)
+    w = CO.fill_uniform((333, 24), 96)
+    f_coeff, f = CO.witness_from_w_ccs(w, DP.B, DP.L)
+    got = LB.gadget_recompose(f)
+    assert np.array_equal(got, CO.gadget_recompose_ntt(f, DP.B, DP.L))
+    assert np.array_equal(got, w)
+
+
 def test_cpp_host_mirror_example():
     # latticeum_b200/host/ajtai.hpp: the C++ mirror of the reference API, on the reference's closed-form commit test
     import subprocess
