@@ -56,11 +56,15 @@ def report(tag, path):
     txt = subprocess.check_output(["ncu", "-i", path, "--page", "raw", "--csv"], text=True, stderr=subprocess.DEVNULL)
     rows = list(csv.reader(txt.splitlines()))
     hdr, units = rows[0], rows[1]
-    for r in rows[2:3]:
+    seen = set()
+    for r in rows[2:]:
         d = dict(zip(hdr, r))
         u = dict(zip(hdr, units))
         name = re.sub(r"\(.*", "", d["Kernel Name"]).replace("void ", "").replace("lat::", "")
         short = re.sub(r"[^a-z0-9_]+", "_", name.lower()).strip("_")
+        if short in seen:
+            continue
+        seen.add(short)
         out = {"kernel": d["Kernel Name"], "source_report": os.path.basename(path),
                "command": "ncu --set full --clock-control none --import-source on -k regex:<kernel> python bench.py --steps 2 --warmup 1 --no-cpu"}
         for k in KEYS:
@@ -77,7 +81,7 @@ def report(tag, path):
         dst = os.path.join(ROOT, "profiles", f"{tag}_{short}.json")
         json.dump(out, open(dst, "w"), indent=1)
         print(dst, "dur", out.get("gpu__time_duration.sum"), "dram bytes", rd + wr)
-        if "mac_kernel" in name:
+        if "mac_kernel<1" in name.replace(" ", ""):
             json.dump({"kernel": d["Kernel Name"], "dram_bytes_per_launch": rd + wr, "from": f"profiles/{tag}_{short}.json"},
                       open(os.path.join(ROOT, "profiles", "mac_kernel_traffic.json"), "w"), indent=1)
 
