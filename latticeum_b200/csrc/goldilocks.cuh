@@ -20,14 +20,56 @@ constexpr u64 Q = 0xFFFFFFFF00000001ull;
 constexpr u64 EPS = 0xFFFFFFFFull;  // 2^64 mod q
 constexpr u64 Q_HALF = (Q - 1) / 2;
 
+// Canonical add / sub.  On the device they are carry chains (5 and 7 instructions; the compare-and-select forms the
+// compiler derives from the C versions cost 8 and 11, and these two are most of what the ring transforms execute):
+//   sub: d = a - b; on borrow add q, i.e. subtract 2^32 - 1 (mod 2^64)
+//   add: a + b = a - (q - b), and q - b is a 2-instruction borrow chain (b = 0 gives q, which sub handles)
+__host__ __device__ __forceinline__ u64 sub(u64 a, u64 b) {
+#ifdef __CUDA_ARCH__
+    u64 d;
+    asm("{\n\t"
+        ".reg .u32 al, ah, bl, bh, m;\n\t"
+        "mov.b64 {al, ah}, %1;\n\t"
+        "mov.b64 {bl, bh}, %2;\n\t"
+        "sub.cc.u32 al, al, bl;\n\t"
+        "subc.cc.u32 ah, ah, bh;\n\t"
+        "subc.u32 m, 0, 0;\n\t"          // 0xFFFFFFFF on borrow, else 0
+        "sub.cc.u32 al, al, m;\n\t"
+        "subc.u32 ah, ah, 0;\n\t"
+        "mov.b64 %0, {al, ah};\n\t"
+        "}"
+        : "=l"(d)
+        : "l"(a), "l"(b));
+    return d;
+#else
+    u64 d = a - b;
+    return (a < b) ? d - EPS : d;  // + q (mod 2^64)
+#endif
+}
 __host__ __device__ __forceinline__ u64 add(u64 a, u64 b) {
+#ifdef __CUDA_ARCH__
+    u64 d;
+    asm("{\n\t"
+        ".reg .u32 al, ah, bl, bh, m;\n\t"
+        "mov.b64 {al, ah}, %1;\n\t"
+        "mov.b64 {bl, bh}, %2;\n\t"
+        "sub.cc.u32 bl, 1, bl;\n\t"          // q - b = (0xFFFFFFFF : 1) - (bh : bl)
+        "subc.u32 bh, 0xFFFFFFFF, bh;\n\t"
+        "sub.cc.u32 al, al, bl;\n\t"
+        "subc.cc.u32 ah, ah, bh;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 al, al, m;\n\t"
+        "subc.u32 ah, ah, 0;\n\t"
+        "mov.b64 %0, {al, ah};\n\t"
+        "}"
+        : "=l"(d)
+        : "l"(a), "l"(b));
+    return d;
+#else
     u64 s = a + b;
     u64 t = s + EPS;  // s - q (mod 2^64); overflows iff s >= q
     return ((s < a) | (t < s)) ? t : s;
-}
-__host__ __device__ __forceinline__ u64 sub(u64 a, u64 b) {
-    u64 d = a - b;
-    return (a < b) ? d - EPS : d;  // + q (mod 2^64)
+#endif
 }
 __host__ __device__ __forceinline__ u64 neg(u64 a) { return a ? Q - a : 0; }
 
