@@ -219,7 +219,7 @@ def run_ours(args):
     for i in range(KAPPA):
         scheme.upload_rows(i, matrix_row(rank, i)[None])
     eng = DeviceScheme(scheme)
-    sharded = ShardedAjtaiScheme(eng, world, rank)
+    sharded = ShardedAjtaiScheme(eng, world, rank, exchange=os.environ.get("LAT_EXCHANGE", "auto"))
     w_host = steady_state_w(rank)
     w_dev = eng.to_device(w_host)
     partial = eng.new_commitment()
@@ -363,7 +363,8 @@ def run_ours(args):
         "config": {"workload": "zkvm_step_witness_commit", "kappa": KAPPA, "w_len": W_LEN, "n_per_gpu": N_COLS,
                    "n_total": world * N_COLS, "d": 24, "B": 1 << LOG2_B, "L": L_LIMBS,
                    "pipeline": "iCRT -> gadget_decompose(2^15,5) -> CRT -> A*f (Witness::from_w_ccs + commit)",
-                   "sharding": f"columns x{world}" + (", NCCL all-gather of 6 KB partials + mod-q fold" if world > 1 else ""),
+                   "sharding": f"columns x{world}" + (f", 6 KB partial commitments exchanged and folded mod q; exchange = {sharded.exchange}"
+                                                        if world > 1 else ""),
                    "l2": "inputs larger than L2 (607 MB matrix streamed every step)"},
         "commitments_per_s": args.steps / (elapsed_ms * 1e-3),
         "e2e": e2e, "gpu_launches": args.steps * (2 + (1 if world > 1 else 0)),

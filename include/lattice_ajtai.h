@@ -187,6 +187,18 @@ int lat_commitment_sum_dev(const uint64_t *parts_dev, uint32_t count, uint64_t w
                            void *cuda_stream);
 int lat_commitment_sum(const uint64_t *parts, uint32_t count, uint64_t words, uint64_t *out, int device);
 
+/* Fused exchange + fold over NVLink peer memory (one kernel per rank, no NCCL call on the data path).
+ * Every rank owns a receive buffer of 2 x world x words u64 and a flag array of 2 x world u64 (zero-initialised),
+ * both mapped into every peer (e.g. torch symmetric memory / cudaIpc).  recv_ptrs[r] and flag_ptrs[r] are the
+ * addresses, valid on THIS GPU, of rank r's buffer and flags (r = rank: the local ones).  The kernel stores this
+ * rank's partial into slot (epoch & 1) of every rank's buffer, fences, raises flag[rank] = epoch on every rank,
+ * waits until all `world` local flags show `epoch`, and folds the received partials mod q into out_dev.
+ * `epoch` must start at 1 and grow by 1 per call on every rank; two slots suffice because a rank can only reach
+ * call e+2 after every peer finished reading call e (it needs their call e+1 data first).                      */
+int lat_commitment_exchange_dev(const uint64_t *partial_dev, uint64_t words, int rank, int world,
+                                const uint64_t *recv_ptrs, const uint64_t *flag_ptrs, uint64_t epoch,
+                                uint64_t *out_dev, void *cuda_stream);
+
 /* ---- diagnostics: CUDA-event timing of the dominant kernel (bench.py's roofline leg) ---------------------------
  * While enabled, every mac_kernel launch (the matrix-vector kernel alone, not its tiny reduce) is bracketed by a
  * pair of events on the handle's stream, taken from a pool so that nothing synchronises inside a timed loop.

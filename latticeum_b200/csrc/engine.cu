@@ -680,6 +680,22 @@ int lat_commitment_sum_dev(const uint64_t *parts_dev, uint32_t count, uint64_t w
     CK(cudaGetLastError());
     return LAT_OK;
 }
+int lat_commitment_exchange_dev(const uint64_t *partial_dev, uint64_t words, int rank, int world,
+                                const uint64_t *recv_ptrs, const uint64_t *flag_ptrs, uint64_t epoch,
+                                uint64_t *out_dev, void *cuda_stream) {
+    if (!partial_dev || !recv_ptrs || !flag_ptrs || !out_dev) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (world < 1 || world > lat::MAX_PEERS || rank < 0 || rank >= world || epoch == 0)
+        return fail(LAT_E_INVALID_ARGUMENT, "need 1 <= world <= 16, 0 <= rank < world, epoch >= 1");
+    lat::PeerPtrs peers{};
+    for (int r = 0; r < world; ++r) {
+        peers.recv[r] = reinterpret_cast<u64 *>(recv_ptrs[r]);
+        peers.flags[r] = reinterpret_cast<u64 *>(flag_ptrs[r]);
+    }
+    lat::launch_exchange((const u64 *)partial_dev, words, rank, world, peers, epoch, (u64 *)out_dev, (cudaStream_t)cuda_stream);
+    CK(cudaGetLastError());
+    return LAT_OK;
+}
+
 int lat_commitment_sum(const uint64_t *parts, uint32_t count, uint64_t words, uint64_t *out, int device) {
     if (words == 0) return LAT_OK;
     if (!parts || !out) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");

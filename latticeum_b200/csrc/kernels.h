@@ -92,4 +92,13 @@ void launch_recompose(const u64 *f, u64 count, int log2b, int L, u64 *out, cudaS
 // out[i] = sum_{p < count} parts[p * words + i] mod q
 void launch_commitment_sum(const u64 *parts, uint32_t count, u64 words, u64 *out, cudaStream_t stream);
 
+// Peer-memory exchange + fold (see lat_commitment_exchange_dev).  recv/flags: up to 16 peer-mapped addresses.
+constexpr int MAX_PEERS = 16;
+struct PeerPtrs {
+    u64 *recv[MAX_PEERS];
+    u64 *flags[MAX_PEERS];
+};
+void launch_exchange(const u64 *partial, u64 words, int rank, int world, const PeerPtrs &peers, u64 epoch, u64 *out,
+                     cudaStream_t stream);
+
 }  // namespace lat

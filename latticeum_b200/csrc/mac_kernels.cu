@@ -473,6 +473,48 @@ void launch_recompose(const u64 *f, u64 count, int log2b, int L, u64 *out, cudaS
     recompose_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, stream>>>(f, nwords, L, 1ull << log2b, out);
 }
 
+// ---- fused exchange + fold of the column-shard partial commitments over NVLink peer memory --------------------------------
+// One block per rank.  Push: plain stores of the 6 KB partial into every rank's receive slot (peer addresses go out over
+// NVLink), a system-scope fence, then one release store per peer flag.  Pull: spin on the local flags with acquire loads
+// until all ranks have delivered, then sum the `world` partials mod q from the local buffer (volatile loads: the data
+// was written by other GPUs).
+__global__ void __launch_bounds__(256)
+exchange_kernel(const u64 *__restrict__ partial, u64 words, int rank, int world, PeerPtrs peers, u64 epoch,
+                u64 *__restrict__ out) {
+    const u64 slot = epoch & 1;
+    for (int r = 0; r < world; ++r) {
+        u64 *dst = peers.recv[r] + (slot * world + rank) * words;
+        for (u64 i = threadIdx.x; i < words; i += blockDim.x) dst[i] = partial[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        u64 *f = peers.flags[threadIdx.x] + slot * world + rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+        const u64 *mine = peers.flags[rank] + slot * world + threadIdx.x;
+        u64 v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+        } while (v != epoch);
+    }
+    __syncthreads();
+    __threadfence_system();
+    const volatile u64 *rb = peers.recv[rank] + slot * world * words;
+    for (u64 i = threadIdx.x; i < words; i += blockDim.x) {
+        u64 lo = 0, hi = 0;
+        for (int r = 0; r < world; ++r) {
+            u64 v = rb[(u64)r * words + i];
+            lo += v;
+            hi += (lo < v);
+        }
+        out[i] = gl::reduce128(lo, hi);
+    }
+}
+void launch_exchange(const u64 *partial, u64 words, int rank, int world, const PeerPtrs &peers, u64 epoch, u64 *out,
+                     cudaStream_t stream) {
+    exchange_kernel<<<1, 256, 0, stream>>>(partial, words, rank, world, peers, epoch, out);
+}
+
 // Sum of `count` partial commitments mod q (column-sharded multi-GPU exchange).
 __global__ void __launch_bounds__(256)
 commitment_sum_kernel(const u64 *__restrict__ parts, uint32_t count, u64 words, u64 *__restrict__ out) {

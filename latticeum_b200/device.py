@@ -89,6 +89,18 @@ class DeviceScheme:
         _raise(capi.lib().lat_commitment_sum_dev(parts.data_ptr(), parts.shape[0], words, out.data_ptr(), C.c_void_p(s)))
         return out
 
+    def exchange_partials(self, partial: torch.Tensor, out: torch.Tensor, peer) -> torch.Tensor:
+        """Fused NVLink exchange + mod-q fold of this rank's partial commitment with all peers (`peer` is a
+        latticeum_b200.sharded.PeerExchange).  Asynchronous on torch's current stream."""
+        peer.epoch += 1
+        n = peer.world
+        recv = (C.c_uint64 * n)(*peer.recv_ptrs)
+        flags = (C.c_uint64 * n)(*peer.flag_ptrs)
+        s = torch.cuda.current_stream(self.device).cuda_stream or 1
+        _raise(capi.lib().lat_commitment_exchange_dev(partial.data_ptr(), partial.numel(), peer.rank, n, recv, flags,
+                                                      peer.epoch, out.data_ptr(), C.c_void_p(s)))
+        return out
+
     def synchronize(self) -> None:
         _raise(capi.lib().lat_ajtai_synchronize(self.scheme._h))
 

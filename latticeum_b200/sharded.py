@@ -23,12 +23,41 @@ def shard_bounds(total: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class PeerExchange:
+    """NVLink peer-memory state for the fused exchange + fold kernel (lat_commitment_exchange_dev): a receive buffer
+    of 2 x world x max_words u64 and 2 x world flags per rank, allocated as torch symmetric memory so that every
+    rank holds addresses of every peer's buffers.  One kernel per rank per exchange, no NCCL call on the data path."""
+
+    def __init__(self, device: torch.device, world: int, rank: int, max_words: int, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank, self.max_words = world, rank, max_words
+        self.recv = symm_mem.empty(2 * world * max_words, dtype=torch.int64, device=device)
+        self.flags = symm_mem.empty(2 * world, dtype=torch.int64, device=device)
+        self.recv.zero_()
+        self.flags.zero_()
+        h_recv = symm_mem.rendezvous(self.recv, group)
+        h_flags = symm_mem.rendezvous(self.flags, group)
+        self.recv_ptrs = [int(p) for p in h_recv.buffer_ptrs]
+        self.flag_ptrs = [int(p) for p in h_flags.buffer_ptrs]
+        self._handles = (h_recv, h_flags)
+        self.epoch = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)  # every rank's flags are zero before anyone raises one
+
+
 class ShardedAjtaiScheme:
     """Commitment over a column-sharded matrix.  `engine` is this rank's local engine front end and must offer
     witness_commit(w_local, cm) / commit_ntt(f_local, cm) / fold_partials(parts, out) / new_commitment(batch)
-    (latticeum_b200.device.DeviceScheme on a GPU)."""
+    (latticeum_b200.device.DeviceScheme on a GPU).
 
-    def __init__(self, engine, world: Optional[int] = None, rank: Optional[int] = None, group=None):
+    exchange = "nccl": all-gather of the partials over NCCL + a fold kernel;
+    exchange = "p2p" : the engine's fused peer-memory kernel (needs an engine with `exchange_partials` and CUDA peers);
+    exchange = "auto": "p2p" when it can be set up, else "nccl"."""
+
+    def __init__(self, engine, world: Optional[int] = None, rank: Optional[int] = None, group=None,
+                 exchange: str = "nccl", max_batch: int = 32):
         self.engine = engine
         self.group = group
         if world is None:
@@ -37,10 +66,24 @@ class ShardedAjtaiScheme:
             rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world, self.rank = world, rank
         self._gather = None
+        self.peer: Optional[PeerExchange] = None
+        self.exchange = "none" if world == 1 else "nccl"
+        if world > 1 and exchange in ("p2p", "auto") and hasattr(engine, "exchange_partials"):
+            try:
+                self.peer = PeerExchange(engine.device, world, rank, max_batch * engine.kappa * 24, group)
+                self.exchange = "p2p"
+            except Exception as e:  # pragma: no cover - depends on the box
+                if exchange == "p2p":
+                    raise
+                self.peer = None
+                self.exchange = f"nccl (p2p unavailable: {type(e).__name__})"
 
     def _exchange(self, partial: torch.Tensor) -> torch.Tensor:
         if self.world == 1:
             return partial
+        if self.peer is not None and partial.numel() <= self.peer.max_words:
+            out = torch.empty_like(partial)
+            return self.engine.exchange_partials(partial, out, self.peer)
         if self._gather is None or self._gather.shape[1:] != partial.shape or self._gather.device != partial.device:
             self._gather = torch.empty((self.world,) + tuple(partial.shape), dtype=partial.dtype, device=partial.device)
         # flat views: gloo's all-gather wants a 1-D output of world * numel; NCCL accepts the same

@@ -403,6 +403,35 @@ def test_gadget_recompose_vs_oracle():
     assert np.array_equal(got, w)
 
 
+def test_commitment_sum_and_single_rank_exchange():
+    # lat_commitment_sum (SURVEY 8e fold of column-shard partials) and the fused exchange kernel with world = 1
+    # (multi-rank runs need real peers: tools/mgpu_check.py under torchrun; a spinning multi-rank emulation on one
+    # GPU is not safe)
+    import ctypes as C
+
+    import torch
+
+    L = capi.lib()
+    parts = CO.fill_uniform((5, 7 * 24), 123)
+    out = np.empty(7 * 24, np.uint64)
+    assert L.lat_commitment_sum(parts.ctypes.data, 5, 7 * 24, out.ctypes.data, 0) == 0, capi.last_error()
+    assert out.tolist() == [int(v) % Q for v in parts.astype(object).sum(axis=0)]
+    words = 32 * 24
+    partial = torch.from_numpy(CO.fill_uniform((words,), 124).view(np.int64)).cuda()
+    recv = torch.zeros(2 * words, dtype=torch.int64, device="cuda")
+    flags = torch.zeros(2, dtype=torch.int64, device="cuda")
+    res = torch.empty(words, dtype=torch.int64, device="cuda")
+    rp, fp = (C.c_uint64 * 1)(recv.data_ptr()), (C.c_uint64 * 1)(flags.data_ptr())
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream or 1)
+    for epoch in (1, 2, 3):
+        st = L.lat_commitment_exchange_dev(partial.data_ptr(), words, 0, 1, rp, fp, epoch, res.data_ptr(), stream)
+        assert st == 0, capi.last_error()
+        torch.cuda.synchronize()
+        assert torch.equal(res, partial)
+    assert flags.tolist() == [2, 3]
+    assert L.lat_commitment_exchange_dev(partial.data_ptr(), words, 0, 1, rp, fp, 0, res.data_ptr(), stream) == capi.LAT_E_INVALID_ARGUMENT
+
+
 def test_cpp_host_mirror_example():
     # latticeum_b200/host/ajtai.hpp: the C++ mirror of the reference API, on the reference's closed-form commit test
     import subprocess

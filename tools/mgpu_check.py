@@ -28,8 +28,11 @@ from latticeum_b200 import _capi as capi
 st = capi.lib().lat_ajtai_upload_rows(scheme._h, 0, KAPPA, A.ctypes.data + lo * L * 24 * 8, n_total)
 assert st == 0, capi.last_error()
 eng = DeviceScheme(scheme)
-sh = ShardedAjtaiScheme(eng)
-cm = sh.witness_commit(eng.to_device(w[lo:hi]))
+mode = os.environ.get("LAT_EXCHANGE", "auto")
+sh = ShardedAjtaiScheme(eng, exchange=mode)
+w_dev = eng.to_device(w[lo:hi])
+for _ in range(5):  # several epochs: exercises both receive slots
+    cm = sh.witness_commit(w_dev)
 torch.cuda.synchronize()
 got = DeviceScheme.to_numpy(cm)
 ok = True
@@ -37,7 +40,7 @@ if rank == 0:
     _, f = CO.witness_from_w_ccs(w, 1 << 15, L)
     exp = CO.commit(A, f)
     ok = bool(np.array_equal(got, exp))
-    print(f"mgpu_check world={world}: sharded commitment {'==' if ok else '!='} oracle (n_total={n_total})", flush=True)
+    print(f"mgpu_check world={world} exchange={sh.exchange}: sharded commitment {'==' if ok else '!='} oracle (n_total={n_total})", flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, 0)
 dist.barrier()
