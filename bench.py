@@ -278,7 +278,8 @@ def run_ours(args):
         cm_e2e = np.ctypeslib.as_array(C.cast(hcm, C.POINTER(C.c_uint64)), shape=(KAPPA, 24)).copy()
         e2e = {"value": N_COLS * args.steps / (t1 - t0), "unit": UNIT, "h2d_bytes_per_step": W_LEN * ELEM_B,
                "d2h_bytes_per_step": KAPPA * ELEM_B + 4, "ms_per_step": (t1 - t0) / args.steps * 1e3,
-               "api": "lat_ajtai_witness_from_w_ccs(w_ccs_host_pinned) -> cm_host; witness stays device-resident"}
+               "api": "lat_ajtai_witness_from_w_ccs(w_ccs_host_pinned) -> cm_host; the witness kernel reads the pinned w_ccs "
+                      "over PCIe (zero-copy, counted as h2d bytes), the commitment is copied back; witness stays device-resident"}
         # the full drop-in (Witness with f and f_coeff materialised on the host, as the reference's struct holds them)
         hf, hfc = C.c_void_p(), C.c_void_p()
         L.lat_host_alloc(C.byref(hf), N_COLS * ELEM_B)

@@ -74,6 +74,8 @@ struct lat_ajtai {
     u64 n = 0;
     lat::MatLayout lay{};
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr;          // host-call uploads, pipelined against the kernels
+    cudaEvent_t copy_done[4] = {nullptr, nullptr, nullptr, nullptr}, work_done = nullptr;
 
     DevBuf A;            // re-laid-out matrix, canonical form
     std::vector<uint8_t> row_done;
@@ -223,6 +225,10 @@ int lat_ajtai_create(lat_ajtai **out, uint32_t kappa, uint64_t n, uint32_t log2_
         if ((e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) break;
         if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) break;
         h->stream = h->own_stream;
+        if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) break;
+        for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->copy_done[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) break;
+        if ((e = cudaEventCreateWithFlags(&h->work_done, cudaEventDisableTiming)) != cudaSuccess) break;
         if ((e = cudaHostAlloc((void **)&h->h_flag, sizeof(int), cudaHostAllocDefault)) != cudaSuccess) break;
         size_t a_bytes = h->lay.total_elems() * sizeof(u64);
         if ((st = h->A.ensure(a_bytes))) break;
@@ -254,6 +260,10 @@ void lat_ajtai_destroy(lat_ajtai *h) {
     if (h->h_flag) cudaFreeHost(h->h_flag);
     for (cudaEvent_t e : h->ev0) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev1) cudaEventDestroy(e);
+    for (cudaEvent_t ev : h->copy_done)
+        if (ev) cudaEventDestroy(ev);
+    if (h->work_done) cudaEventDestroy(h->work_done);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -395,10 +405,50 @@ static int witness_host(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool in
     if ((st = h->in.ensure(in_bytes))) return st;
     if (f_coeff && (st = h->fcoeff64.ensure(n_bytes))) return st;
     if (f && (st = h->f.ensure(n_bytes))) return st;
-    CK(cudaMemcpyAsync(h->in.p, w, in_bytes, cudaMemcpyHostToDevice, h->stream));
-    st = witness_core(h, h->in.as<u64>(), w_len, in_coeff, f_coeff ? h->fcoeff64.as<u64>() : nullptr,
-                      f ? h->f.as<u64>() : nullptr, cm ? h->cms.as<u64>() : nullptr);
-    if (st) return st;
+    // Pipeline the upload with the witness kernel: w_ccs goes up in chunks on a copy stream and each chunk's
+    // iCRT/decompose/CRT starts as soon as its bytes have landed (per-element work, so chunks are independent); only
+    // the matrix-vector kernel needs the whole witness.  With pinned host memory this hides the witness kernel behind
+    // the PCIe transfer.
+    u64 *d_fc = f_coeff ? h->fcoeff64.as<u64>() : nullptr, *d_f = f ? h->f.as<u64>() : nullptr;
+    u64 *d_fx = cm ? h->fx.as<u64>() : nullptr;
+    // Pinned (page-locked) host memory is mapped into the device address space: the witness kernel then reads w_ccs
+    // straight over PCIe -- no staging copy, no extra launch, the 8-lane loads are contiguous 768-byte runs per warp.
+    const u64 *w_mapped = nullptr;
+    {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, w) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+            w_mapped = static_cast<const u64 *>(attr.devicePointer);
+        else
+            cudaGetLastError();  // pageable memory: not an error, take the copy path
+    }
+    u64 nchunks = w_len >= 4096 ? 4 : 1;
+    if (w_mapped) {
+        nchunks = 0;
+        lat::launch_witness(w_mapped, w_len, (int)h->log2_B, (int)h->L, h->mont, in_coeff, h->f16.as<int16_t>(), d_fc, d_f,
+                            d_fx, h->flag.as<int>(), h->stream);
+        CK(cudaGetLastError());
+    }
+    for (u64 c = 0; c < nchunks; ++c) {
+        const u64 e0 = w_len * c / nchunks, e1 = w_len * (c + 1) / nchunks, cnt = e1 - e0, lo = e0 * h->L;
+        cudaStream_t cs = nchunks > 1 ? h->copy_stream : h->stream;
+        CK(cudaMemcpyAsync(h->in.as<u64>() + e0 * LAT_RING_DEGREE, w + e0 * LAT_RING_DEGREE, cnt * ELEM_BYTES,
+                           cudaMemcpyHostToDevice, cs));
+        if (nchunks > 1) {
+            CK(cudaEventRecord(h->copy_done[c], cs));
+            CK(cudaStreamWaitEvent(h->stream, h->copy_done[c], 0));
+        }
+        lat::launch_witness(h->in.as<u64>() + e0 * LAT_RING_DEGREE, cnt, (int)h->log2_B, (int)h->L, h->mont, in_coeff,
+                            h->f16.as<int16_t>() + lo * LAT_RING_DEGREE, d_fc ? d_fc + lo * LAT_RING_DEGREE : nullptr,
+                            d_f ? d_f + lo * LAT_RING_DEGREE : nullptr, d_fx ? d_fx + lo * lat::FX_WORDS : nullptr,
+                            h->flag.as<int>(), h->stream);
+        CK(cudaGetLastError());
+    }
+    h->has_resident = true;
+    if (cm && (st = h->mac_fx(h->fx.as<u64>(), h->n, 1, h->cms.as<u64>()))) return st;
+    if (nchunks > 1) {  // the next call's copies must not overtake this call's kernels reading h->in
+        CK(cudaEventRecord(h->work_done, h->stream));
+        CK(cudaStreamWaitEvent(h->copy_stream, h->work_done, 0));
+    }
     if (cm) CK(cudaMemcpyAsync(cm, h->cms.p, (size_t)h->kappa * ELEM_BYTES, cudaMemcpyDeviceToHost, h->stream));
     if (f_coeff) CK(cudaMemcpyAsync(f_coeff, h->fcoeff64.p, n_bytes, cudaMemcpyDeviceToHost, h->stream));
     if (f) CK(cudaMemcpyAsync(f, h->f.p, n_bytes, cudaMemcpyDeviceToHost, h->stream));
