@@ -24,6 +24,9 @@ extern "C" {
     fn lat_ajtai_commit_ntt_batch(h: *mut LatAjtai, fs: *const u64, count: u32, f_len: u64, cms: *mut u64) -> c_int;
     fn lat_ajtai_witness_from_w_ccs(h: *mut LatAjtai, w_ccs: *const u64, w_len: u64, f_coeff: *mut u64, f: *mut u64, cm: *mut u64) -> c_int;
     fn lat_ajtai_decompose_commit(h: *mut LatAjtai, f_coeff: *const u64, n: u64, cm: *const u64, planes_coeff: *mut u64, planes_f: *mut u64, cms: *mut u64) -> c_int;
+    fn lat_ajtai_select_side(h: *mut LatAjtai, side: c_int) -> c_int;
+    fn lat_ajtai_fold_witness(h: *mut LatAjtai, rho: *const u64, f0: *mut u64, f0_coeff: *mut u64) -> c_int;
+    fn lat_ring_gadget_recompose(f: *const u64, count: u64, log2_b: u32, l: u32, out: *mut u64, repr: c_int, device: c_int) -> c_int;
     fn lat_ring_crt(coeff: *const u64, count: u64, ntt: *mut u64, device: c_int) -> c_int;
     fn lat_ring_icrt(ntt: *const u64, count: u64, coeff: *mut u64, device: c_int) -> c_int;
 }
@@ -119,6 +122,20 @@ impl CudaAjtai {
         )?;
         Ok((pc.chunks(n).map(|c| c.to_vec()).collect(), pf.chunks(n).map(|c| c.to_vec()).collect(), cms.chunks(kappa).map(|c| c.to_vec()).collect()))
     }
+    /// Which side (0 = accumulator, 1 = step witness) the following `decompose_commit` calls fill; both sides' planes
+    /// stay resident for `fold_witness`.
+    pub fn select_side(&self, side: i32) -> Result<(), CudaCommitError> {
+        check(unsafe { lat_ajtai_select_side(self.h, side) }, 0, 0)
+    }
+    /// LFFoldingProver::compute_f_0 (nifs/folding/utils.rs:351-376) followed by Witness::from_f's iCRT
+    /// (arith.rs:275-289) over the 2K resident planes.  Returns (f_0, f_0 in coefficient form).
+    pub fn fold_witness(&self, rho_s: &[NTT]) -> Result<(Vec<NTT>, Vec<Coeff>), CudaCommitError> {
+        assert_eq!(rho_s.len(), 2 * self.k);
+        let mut f0 = vec![NTT::default(); self.n];
+        let mut f0_coeff = vec![Coeff::default(); self.n];
+        check(unsafe { lat_ajtai_fold_witness(self.h, limbs(rho_s), limbs_mut(&mut f0), limbs_mut(&mut f0_coeff)) }, 0, 0)?;
+        Ok((f0, f0_coeff))
+    }
 }
 
 impl Drop for CudaAjtai {
@@ -136,6 +153,14 @@ pub fn elementwise_crt(v: &[Coeff], device: i32) -> Result<Vec<NTT>, CudaCommitE
 pub fn elementwise_icrt(v: &[NTT], device: i32) -> Result<Vec<Coeff>, CudaCommitError> {
     let mut out = vec![Coeff::default(); v.len()];
     check(unsafe { lat_ring_icrt(limbs(v), v.len() as u64, limbs_mut(&mut out), device) }, 0, 0)?;
+    Ok(out)
+}
+
+/// GadgetRecompose for a CRT-form vector (arith.rs:305,330; balanced_decomposition/mod.rs:177-190).
+pub fn gadget_recompose(f: &[NTT], log2_b: u32, l: u32, device: i32) -> Result<Vec<NTT>, CudaCommitError> {
+    let count = f.len() / l as usize;
+    let mut out = vec![NTT::default(); count];
+    check(unsafe { lat_ring_gadget_recompose(limbs(f), count as u64, log2_b, l, limbs_mut(&mut out), LAT_REPR_MONTGOMERY, device) }, 0, 0)?;
     Ok(out)
 }
 

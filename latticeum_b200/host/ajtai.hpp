@@ -90,6 +90,11 @@ class AjtaiCommitmentScheme {
             out[k].val.assign(cms.begin() + (size_t)k * kappa_ * LAT_RING_DEGREE, cms.begin() + (size_t)(k + 1) * kappa_ * LAT_RING_DEGREE);
         return out;
     }
+    // Which side (0 = accumulator, 1 = step witness) the following decompose_commit calls fill (kept resident).
+    void select_side(int side) const { check(lat_ajtai_select_side(h_, side)); }
+    // LFFoldingProver::compute_f_0 (nifs/folding/utils.rs:351-376) + Witness::from_f's iCRT (arith.rs:275-289) over
+    // the 2K resident planes; rho: 2K ring elements (CRT form); f0 / f0_coeff: n x 24, either may be null.
+    void fold_witness(const uint64_t *rho, uint64_t *f0, uint64_t *f0_coeff) const { check(lat_ajtai_fold_witness(h_, rho, f0, f0_coeff)); }
     lat_ajtai *handle() const { return h_; }
 
    private:
@@ -98,5 +103,11 @@ class AjtaiCommitmentScheme {
     uint64_t n_;
     DecompositionParams p_;
 };
+
+// GadgetRecompose for a CRT-form vector (arith.rs:305,330): out[i] = sum_l B^l f[i*L + l]
+inline void gadget_recompose(const uint64_t *f, size_t count, DecompositionParams p, uint64_t *out, lat_repr repr = LAT_REPR_CANONICAL,
+                             int device = 0) {
+    check(lat_ring_gadget_recompose(f, count, p.log2_B, p.L, out, repr, device));
+}
 
 }  // namespace lat

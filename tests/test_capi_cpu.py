@@ -115,3 +115,19 @@ def test_params():
     assert S.GoldiLocksDP.log2_B == 15 and S.N == 98815 and S.KAPPA == 32
     with pytest.raises(ValueError):
         S.DecompositionParams(B=10, L=5, B_SMALL=2, K=15).log2_B
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    # bench.py --impl reference times the CPU path (the oracle port) and prints exactly one JSON line on stdout
+    import json
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, env={**os.environ, "OMP_NUM_THREADS": "4"})
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "ring elems/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["higher_is_better"] is True
