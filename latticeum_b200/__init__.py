@@ -8,6 +8,7 @@ reference's API.  There is no CPU fallback.
 from .scheme import (  # noqa: F401
     AjtaiCommitmentScheme,
     Commitment,
+    CommitPipeline,
     CommitmentError,
     DecompositionParams,
     DigitOverflow,
@@ -26,11 +27,12 @@ from .scheme import (  # noqa: F401
     gadget_recompose,
     get_fhat,
     ntt_from_scalar,
+    pinned_empty,
     to_mont,
 )
 
 __all__ = [
-    "AjtaiCommitmentScheme", "Commitment", "CommitmentError", "DecompositionParams", "DigitOverflow", "EngineError",
+    "AjtaiCommitmentScheme", "Commitment", "CommitPipeline", "pinned_empty", "CommitmentError", "DecompositionParams", "DigitOverflow", "EngineError",
     "GoldiLocksDP", "KAPPA", "LFDecompositionProver", "LFFoldingProver", "gadget_recompose", "N", "W_SIZE", "Witness", "WrongAjtaiMatrixDimensions",
     "WrongCommitmentLength", "WrongWitnessLength", "from_mont", "get_fhat", "ntt_from_scalar", "to_mont",
 ]

@@ -23,6 +23,7 @@ LAT_E_MATRIX_INCOMPLETE = 7
 LAT_REPR_CANONICAL = 0
 LAT_REPR_MONTGOMERY = 1
 LAT_ABI_VERSION = 1
+LAT_PIPELINE_DEPTH = 4
 
 _u64p = C.c_void_p  # raw addresses (host or device); arrays are passed by address
 _H = C.c_void_p     # lat_ajtai*
@@ -49,6 +50,8 @@ SIGNATURES = {
     "lat_ajtai_decompose_and_commit_ntt": (C.c_int, [_H, _u64p, C.c_uint64, _u64p]),
     "lat_ajtai_witness_from_w_ccs": (C.c_int, [_H, _u64p, C.c_uint64, _u64p, _u64p, _u64p]),
     "lat_ajtai_witness_from_w_ccs_dev": (C.c_int, [_H, _u64p, C.c_uint64, _u64p, _u64p, _u64p]),
+    "lat_ajtai_submit_w_ccs": (C.c_int, [_H, _u64p, C.c_uint64, _u64p, C.POINTER(C.c_uint64)]),
+    "lat_ajtai_wait": (C.c_int, [_H, C.c_uint64]),
     "lat_ajtai_decompose_commit": (C.c_int, [_H, _u64p, C.c_uint64, _u64p, _u64p, _u64p, _u64p]),
     "lat_ajtai_decompose_commit_dev": (C.c_int, [_H, _u64p, C.c_uint64, _u64p, _u64p, _u64p, _u64p]),
     "lat_ajtai_decompose_commit_resident": (C.c_int, [_H, _u64p, _u64p, _u64p, _u64p]),

@@ -100,6 +100,19 @@ struct lat_ajtai {
     DevBuf flag;         // int
     int *h_flag = nullptr;  // pinned
     bool has_resident = false;
+    // pipelined host-buffer steps (lat_ajtai_submit_w_ccs / lat_ajtai_wait): per-slot input staging, result and flag
+    struct Slot {
+        DevBuf in, cm, flag;          // w_ccs staging, kappa x 24 result, overflow flag
+        u64 *h_cm = nullptr;          // pinned mirror of cm (the caller's buffer may be pageable)
+        int *h_flag = nullptr;        // pinned
+        cudaEvent_t uploaded = nullptr, computed = nullptr, done = nullptr;
+        uint64_t ticket = 0;
+        uint64_t *user_cm = nullptr;
+        bool busy = false;
+    };
+    Slot slots[LAT_PIPELINE_DEPTH];
+    cudaStream_t d2h_stream = nullptr;
+    uint64_t next_ticket = 0;
     // profiling: pool of event pairs around mac_kernel launches, drained lazily
     static constexpr int EV_POOL = 256;
     bool profiling = false;
@@ -258,6 +271,17 @@ void lat_ajtai_destroy(lat_ajtai *h) {
                       &h->rho, &h->f0, &h->planes_coeff, &h->cms, &h->cm_in, &h->ws, &h->flag};
     for (DevBuf *b : bufs) b->release();
     if (h->h_flag) cudaFreeHost(h->h_flag);
+    if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
+    for (lat_ajtai::Slot &sl : h->slots) {
+        sl.in.release();
+        sl.cm.release();
+        sl.flag.release();
+        if (sl.h_cm) cudaFreeHost(sl.h_cm);
+        if (sl.h_flag) cudaFreeHost(sl.h_flag);
+        for (cudaEvent_t ev : {sl.uploaded, sl.computed, sl.done})
+            if (ev) cudaEventDestroy(ev);
+    }
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     for (cudaEvent_t e : h->ev0) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev1) cudaEventDestroy(e);
     for (cudaEvent_t ev : h->copy_done)
@@ -466,6 +490,71 @@ int lat_ajtai_decompose_and_commit_ntt(lat_ajtai *h, const uint64_t *w, uint64_t
 int lat_ajtai_decompose_and_commit_coeff(lat_ajtai *h, const uint64_t *w_coeff, uint64_t w_len, uint64_t *cm) {
     if (!cm) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
     return witness_host(h, w_coeff, w_len, true, nullptr, nullptr, cm);
+}
+
+// ---- pipelined steps ------------------------------------------------------------------------------------------------
+// A prover that commits one witness per VM step (ZKVM/main.rs:348-367) knows step i+1's w_ccs before it needs step i's
+// commitment.  submit() queues upload (copy engine) -> witness kernel -> matrix-vector kernel -> result download
+// (second copy engine) on three streams chained by events and returns; wait() blocks on one ticket.  In steady state
+// the PCIe transfers of neighbouring steps hide under the kernels.
+static int slot_prepare(lat_ajtai *h, lat_ajtai::Slot &sl, size_t in_bytes) {
+    int st;
+    const size_t cm_bytes = (size_t)h->kappa * ELEM_BYTES;
+    if ((st = sl.in.ensure(in_bytes)) || (st = sl.cm.ensure(cm_bytes)) || (st = sl.flag.ensure(sizeof(int)))) return st;
+    if (!sl.h_cm) CK(cudaHostAlloc((void **)&sl.h_cm, cm_bytes, cudaHostAllocDefault));
+    if (!sl.h_flag) CK(cudaHostAlloc((void **)&sl.h_flag, sizeof(int), cudaHostAllocDefault));
+    for (cudaEvent_t *ev : {&sl.uploaded, &sl.computed, &sl.done})
+        if (!*ev) CK(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    if (!h->d2h_stream) CK(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    return LAT_OK;
+}
+
+int lat_ajtai_submit_w_ccs(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_len, uint64_t *cm, uint64_t *ticket) {
+    if (!h || !w_ccs || !cm || !ticket) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (w_len * h->L != h->n) return h->wrong_len(w_len * h->L);
+    int st = h->bind();
+    if (st || (st = h->matrix_ready())) return st;
+    lat_ajtai::Slot &sl = h->slots[h->next_ticket % LAT_PIPELINE_DEPTH];
+    if (sl.busy)
+        return fail(LAT_E_INVALID_ARGUMENT, "pipeline full: lat_ajtai_wait(ticket " + std::to_string(sl.ticket) + ") first");
+    const size_t in_bytes = w_len * ELEM_BYTES, cm_bytes = (size_t)h->kappa * ELEM_BYTES;
+    if ((st = slot_prepare(h, sl, in_bytes))) return st;
+    // upload on the copy stream (the slot's previous user was waited for, so its staging buffer is free)
+    CK(cudaMemcpyAsync(sl.in.p, w_ccs, in_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaEventRecord(sl.uploaded, h->copy_stream));
+    // compute on the handle's stream
+    CK(cudaStreamWaitEvent(h->stream, sl.uploaded, 0));
+    CK(cudaMemsetAsync(sl.flag.p, 0, sizeof(int), h->stream));
+    lat::launch_witness(sl.in.as<u64>(), w_len, (int)h->log2_B, (int)h->L, h->mont, false, h->f16.as<int16_t>(), nullptr, nullptr,
+                        h->fx.as<u64>(), sl.flag.as<int>(), h->stream);
+    CK(cudaGetLastError());
+    h->has_resident = true;
+    if ((st = h->mac_fx(h->fx.as<u64>(), h->n, 1, sl.cm.as<u64>()))) return st;
+    CK(cudaEventRecord(sl.computed, h->stream));
+    // download on the second copy stream
+    CK(cudaStreamWaitEvent(h->d2h_stream, sl.computed, 0));
+    CK(cudaMemcpyAsync(sl.h_cm, sl.cm.p, cm_bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
+    CK(cudaMemcpyAsync(sl.h_flag, sl.flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->d2h_stream));
+    CK(cudaEventRecord(sl.done, h->d2h_stream));
+    sl.busy = true;
+    sl.user_cm = cm;
+    sl.ticket = h->next_ticket;
+    *ticket = h->next_ticket++;
+    return LAT_OK;
+}
+
+int lat_ajtai_wait(lat_ajtai *h, uint64_t ticket) {
+    if (!h) return fail(LAT_E_INVALID_ARGUMENT, "NULL handle");
+    lat_ajtai::Slot &sl = h->slots[ticket % LAT_PIPELINE_DEPTH];
+    if (!sl.busy || sl.ticket != ticket) return fail(LAT_E_INVALID_ARGUMENT, "no such ticket in flight");
+    int st = h->bind();
+    if (st) return st;
+    sl.busy = false;
+    CK(cudaEventSynchronize(sl.done));
+    memcpy(sl.user_cm, sl.h_cm, (size_t)h->kappa * ELEM_BYTES);
+    if (*sl.h_flag)
+        return fail(LAT_E_DIGIT_OVERFLOW, "a coefficient needs more digits than the decomposition padding allows");
+    return LAT_OK;
 }
 
 // ---- decompose_witness + commit_witnesses ---------------------------------------------------------------------------

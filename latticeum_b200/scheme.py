@@ -326,6 +326,47 @@ class AjtaiCommitmentScheme:
         return Commitment(cm, self.mont)
 
 
+class CommitPipeline:
+    """A stream of per-step commitments (zkvm/src/main.rs:121-219 commits one witness per VM step, :348-367): `submit`
+    queues Witness::from_w_ccs + Witness::commit for one step and returns a ticket at once, `wait` returns that step's
+    Commitment.  Up to `depth` steps are in flight; the PCIe transfers of neighbouring steps overlap the kernels when
+    the w_ccs buffers are page-locked (`pinned_empty`).  Buffers passed to `submit` must stay untouched until `wait`."""
+
+    depth = capi.LAT_PIPELINE_DEPTH
+
+    def __init__(self, scheme: "AjtaiCommitmentScheme"):
+        self.scheme = scheme
+        self._out = {}
+
+    def submit(self, w_ccs) -> int:
+        w = _as_u64(w_ccs, "w_ccs").reshape(-1, D)
+        cm = np.empty((self.scheme._kappa, D), np.uint64)
+        ticket = C.c_uint64(0)
+        st = capi.lib().lat_ajtai_submit_w_ccs(self.scheme._h, _ptr(w), w.shape[0], _ptr(cm), C.byref(ticket))
+        _raise(st, w.shape[0] * self.scheme.params.L, self.scheme._n)
+        self._out[ticket.value] = (cm, w)  # keep both alive until the ticket is waited for
+        return ticket.value
+
+    def wait(self, ticket: int) -> Commitment:
+        cm, _ = self._out.pop(ticket)
+        _raise(capi.lib().lat_ajtai_wait(self.scheme._h, ticket))
+        return Commitment(cm, self.scheme.mont)
+
+
+def pinned_empty(shape, device: int = 0) -> np.ndarray:
+    """A page-locked uint64 array (lat_host_alloc): uploads from it run on a copy engine and overlap the kernels.
+    The memory is released when the array is garbage collected."""
+    import weakref
+
+    count = int(np.prod(shape))
+    ptr = C.c_void_p()
+    _raise(capi.lib().lat_host_alloc(C.byref(ptr), max(count, 1) * 8))
+    buf = (C.c_uint64 * max(count, 1)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=np.uint64, count=count).reshape(shape)
+    weakref.finalize(buf, capi.lib().lat_host_free, ptr)
+    return arr
+
+
 # ---- Witness --------------------------------------------------------------------------------------------------------------
 class Witness:
     """latticefold/src/arith.rs:214-223.  `f_hat` (the MLE tables) stays with the host's MLE code and is derived

@@ -304,6 +304,71 @@ def test_resident_witness_path():
     scheme.close()
 
 
+# ---- pipelined steps (submit / wait) ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mont", [False, True], ids=["canonical", "montgomery"])
+@pytest.mark.parametrize("pinned", [False, True], ids=["pageable", "pinned"])
+def test_commit_pipeline_matches_blocking_calls(mont, pinned):
+    kappa, wl, steps = 9, 300, 11
+    n = wl * DP.L
+    A = CO.fill_uniform((kappa, n, 24), 81)
+    scheme = make_scheme(A, mont)
+    pipe = LB.CommitPipeline(scheme)
+    ws = []
+    for k in range(steps):
+        w = maybe_mont(CO.fill_uniform((wl, 24), 800 + k), mont)
+        if pinned:
+            buf = LB.pinned_empty((wl, 24))
+            buf[:] = w
+            w = buf
+        ws.append(w)
+    got, tickets = {}, []
+    for k in range(steps):
+        if len(tickets) == pipe.depth:  # keep the pipeline full: wait for the oldest, submit the next
+            t = tickets.pop(0)
+            got[t] = pipe.wait(t)
+        tickets.append(pipe.submit(ws[k]))
+    for t in tickets:
+        got[t] = pipe.wait(t)
+    assert sorted(got) == list(range(steps))
+    for k in range(steps):
+        _, f = CO.witness_from_w_ccs(unmont(np.array(ws[k]), mont), DP.B, DP.L)
+        assert np.array_equal(unmont(got[k].as_ref(), mont), CO.commit(A, f)), f"step {k}"
+    # the last submitted step is the handle's resident witness
+    wit, cm = LB.Witness.from_w_ccs(scheme, ws[-1], commit=True)
+    assert cm == got[steps - 1]
+    scheme.close()
+
+
+def test_commit_pipeline_errors():
+    # two limbs of 2^15 only, so that a coefficient can overflow the padding at all (2^75 > q with the zkVM's L = 5)
+    kappa, wl = 4, 40
+    params = LB.DecompositionParams(B=1 << 15, L=2, B_SMALL=2, K=15)
+    n = wl * params.L
+    A = CO.fill_uniform((kappa, n, 24), 83)
+    scheme = make_scheme(A, params=params)
+    pipe = LB.CommitPipeline(scheme)
+    small = np.zeros((wl, 24), np.uint64)
+    small[:, :] = CO.fill_uniform((wl, 24), 84) % np.uint64(1 << 28)
+    w = CO.crt(small)
+    with pytest.raises(LB.WrongWitnessLength):
+        pipe.submit(w[:-1])
+    tickets = [pipe.submit(w) for _ in range(pipe.depth)]
+    with pytest.raises(LB.EngineError):  # full
+        pipe.submit(w)
+    assert capi.lib().lat_ajtai_wait(scheme._h, 10_000) == capi.LAT_E_INVALID_ARGUMENT  # unknown ticket
+    # a digit overflow is reported by the wait of the step that caused it, and only that one
+    bad = w.copy()
+    bad[3] = CO.crt(np.full((1, 24), 1 << 31, np.uint64))[0]  # 2^31 needs three limbs of 2^15
+    first = pipe.wait(tickets.pop(0))
+    tb = pipe.submit(bad)
+    for t in tickets:
+        assert pipe.wait(t) == first
+    with pytest.raises(LB.DigitOverflow):
+        pipe.wait(tb)
+    assert pipe.wait(pipe.submit(w)) == first
+    scheme.close()
+
+
 # ---- the zkVM's full size: oracle on a bounded part + size-independent properties -----------------------------------------
 @pytest.fixture(scope="module")
 def zkvm():
