@@ -103,3 +103,66 @@ class ShardedAjtaiScheme:
             partial = self.engine.new_commitment(f_local.shape[0] if f_local.dim() == 3 else 1)
         self.engine.commit_ntt(f_local, partial)
         return self._exchange(partial)
+
+
+class ShardedCommitPipeline:
+    """A stream of per-step sharded commitments with HOST buffers: `submit(w_host)` queues, on this rank, the upload of
+    its block of the step's w_ccs (copy stream), witness_commit + the partial exchange (the engine's stream) and the
+    download of the full commitment (second copy stream), and returns a ticket; `wait(ticket)` returns the pinned
+    host tensor holding that step's commitment.  `depth` steps are in flight, so the PCIe transfers of neighbouring
+    steps hide under the kernels.  Every rank must submit the same sequence of steps (the exchange is collective).
+    On a CPU device (gloo tests) the same calls run synchronously."""
+
+    def __init__(self, sharded: ShardedAjtaiScheme, w_len_local: int, depth: int = 4):
+        self.sharded, self.depth = sharded, depth
+        eng = sharded.engine
+        dev = getattr(eng, "device", torch.device("cpu"))
+        self.cuda = dev.type == "cuda"
+        self.next_ticket = 0
+        self.slots = []
+        for _ in range(depth):
+            sl = {
+                "w": torch.empty((w_len_local, 24), dtype=torch.int64, device=dev),
+                "partial": eng.new_commitment(),
+                "cm_host": torch.empty((eng.kappa, 24), dtype=torch.int64),
+                "ticket": None,
+            }
+            if self.cuda:
+                sl["cm_host"] = sl["cm_host"].pin_memory()
+                sl["uploaded"], sl["computed"], sl["done"] = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+            self.slots.append(sl)
+        if self.cuda:
+            self.up, self.down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def submit(self, w_host: torch.Tensor) -> int:
+        sl = self.slots[self.next_ticket % self.depth]
+        if sl["ticket"] is not None:
+            raise RuntimeError(f"pipeline full: wait for ticket {sl['ticket']} first")
+        if not self.cuda:
+            sl["w"].copy_(w_host)
+            sl["cm_host"].copy_(self.sharded.witness_commit(sl["w"], sl["partial"]))
+        else:
+            compute = torch.cuda.current_stream()
+            with torch.cuda.stream(self.up):  # the slot's previous user has been waited for: its staging buffer is free
+                sl["w"].copy_(w_host, non_blocking=True)
+                sl["uploaded"].record(self.up)
+            compute.wait_event(sl["uploaded"])
+            cm = self.sharded.witness_commit(sl["w"], sl["partial"])
+            sl["computed"].record(compute)
+            self.down.wait_event(sl["computed"])
+            with torch.cuda.stream(self.down):
+                sl["cm_host"].copy_(cm, non_blocking=True)
+                sl["done"].record(self.down)
+            cm.record_stream(self.down)
+        sl["ticket"] = self.next_ticket
+        self.next_ticket += 1
+        return sl["ticket"]
+
+    def wait(self, ticket: int) -> torch.Tensor:
+        sl = self.slots[ticket % self.depth]
+        if sl["ticket"] != ticket:
+            raise KeyError(f"no such ticket in flight: {ticket}")
+        if self.cuda:
+            sl["done"].synchronize()
+        sl["ticket"] = None
+        return sl["cm_host"]

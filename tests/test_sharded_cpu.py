@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from latticeum_b200.sharded import ShardedAjtaiScheme, shard_bounds
+from latticeum_b200.sharded import ShardedCommitPipeline, ShardedAjtaiScheme, shard_bounds
 from oracle import c_oracle as CO
 
 Q = 2**64 - 2**32 + 1
@@ -82,6 +82,16 @@ def _worker(rank, world, port, results):
         _, f = CO.witness_from_w_ccs(w, B, L)
         fs = np.stack([f, CO.fill_uniform((W_TOTAL * L, 24), 3)])
         cms = sh.commit_ntt(to_t(np.ascontiguousarray(fs[:, lo * L : hi * L])))
+        # the pipelined front end: three steps through two slots, tickets waited for in order
+        pipe = ShardedCommitPipeline(sh, hi - lo, depth=2)
+        outs = []
+        t0 = pipe.submit(to_t(w[lo:hi]))
+        t1 = pipe.submit(to_t(w[lo:hi]))
+        outs.append(to_np(pipe.wait(t0)).copy())
+        t2 = pipe.submit(to_t(w[lo:hi]))
+        outs.append(to_np(pipe.wait(t1)).copy())
+        outs.append(to_np(pipe.wait(t2)).copy())
+        assert np.array_equal(outs[0], to_np(cm)) and np.array_equal(outs[1], to_np(cm)) and np.array_equal(outs[2], to_np(cm))
         results[rank] = (to_np(cm).copy(), to_np(cms).copy())
     finally:
         dist.destroy_process_group()
