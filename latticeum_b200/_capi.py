@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liblattice_ajtai.so")
+LIB_PATH = os.environ.get("LAT_LIB") or os.path.join(_HERE, "lib", "liblattice_ajtai.so")  # LAT_LIB: tuning builds
 
 # lat_status (include/lattice_ajtai.h)
 LAT_OK = 0

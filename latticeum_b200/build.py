@@ -50,5 +50,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(tag: str, defines) -> str:
+    """A tuning build with extra -D flags into lib/variants/<tag>/ (tools/tune_mac.py loads it through LAT_LIB)."""
+    out = os.path.join(LIBDIR, "variants", tag)
+    os.makedirs(out, exist_ok=True)
+    lib = os.path.join(out, "liblattice_ajtai.so")
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.check_call([nvcc(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++",
+                           "-shared", *[f"-D{d}" for d in defines], "-o", lib, *srcs])
+    return lib
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -179,6 +179,26 @@ struct MacGeo {
     static constexpr int MIN_CTAS = PT == 1 ? 2 : 1;
 };
 
+#ifdef LAT_MAC_TRACE
+// Tuning builds only (latticeum_b200.build.build_variant + tools/trace_mac.py): per-CTA globaltimer stamps of the last
+// launch -- entry, first tile landed, loop done, partials published, exit, SM id -- to size the fixed cost of a launch.
+__device__ unsigned long long g_mac_trace[8192 * 8];
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TRACE(k)                                                                                               \
+    do {                                                                                                       \
+        if (threadIdx.x == 0) {                                                                                \
+            const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);               \
+            if (cta < 8192) g_mac_trace[cta * 8 + (k)] = gtime();                                              \
+        }                                                                                                      \
+    } while (0)
+#else
+#define TRACE(k)
+#endif
+
 template <int PT, int RG>
 __global__ void __launch_bounds__(MacGeo<PT, RG>::THREADS, MacGeo<PT, RG>::MIN_CTAS)
 mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__ Fx, u64 f_stride, uint32_t planes,
@@ -192,6 +212,15 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u32 rbk = blockIdx.y;
     const u32 p0 = blockIdx.z * PT;
+    TRACE(0);
+#ifdef LAT_MAC_TRACE
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        if (cta < 8192) g_mac_trace[cta * 8 + 5] = smid;
+    }
+#endif
 
     // contiguous tile range of this CTA
     const u64 t_begin = lay.ntiles * blockIdx.x / gridDim.x;
@@ -240,6 +269,9 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
     bool ready = false;  // result of the early, non-blocking poll of this tile's barrier
     for (u32 t = 0; t < my_tiles; ++t) {
         if (!ready) mbar_wait(&bars[st], ph);
+#ifdef LAT_MAC_TRACE
+        if (t == 0) TRACE(1);
+#endif
         const u64 *sa = reinterpret_cast<const u64 *>(smem_raw + (size_t)st * G::STAGE_BYTES) + il * 8 + s;
         const ulonglong2 *sf =
             reinterpret_cast<const ulonglong2 *>(smem_raw + (size_t)st * G::STAGE_BYTES + G::TILE_BYTES) + s * 3;
@@ -255,11 +287,19 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
             const u32 jj = cgi + q * G::CG;
             const u64 *pa = sa + jj * (3 * G::RB * 8);
             u64 a0 = pa[0], a1 = pa[G::RB * 8], a2 = pa[2 * G::RB * 8];
+            if constexpr (PT == 1) {
+                // one witness: exact 65-bit sums, the carry goes straight into the accumulator (fewest instructions)
+                ulonglong2 x = sf[jj * (FX / 2)], y = sf[jj * (FX / 2) + 1], z = sf[jj * (FX / 2) + 2];
+                acc[0].mac(a0, a1, a2, x.x, x.y, y.x, y.y, z.x, z.y);
+            } else {
+                // several witnesses share the matrix entry: fold its three sums to 64 bits once
+                const u64 a01 = gl::add_fold(a0, a1), a02 = gl::add_fold(a0, a2), a12 = gl::add_fold(a1, a2);
 #pragma unroll
-            for (int p = 0; p < PT; ++p) {
-                const ulonglong2 *pf = sf + (p * G::TJ + jj) * (FX / 2);
-                ulonglong2 x = pf[0], y = pf[1], z = pf[2];
-                acc[p].mac(a0, a1, a2, x.x, x.y, y.x, y.y, z.x, z.y);
+                for (int p = 0; p < PT; ++p) {
+                    const ulonglong2 *pf = sf + (p * G::TJ + jj) * (FX / 2);
+                    ulonglong2 x = pf[0], y = pf[1], z = pf[2];
+                    acc[p].mac_presummed(a0, a1, a2, a01, a02, a12, x.x, x.y, y.x, y.y, z.x, z.y);
+                }
             }
         }
         __syncwarp();
@@ -274,6 +314,7 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
         ph = ph_n;
     }
 
+    TRACE(2);
     // ===== epilogue ============================================================================================
     // One special-form reduction per output, then the cross-CTA sum: every partial (canonical, < 2^64) is split into
     // its 32-bit halves and added with two 64-bit REDs into ws[2*idx], ws[2*idx+1] (a few hundred addends cannot
@@ -298,6 +339,7 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
     u64 *counter = ws + 2 * nout;
     __threadfence();
     __syncthreads();
+    TRACE(3);
     if (threadIdx.x == 0) {
         const u32 total = gridDim.x * gridDim.y * gridDim.z;
         s_last = (atomicAdd(reinterpret_cast<unsigned long long *>(counter), 1ull) == total - 1) ? 1u : 0u;
@@ -315,7 +357,14 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
         }
         if (threadIdx.x == 0) *counter = 0;
     }
+    TRACE(4);
 }
+
+#ifdef LAT_MAC_TRACE
+extern "C" int lat_debug_mac_trace(unsigned long long *out, int ctas) {
+    return (int)cudaMemcpyFromSymbol(out, g_mac_trace, (size_t)ctas * 8 * sizeof(unsigned long long));
+}
+#endif
 
 template <int PT, int RG>
 static size_t mac_stage_bytes() { return MacGeo<PT, RG>::STAGE_BYTES; }
@@ -434,12 +483,30 @@ fold_kernel(const u64 *__restrict__ s0, const u64 *__restrict__ s1, int nsides, 
     const u32 sl = (u32)(idx & 7);
     gl::Fq3Acc acc;
     acc.clear();
-    for (int side = 0; side < nsides; ++side) {
-        const u64 *base = (side == 0 ? s0 : s1) + idx * 6;
-        for (int k = 0; k < pps; ++k) {
-            const ulonglong2 *pf = reinterpret_cast<const ulonglong2 *>(base + (u64)k * n * FX);
-            ulonglong2 x = __ldg(pf), y = __ldg(pf + 1), z = __ldg(pf + 2);
-            const u64 *r = s_rho + (side * pps + k) * ring::D + 3 * sl;
+    // HBM-bound (48 B per thread per plane, 2K planes): keep two planes' loads in flight ahead of the arithmetic
+    auto plane_ptr = [&](int p) {
+        const u64 *base = (p < pps ? s0 + (u64)p * n * FX : s1 + (u64)(p - pps) * n * FX) + idx * 6;
+        return reinterpret_cast<const ulonglong2 *>(base);
+    };
+    constexpr int AHEAD = 2;
+    ulonglong2 buf[AHEAD][3];
+#pragma unroll
+    for (int a = 0; a < AHEAD; ++a)
+        if (a < nplanes) {
+            const ulonglong2 *pf = plane_ptr(a);
+            buf[a][0] = __ldcs(pf); buf[a][1] = __ldcs(pf + 1); buf[a][2] = __ldcs(pf + 2);
+        }
+    for (int p0 = 0; p0 < nplanes; p0 += AHEAD) {
+#pragma unroll
+        for (int a = 0; a < AHEAD; ++a) {
+            const int p = p0 + a;
+            if (p >= nplanes) break;
+            const ulonglong2 x = buf[a][0], y = buf[a][1], z = buf[a][2];
+            if (p + AHEAD < nplanes) {
+                const ulonglong2 *pf = plane_ptr(p + AHEAD);
+                buf[a][0] = __ldcs(pf); buf[a][1] = __ldcs(pf + 1); buf[a][2] = __ldcs(pf + 2);
+            }
+            const u64 *r = s_rho + p * ring::D + 3 * sl;
             acc.mac(r[0], r[1], r[2], x.x, x.y, y.x, y.y, z.x, z.y);
         }
     }

@@ -433,6 +433,57 @@ def test_zkvm_fold_step_properties(zkvm):
     assert scheme.commit(s) == scheme.commit(wit.f) + scheme.commit(f2)
 
 
+def test_zkvm_fold_both_sides_realistic_and_f0(zkvm):
+    """SURVEY 8d case 2, realistic: right side = limbs of a steady-state step witness, left side = a folded witness
+    (rounded Gaussian, sigma ~ 350, clipped to +-(2^15 - 1): mostly-empty high planes).  Both sides decomposed and
+    committed at the zkVM's full size, then folded (compute_f_0 + iCRT) against the oracle."""
+    A, scheme = zkvm
+    rng = np.random.default_rng(5)
+    left = np.clip(np.rint(rng.normal(0.0, 350.0, size=(LB.N, 24))), -(2**15 - 1), 2**15 - 1).astype(np.int64)
+    left[0, :4] = [2**15 - 1, -(2**15 - 1), 2**14, -(2**14)]
+    fc_left = signed_to_fq(left)
+    fc_right, _ = CO.witness_from_w_ccs(steady_state_w(82), DP.B, DP.L)
+    planes = []
+    for side, fc in ((0, fc_left), (1, fc_right)):
+        cm = scheme.commit_coeff(fc)
+        _, ys = LB.LFDecompositionProver.decompose_and_commit(scheme, fc, cm, want_planes=False, side=side)
+        pl = CO.decompose_planes(fc, 2, DP.K)
+        for k in (1, 9, 14):  # a full plane, a sparse one, the (almost) empty top one
+            assert np.array_equal(ys[k].as_ref(), CO.commit(A, CO.crt(pl[k]))), (side, k)
+        acc = LB.Commitment.zeroed(LB.KAPPA)
+        for y in reversed(ys):
+            acc = acc * S.ntt_from_scalar(2) + y
+        assert acc == cm
+        planes += [CO.crt(pl[k]) for k in range(DP.K)]
+    rho = CO.crt(signed_to_fq(rng.integers(-32, 32, size=(2 * DP.K, 24))))  # short challenges, CYC/rings/goldilocks.rs:32-35
+    wit0 = LB.LFFoldingProver.compute_f_0(scheme, rho)
+    exp = CO.compute_f0(rho, planes)
+    assert np.array_equal(wit0.f, exp)
+    assert np.array_equal(wit0.f_coeff, CO.icrt(exp))
+
+
+def test_sharded_config_shape_n_2_20():
+    """BASELINE configs[2] / SURVEY 8d case 4 on one GPU: kappa = 32, n = 2^20 (A = 6.44 GB), uniform f in CRT form.
+    Rows are generated, uploaded and checked one at a time so that the host never holds the matrix."""
+    kappa, n = 32, 1 << 20
+    scheme = LB.AjtaiCommitmentScheme(kappa, n)
+    f = CO.fill_uniform((n, 24), 7)
+    exp = np.empty((kappa, 24), np.uint64)
+    for i in range(kappa):
+        row = CO.fill_uniform((1, n, 24), 1000 + i)
+        scheme.upload_rows(i, row)
+        exp[i] = CO.commit(row, f)[0]
+    cm = scheme.commit_ntt(f)
+    assert np.array_equal(cm.as_ref(), exp)
+    # linearity at this size
+    g = CO.fill_uniform((n, 24), 8)
+    s = ((f.astype(object) + g.astype(object)) % Q).astype(np.uint64)
+    assert scheme.commit_ntt(s) == cm + scheme.commit_ntt(g)
+    with pytest.raises(LB.WrongWitnessLength):
+        scheme.commit_ntt(f[:-1])
+    scheme.close()
+
+
 @pytest.mark.parametrize("mont", [False, True], ids=["canonical", "montgomery"])
 def test_fold_witness_compute_f0_vs_oracle(mont):
     # LF/nifs/folding.rs:258-268 (compute_f_0) + LF/arith.rs:299-313 (Witness::from_f) on the resident planes

@@ -81,5 +81,37 @@ mac_ms, mac_n = eng.mac_profile()
 wide28 = 28 * KAPPA * N * 8 * 24
 out["batch28"] = {"ms": t28, "mac_kernel_ms": mac_ms / mac_n, "imad_pipe_frac": wide28 / (mac_ms / mac_n * 1e-3) / 9.154e12}
 print(out["batch28"], flush=True)
+# fold of the 2K resident planes (compute_f_0 + iCRT), both sides filled by decompose_commit
+scheme_h = scheme._h
+for side in (0, 1):
+    assert L.lat_ajtai_select_side(scheme_h, side) == 0
+    eng.decompose_commit(fc_dev, cm, cms)
+rho = eng.to_device(rng.integers(0, 2**63, size=(2 * K, 24), dtype=np.uint64))
+f0 = torch.empty((N, 24), dtype=torch.int64, device="cuda")
+f0c = torch.empty_like(f0)
+t_fold = timeit(lambda: L.lat_ajtai_fold_witness_dev(scheme_h, rho.data_ptr(), f0.data_ptr(), f0c.data_ptr()), reps=10)
+out["fold_witness"] = {"what": "compute_f_0 over 2K = 30 resident planes + iCRT (n = 98 815)", "ms": t_fold,
+                       "bytes_read": 2 * K * N * 48 * 8, "GBps": 2 * K * N * 48 * 8 / t_fold / 1e6}
+print(out["fold_witness"], flush=True)
+del fs, cms28
+scheme.close()
+
+# ---- configs[2] shape on one GPU: kappa = 32, n = 2^20 (A = 6.44 GB), single commit ---------------------------------------
+N20 = 1 << 20
+big = LB.AjtaiCommitmentScheme(KAPPA, N20)
+row = rng.integers(0, 2**63, size=(1, N20, 24), dtype=np.uint64)
+for i in range(KAPPA):
+    big.upload_rows(i, row)  # the same random row 32 times: timing only
+eng2 = DeviceScheme(big)
+f20 = torch.from_numpy(rng.integers(0, 2**63, size=(N20, 24), dtype=np.int64)).cuda()
+cm20 = eng2.new_commitment()
+eng2.set_profiling(True)
+eng2.mac_profile()
+t20 = timeit(lambda: eng2.commit_ntt(f20, cm20), reps=10)
+mac_ms, mac_n = eng2.mac_profile()
+out["commit_n_2_20"] = {"what": "commit_ntt, kappa = 32, n = 2^20, one GPU (A = 6.44 GB streamed)", "ms": t20,
+                        "mac_kernel_ms": mac_ms / mac_n, "GBps": KAPPA * N20 * 192 / (mac_ms / mac_n) / 1e6,
+                        "hbm_frac": KAPPA * N20 * 192 / (mac_ms / mac_n) / 1e6 / 6548.8}
+print(out["commit_n_2_20"], flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/extra.json", "w"), indent=1)
