@@ -146,6 +146,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 // ---- witness -> extended layout (only for caller-supplied CRT-form witnesses; the CRT kernels emit it directly) -----
 __global__ void __launch_bounds__(256)
 fext_kernel(const u64 *__restrict__ f, u64 count_slots, u64 *__restrict__ fx) {
+    asm volatile("griddepcontrol.launch_dependents;");  // the MAC behind it may start its prologue (see mac_kernel)
     u64 i = (u64)blockIdx.x * 256 + threadIdx.x;  // (element, slot)
     if (i >= count_slots) return;
     u64 f0 = f[i * 3], f1 = f[i * 3 + 1], f2 = f[i * 3 + 2];
@@ -202,7 +203,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 template <int PT, int RG>
 __global__ void __launch_bounds__(MacGeo<PT, RG>::THREADS, MacGeo<PT, RG>::MIN_CTAS)
 mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__ Fx, u64 f_stride, uint32_t planes,
-           uint32_t stages, u64 *__restrict__ ws, u64 *__restrict__ cms) {
+           uint32_t stages, u64 *__restrict__ ws, u64 *__restrict__ cms, uint32_t dependent_launch) {
     using G = MacGeo<PT, RG>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // after the stages: [full mbarrier x stages][release counter x stages]
@@ -231,21 +232,27 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
     // Stream tile `nt` into stage `st` with TMA bulk copies (one thread).  There is no producer role: the warp that
     // is LAST to release a stage refills it at once (release counters below), so no warp ever waits for another
     // except through the data itself, and `stages` tiles are in flight or being consumed at all times.
-    auto issue_tile = [&](u32 nt, u32 st) {
+    // The last tile may hang over the end of F (columns >= n): copy only the valid columns.  The matching matrix
+    // columns are zero padding, so whatever the stale tail of the stage holds contributes 0 (exact integer
+    // arithmetic, no NaNs to worry about).
+    auto witness_bytes = [&](u32 nt) { return (u32)min((u64)G::TJ, lay.n - (t_begin + nt) * G::TJ) * FX * 8; };
+    auto issue_matrix = [&](u32 nt, u32 st) {
+        mbar_arrive_expect_tx(&bars[st], G::TILE_BYTES + PT * witness_bytes(nt));
+        tma_bulk_g2s(smem_raw + (size_t)st * G::STAGE_BYTES, a_src + (u64)nt * G::TILE_ELEMS, G::TILE_BYTES, &bars[st]);
+    };
+    auto issue_witness = [&](u32 nt, u32 st) {
         unsigned char *dst = smem_raw + (size_t)st * G::STAGE_BYTES;
-        // The last tile may hang over the end of F (columns >= n): copy only the valid columns.  The matching
-        // matrix columns are zero padding, so whatever the stale tail of the stage holds contributes 0
-        // (exact integer arithmetic, no NaNs to worry about).
         const u64 col0 = (t_begin + nt) * G::TJ;
-        const u32 fcols = (u32)min((u64)G::TJ, lay.n - col0);
-        const u32 fb = fcols * FX * 8;
-        mbar_arrive_expect_tx(&bars[st], G::TILE_BYTES + PT * fb);
-        tma_bulk_g2s(dst, a_src + (u64)nt * G::TILE_ELEMS, G::TILE_BYTES, &bars[st]);
+        const u32 fb = witness_bytes(nt);
 #pragma unroll
         for (int p = 0; p < PT; ++p) {
             const u64 *f_src = Fx + ((u64)(p0 + p) * f_stride + col0) * FX;
             tma_bulk_g2s(dst + G::TILE_BYTES + p * G::F_BYTES, f_src, fb, &bars[st]);
         }
+    };
+    auto issue_tile = [&](u32 nt, u32 st) {
+        issue_matrix(nt, st);
+        issue_witness(nt, st);
     };
 
     if (threadIdx.x == 0) {
@@ -254,8 +261,13 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
             released[st] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // Programmatic dependent launch: this grid may start while the kernel that produces the witness (Fx) is
+        // still draining.  The matrix does not depend on it, so the first tiles' matrix halves are requested at
+        // once; only the witness halves wait for the producer grid to complete.
         const u32 pre = min(stages, my_tiles);
-        for (u32 nt = 0; nt < pre; ++nt) issue_tile(nt, nt);
+        for (u32 nt = 0; nt < pre; ++nt) issue_matrix(nt, nt);
+        if (dependent_launch) asm volatile("griddepcontrol.wait;" ::: "memory");
+        for (u32 nt = 0; nt < pre; ++nt) issue_witness(nt, nt);
     }
     __syncthreads();
 
@@ -403,7 +415,7 @@ MacPlan plan_mac(const MatLayout &lay, uint32_t planes, int sm_count) {
 
 template <int PT, int RG>
 static void launch_mac_t(dim3 grid, const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes,
-                         const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream) {
+                         const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream, bool pdl) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(mac_kernel<PT, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // minus the static bytes
@@ -419,31 +431,43 @@ static void launch_mac_t(dim3 grid, const u64 *A_dev, const MatLayout &lay, cons
                 PT, RG, grid.x, grid.y, grid.z, MacGeo<PT, RG>::THREADS, plan.smem_bytes, plan.stages, fa.numRegs,
                 fa.maxDynamicSharedSizeBytes, fa.sharedSizeBytes, occ, fa.maxThreadsPerBlock);
     }
-    mac_kernel<PT, RG><<<grid, MacGeo<PT, RG>::THREADS, plan.smem_bytes, stream>>>(A_dev, lay, Fx, f_stride, planes,
-                                                                                    plan.stages, workspace, cms);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(MacGeo<PT, RG>::THREADS);
+    cfg.dynamicSmemBytes = plan.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see griddepcontrol.wait in the kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, mac_kernel<PT, RG>, A_dev, lay, Fx, f_stride, planes, plan.stages, workspace, cms, (uint32_t)(pdl ? 1 : 0));
 }
 
 template <int PT>
 static void launch_mac_pt(dim3 grid, const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes,
-                          const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream) {
+                          const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream, bool pdl) {
     switch (lay.rg) {
-        case 1: launch_mac_t<PT, 1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream); break;
-        case 2: launch_mac_t<PT, 2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream); break;
-        case 3: launch_mac_t<PT, 3>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream); break;
-        case 4: launch_mac_t<PT, 4>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream); break;
-        case 5: launch_mac_t<PT, 5>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream); break;
-        case 6: launch_mac_t<PT, 6>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream); break;
-        case 7: launch_mac_t<PT, 7>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream); break;
-        default: launch_mac_t<PT, 8>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream); break;
+        case 1: launch_mac_t<PT, 1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl); break;
+        case 2: launch_mac_t<PT, 2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl); break;
+        case 3: launch_mac_t<PT, 3>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl); break;
+        case 4: launch_mac_t<PT, 4>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl); break;
+        case 5: launch_mac_t<PT, 5>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl); break;
+        case 6: launch_mac_t<PT, 6>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl); break;
+        case 7: launch_mac_t<PT, 7>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl); break;
+        default: launch_mac_t<PT, 8>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl); break;
     }
 }
 
 void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes, const MacPlan &plan,
                 u64 *workspace, u64 *cms, cudaStream_t stream, cudaEvent_t ev_begin, cudaEvent_t ev_end) {
     dim3 grid(plan.grid_x, lay.nrb, planes / plan.pt);
+    // overlap with the producer kernel's tail unless events bracket the launch (they would serialise it anyway)
+    static const bool pdl_off = getenv("LAT_NO_PDL") != nullptr;
+    const bool pdl = !ev_begin && !pdl_off;
     if (ev_begin) cudaEventRecord(ev_begin, stream);
-    if (plan.pt == 1) launch_mac_pt<1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream);
-    else launch_mac_pt<2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream);
+    if (plan.pt == 1) launch_mac_pt<1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl);
+    else launch_mac_pt<2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl);
     if (ev_end) cudaEventRecord(ev_end, stream);
 }
 

@@ -173,6 +173,9 @@ witness_kernel(const u64 *__restrict__ w, u64 w_len, int log2b, int L, bool in_c
                u64 *__restrict__ f_coeff, u64 *__restrict__ f_plain, u64 *__restrict__ fx, int *__restrict__ flag) {
     __shared__ __align__(16) int16_t tile[OPB * WIT_MAX_L * ring::D];  // [octet][limb][24] = 6 KB
     extern __shared__ __align__(16) unsigned char dyn_smem[];
+    // let the matrix-vector kernel launched behind this one start its prologue (barriers, first matrix tiles) on SMs
+    // as they drain; it still waits for this grid to complete before touching the witness (griddepcontrol.wait there)
+    asm volatile("griddepcontrol.launch_dependents;");
     ulonglong2 *otile = reinterpret_cast<ulonglong2 *>(dyn_smem);
     const Octet o = octet_of(w_len);
     const bool tiled = L <= WIT_MAX_L;  // the engine's L is <= 8; only lat_ring_gadget_decompose allows more
@@ -264,6 +267,7 @@ template <bool MONT>
 __global__ void __launch_bounds__(PLANE_THREADS)
 planes_kernel(const int16_t *__restrict__ f16, u64 n, int K, u64 *__restrict__ planes_f, u64 *__restrict__ planes_fx,
               u64 *__restrict__ planes_coeff) {
+    asm volatile("griddepcontrol.launch_dependents;");  // the MAC behind it may start its prologue (see mac_kernel)
     __shared__ __align__(16) ulonglong2 otile[PLANE_THREADS * (FX_UNITS + 1)];  // 25.6 KB
     const u64 e0 = (u64)blockIdx.x * PLANE_THREADS;
     const u64 e = e0 + threadIdx.x;
