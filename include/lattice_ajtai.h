@@ -211,6 +211,16 @@ int lat_commitment_exchange_dev(const uint64_t *partial_dev, uint64_t words, int
                                 const uint64_t *recv_ptrs, const uint64_t *flag_ptrs, uint64_t epoch,
                                 uint64_t *out_dev, void *cuda_stream);
 
+/* ---- overlap of consecutive steps on the device ---------------------------------------------------------------------
+ * With the option enabled, the iCRT/decompose/CRT kernel of a lat_ajtai_witness_from_w_ccs_dev call that directly
+ * follows a commitment on the same handle starts while that commitment's matrix-vector kernel is still draining
+ * (programmatic dependent launch; the witness goes to a second buffer, and the kernels order themselves so that every
+ * result is still produced as if the calls ran back to back).  CONTRACT for a caller-supplied stream: between the
+ * previous call on this handle and this one, nothing else enqueued on the stream produces w_ccs_dev or consumes
+ * the previous call's outputs -- such work would no longer be ordered before the early-starting kernel.  Off by
+ * default; host-buffer entry points are unaffected (they synchronise).                                          */
+int lat_ajtai_set_step_overlap(lat_ajtai *h, int enabled);
+
 /* ---- diagnostics: CUDA-event timing of the dominant kernel (bench.py's roofline leg) ---------------------------
  * While enabled, every mac_kernel launch (the matrix-vector kernel alone, not its tiny reduce) is bracketed by a
  * pair of events on the handle's stream, taken from a pool so that nothing synchronises inside a timed loop.

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -86,6 +87,11 @@ struct lat_ajtai {
     DevBuf f16;          // resident decomposed witness, int16 digits, n x 24
     DevBuf f;            // CRT-form witness, n x 24 u64 (only when a caller wants it on the host)
     DevBuf fx;           // CRT-form witness(es) in the MAC kernel's extended layout, count x n x 48 u64
+    DevBuf fx_alt;       // second single-witness buffer for overlapped steps (lat_ajtai_set_step_overlap)
+    bool step_overlap = false;
+    const void *last_mac_src = nullptr;  // witness buffer the most recent matrix-vector launch reads
+    bool last_op_was_mac = false;        // ... and whether that launch is still the newest kernel this handle enqueued
+    bool mac_was_last = false;           // snapshot of the above at the start of the current entry point
     DevBuf fcoeff64;     // f_coeff as u64 for host output
     DevBuf planes;       // K x n x 24 CRT-form planes (only when a caller wants them)
     DevBuf planes_fx[2]; // K x n x 48 CRT-form planes, extended layout (MAC input), one buffer per fold side
@@ -135,6 +141,8 @@ struct lat_ajtai {
 
     int bind() {
         CK(cudaSetDevice(device));
+        mac_was_last = last_op_was_mac;
+        last_op_was_mac = false;
         return LAT_OK;
     }
     int matrix_ready() const {
@@ -165,6 +173,8 @@ struct lat_ajtai {
         }
         lat::launch_mac(A.as<u64>(), lay, Fx, stride, count, plan, ws.as<u64>(), cms_dev, stream, e0, e1);
         CK(cudaGetLastError());
+        last_mac_src = Fx;
+        last_op_was_mac = true;
         return LAT_OK;
     }
     // same for caller-supplied plain CRT-form witnesses (count x stride x 24): extend first
@@ -268,7 +278,7 @@ void lat_ajtai_destroy(lat_ajtai *h) {
     cudaSetDevice(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     DevBuf *bufs[] = {&h->A, &h->stage, &h->in, &h->f16, &h->f, &h->fx, &h->fcoeff64, &h->planes, &h->planes_fx[0], &h->planes_fx[1],
-                      &h->rho, &h->f0, &h->planes_coeff, &h->cms, &h->cm_in, &h->ws, &h->flag};
+                      &h->rho, &h->f0, &h->planes_coeff, &h->cms, &h->cm_in, &h->ws, &h->flag, &h->fx_alt};
     for (DevBuf *b : bufs) b->release();
     if (h->h_flag) cudaFreeHost(h->h_flag);
     if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
@@ -400,11 +410,21 @@ int lat_ajtai_commit_coeff(lat_ajtai *h, const uint64_t *f_coeff, uint64_t f_len
 static int witness_core(lat_ajtai *h, const u64 *w_dev, u64 w_len, bool in_coeff, u64 *f_coeff_dev, u64 *f_dev,
                         u64 *cm_dev) {
     // one kernel: iCRT -> digits -> CRT; the extended layout feeds the MAC, the plain layout only if the caller wants f
+    // With step overlap this kernel may start while the previous commitment's matrix-vector kernel is draining: it
+    // then writes the witness buffer that kernel is NOT reading (the protocol in ring_kernels.cu / mac_kernels.cu
+    // makes the buffer of two steps back safe to reuse).  Event brackets (profiling) serialise the launches anyway.
+    u64 *fxp = h->fx.as<u64>();
+    const bool chained = h->step_overlap && cm_dev && h->mac_was_last && !h->profiling;
+    if (chained && h->last_mac_src == h->fx.p) {
+        int st = h->fx_alt.ensure(h->n * lat::FX_WORDS * sizeof(u64));
+        if (st) return st;
+        fxp = h->fx_alt.as<u64>();
+    }
     lat::launch_witness(w_dev, w_len, (int)h->log2_B, (int)h->L, h->mont, in_coeff, h->f16.as<int16_t>(), f_coeff_dev,
-                        f_dev, cm_dev ? h->fx.as<u64>() : nullptr, h->flag.as<int>(), h->stream);
+                        f_dev, cm_dev ? fxp : nullptr, h->flag.as<int>(), h->stream, chained);
     CK(cudaGetLastError());
     h->has_resident = true;
-    if (cm_dev) return h->mac_fx(h->fx.as<u64>(), h->n, 1, cm_dev);
+    if (cm_dev) return h->mac_fx(fxp, h->n, 1, cm_dev);
     return LAT_OK;
 }
 
@@ -579,6 +599,7 @@ static int planes_core(lat_ajtai *h, const u64 *cm_dev, u64 *planes_coeff_dev, u
         }
         lat::launch_y0(cm_dev, cms_dev, h->K, h->kappa, h->stream);
         CK(cudaGetLastError());
+        h->last_op_was_mac = false;
     }
     return LAT_OK;
 }
@@ -780,6 +801,12 @@ int lat_ring_gadget_decompose(const uint64_t *in, uint64_t count, uint32_t log2_
     if (st) return st;
     if (e != cudaSuccess) return fail_cuda(e, "lat_ring_gadget_decompose", __LINE__);
     if (h_flag) return fail(LAT_E_DIGIT_OVERFLOW, "a coefficient needs more than L digits");
+    return LAT_OK;
+}
+
+int lat_ajtai_set_step_overlap(lat_ajtai *h, int enabled) {
+    if (!h) return fail(LAT_E_INVALID_ARGUMENT, "NULL handle");
+    h->step_overlap = enabled != 0;
     return LAT_OK;
 }
 

@@ -267,6 +267,10 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
         const u32 pre = min(stages, my_tiles);
         for (u32 nt = 0; nt < pre; ++nt) issue_matrix(nt, nt);
         if (dependent_launch) asm volatile("griddepcontrol.wait;" ::: "memory");
+        // Only now may the kernel behind this one start (the next step's witness kernel, if the caller allows the
+        // overlap): once every CTA has passed its wait the producer grid -- and through its block 0 the previous
+        // commitment -- is complete, so that kernel can reuse the buffers of two steps back.
+        asm volatile("griddepcontrol.launch_dependents;");
         for (u32 nt = 0; nt < pre; ++nt) issue_witness(nt, nt);
     }
     __syncthreads();

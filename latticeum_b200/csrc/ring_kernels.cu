@@ -168,14 +168,11 @@ __device__ __forceinline__ void load_i16x24(const int16_t *p, int (&d)[ring::D])
 // Dynamic shared memory: OPB*L rows x (FX_UNITS + 1) x 16 B for the output tile.
 constexpr int WIT_MAX_L = 8;
 template <bool MONT>
-__global__ void __launch_bounds__(THREADS, 4)
-witness_kernel(const u64 *__restrict__ w, u64 w_len, int log2b, int L, bool in_coeff, int16_t *__restrict__ f16,
-               u64 *__restrict__ f_coeff, u64 *__restrict__ f_plain, u64 *__restrict__ fx, int *__restrict__ flag) {
+__device__ __forceinline__ void witness_body(const u64 *__restrict__ w, u64 w_len, int log2b, int L, bool in_coeff,
+                                             int16_t *__restrict__ f16, u64 *__restrict__ f_coeff, u64 *__restrict__ f_plain,
+                                             u64 *__restrict__ fx, int *__restrict__ flag) {
     __shared__ __align__(16) int16_t tile[OPB * WIT_MAX_L * ring::D];  // [octet][limb][24] = 6 KB
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    // let the matrix-vector kernel launched behind this one start its prologue (barriers, first matrix tiles) on SMs
-    // as they drain; it still waits for this grid to complete before touching the witness (griddepcontrol.wait there)
-    asm volatile("griddepcontrol.launch_dependents;");
     ulonglong2 *otile = reinterpret_cast<ulonglong2 *>(dyn_smem);
     const Octet o = octet_of(w_len);
     const bool tiled = L <= WIT_MAX_L;  // the engine's L is <= 8; only lat_ring_gadget_decompose allows more
@@ -242,8 +239,24 @@ witness_kernel(const u64 *__restrict__ w, u64 w_len, int log2b, int L, bool in_c
     }
 }
 
+// Programmatic dependent launches on both sides of this kernel (see mac_kernel):
+//  * the matrix-vector kernel launched BEHIND it may start its prologue (barriers, first matrix tiles) on SMs as they
+//    drain; it still waits for this grid to complete before touching the witness;
+//  * with `chained` (lat_ajtai_set_step_overlap) this grid was itself launched while the PREVIOUS step's
+//    matrix-vector kernel is still draining: it writes the other witness buffer, and block 0 does not retire before
+//    that kernel has completed, so "this grid complete" implies "previous commitment complete" for everything
+//    ordered after it (the buffer two steps back, the workspace, the output).
+template <bool MONT>
+__global__ void __launch_bounds__(THREADS, 4)
+witness_kernel(const u64 *__restrict__ w, u64 w_len, int log2b, int L, bool in_coeff, int16_t *__restrict__ f16,
+               u64 *__restrict__ f_coeff, u64 *__restrict__ f_plain, u64 *__restrict__ fx, int *__restrict__ flag, int chained) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    witness_body<MONT>(w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag);
+    if (chained && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 void launch_witness(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool in_coeff, int16_t *f16, u64 *f_coeff,
-                    u64 *f_plain, u64 *fx, int *flag, cudaStream_t stream) {
+                    u64 *f_plain, u64 *fx, int *flag, cudaStream_t stream, bool overlap_previous) {
     if (!w_len) return;
     unsigned grid = (unsigned)((w_len + OPB - 1) / OPB);
     size_t smem = (f_plain || fx) ? (size_t)OPB * L * (FX_UNITS + 1) * 16 : 0;  // 32 KB at L = 5
@@ -251,10 +264,19 @@ void launch_witness(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool i
         cudaFuncSetAttribute(witness_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(witness_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
-    if (mont)
-        witness_kernel<true><<<grid, THREADS, smem, stream>>>(w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag);
-    else
-        witness_kernel<false><<<grid, THREADS, smem, stream>>>(w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = overlap_previous ? 1 : 0;
+    const int chained = overlap_previous ? 1 : 0;
+    if (mont) cudaLaunchKernelEx(&cfg, witness_kernel<true>, w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag, chained);
+    else cudaLaunchKernelEx(&cfg, witness_kernel<false>, w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag, chained);
 }
 
 // ---- int16 coefficients -> K sign*bit planes, each CRT'd ---------------------------------------------------

@@ -104,6 +104,12 @@ class DeviceScheme:
     def synchronize(self) -> None:
         _raise(capi.lib().lat_ajtai_synchronize(self.scheme._h))
 
+    def set_step_overlap(self, on: bool) -> None:
+        """Let the witness kernel of a step start while the previous step's matrix-vector kernel is draining
+        (lat_ajtai_set_step_overlap).  Only for callers whose w_ccs tensors are complete before the previous
+        witness_commit was enqueued and whose stream carries nothing else between two calls (see the header)."""
+        _raise(capi.lib().lat_ajtai_set_step_overlap(self.scheme._h, int(on)))
+
     # -- diagnostics ---------------------------------------------------------------------------------------------------
     def set_profiling(self, on: bool) -> None:
         _raise(capi.lib().lat_ajtai_set_profiling(self.scheme._h, int(on)))

@@ -369,6 +369,42 @@ def test_commit_pipeline_errors():
     scheme.close()
 
 
+def test_step_overlap_gives_identical_commitments():
+    """lat_ajtai_set_step_overlap: consecutive device-resident steps whose kernels overlap (next witness kernel
+    under the draining matrix-vector kernel, alternating witness buffers) commit exactly what serialised steps do,
+    also when other entry points are interleaved."""
+    import torch
+    from latticeum_b200.device import DeviceScheme
+
+    kappa, wl, steps = 32, 4000, 12
+    n = wl * DP.L
+    A = CO.fill_uniform((kappa, n, 24), 85)
+    scheme = make_scheme(A)
+    eng = DeviceScheme(scheme)
+    ws = [eng.to_device(CO.fill_uniform((wl, 24), 860 + k)) for k in range(steps)]
+    exp = []
+    for k in range(steps):
+        cm = eng.new_commitment()
+        eng.witness_commit(ws[k], cm)
+        exp.append(cm.clone())
+    torch.cuda.synchronize()
+    eng.set_step_overlap(True)
+    outs = [eng.new_commitment() for _ in range(steps)]
+    for rep in range(3):
+        for k in range(steps):
+            eng.witness_commit(ws[k], outs[k])
+            if rep == 1 and k % 4 == 3:  # an unrelated call between two steps: f of a random vector, batch of 2
+                f = eng.to_device(CO.fill_uniform((2, n, 24), 900 + k))
+                eng.commit_ntt(f, eng.new_commitment(2))
+        torch.cuda.synchronize()
+        for k in range(steps):
+            assert torch.equal(outs[k], exp[k]), (rep, k)
+    _, f = CO.witness_from_w_ccs(ws[3].cpu().numpy().view(np.uint64), DP.B, DP.L)
+    assert np.array_equal(exp[3].cpu().numpy().view(np.uint64), CO.commit(A, f))
+    eng.set_step_overlap(False)
+    scheme.close()
+
+
 # ---- the zkVM's full size: oracle on a bounded part + size-independent properties -----------------------------------------
 @pytest.fixture(scope="module")
 def zkvm():
