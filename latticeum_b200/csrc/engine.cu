@@ -2,6 +2,7 @@
 // CPU fallback: every compute entry point ends in a CUDA kernel launch or fails with LAT_E_CUDA.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -108,16 +109,18 @@ struct lat_ajtai {
     bool has_resident = false;
     // pipelined host-buffer steps (lat_ajtai_submit_w_ccs / lat_ajtai_wait): per-slot input staging, result and flag
     struct Slot {
-        DevBuf in, cm, flag;          // w_ccs staging, kappa x 24 result, overflow flag
-        u64 *h_cm = nullptr;          // pinned mirror of cm (the caller's buffer may be pageable)
-        int *h_flag = nullptr;        // pinned
-        cudaEvent_t uploaded = nullptr, computed = nullptr, done = nullptr;
+        DevBuf in, cm, flag, ready;   // w_ccs staging, kappa x 24 result, overflow flag, "upload landed" ticket
+        // page-locked and mapped into the device address space: the last CTA of the matrix-vector kernel writes the
+        // commitment, the overflow flag and finally the ticket here; lat_ajtai_wait polls the ticket
+        u64 *h_cm = nullptr;
+        int *h_flag = nullptr;
+        volatile unsigned long long *h_done = nullptr;
+        unsigned long long *h_ticket = nullptr;  // source of the ticket copy that follows the upload
         uint64_t ticket = 0;
         uint64_t *user_cm = nullptr;
         bool busy = false;
     };
     Slot slots[LAT_PIPELINE_DEPTH];
-    cudaStream_t d2h_stream = nullptr;
     uint64_t next_ticket = 0;
     // profiling: pool of event pairs around mac_kernel launches, drained lazily
     static constexpr int EV_POOL = 256;
@@ -156,7 +159,7 @@ struct lat_ajtai {
                                                     ", expected: " + std::to_string(n));
     }
     // mac + reduce into cms_dev for `count` witnesses in the extended layout, count x stride x 48
-    int mac_fx(const u64 *Fx, u64 stride, uint32_t count, u64 *cms_dev) {
+    int mac_fx(const u64 *Fx, u64 stride, uint32_t count, u64 *cms_dev, const lat::MacReport &report = lat::MacReport()) {
         lat::MacPlan plan = lat::plan_mac(lay, count, sm_count);
         size_t had = ws.bytes;
         int st = ws.ensure(plan.ws_elems * sizeof(u64));
@@ -171,7 +174,7 @@ struct lat_ajtai {
             e1 = ev1[i];
             ev_pending[i] = 1;
         }
-        lat::launch_mac(A.as<u64>(), lay, Fx, stride, count, plan, ws.as<u64>(), cms_dev, stream, e0, e1);
+        lat::launch_mac(A.as<u64>(), lay, Fx, stride, count, plan, ws.as<u64>(), cms_dev, stream, e0, e1, report);
         CK(cudaGetLastError());
         last_mac_src = Fx;
         last_op_was_mac = true;
@@ -281,17 +284,17 @@ void lat_ajtai_destroy(lat_ajtai *h) {
                       &h->rho, &h->f0, &h->planes_coeff, &h->cms, &h->cm_in, &h->ws, &h->flag, &h->fx_alt};
     for (DevBuf *b : bufs) b->release();
     if (h->h_flag) cudaFreeHost(h->h_flag);
-    if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     for (lat_ajtai::Slot &sl : h->slots) {
         sl.in.release();
         sl.cm.release();
         sl.flag.release();
+        sl.ready.release();
         if (sl.h_cm) cudaFreeHost(sl.h_cm);
         if (sl.h_flag) cudaFreeHost(sl.h_flag);
-        for (cudaEvent_t ev : {sl.uploaded, sl.computed, sl.done})
-            if (ev) cudaEventDestroy(ev);
+        if (sl.h_done) cudaFreeHost((void *)sl.h_done);
+        if (sl.h_ticket) cudaFreeHost(sl.h_ticket);
     }
-    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     for (cudaEvent_t e : h->ev0) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev1) cudaEventDestroy(e);
     for (cudaEvent_t ev : h->copy_done)
@@ -520,12 +523,24 @@ int lat_ajtai_decompose_and_commit_coeff(lat_ajtai *h, const uint64_t *w_coeff, 
 static int slot_prepare(lat_ajtai *h, lat_ajtai::Slot &sl, size_t in_bytes) {
     int st;
     const size_t cm_bytes = (size_t)h->kappa * ELEM_BYTES;
-    if ((st = sl.in.ensure(in_bytes)) || (st = sl.cm.ensure(cm_bytes)) || (st = sl.flag.ensure(sizeof(int)))) return st;
-    if (!sl.h_cm) CK(cudaHostAlloc((void **)&sl.h_cm, cm_bytes, cudaHostAllocDefault));
-    if (!sl.h_flag) CK(cudaHostAlloc((void **)&sl.h_flag, sizeof(int), cudaHostAllocDefault));
-    for (cudaEvent_t *ev : {&sl.uploaded, &sl.computed, &sl.done})
-        if (!*ev) CK(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
-    if (!h->d2h_stream) CK(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    if ((st = sl.in.ensure(in_bytes)) || (st = sl.cm.ensure(cm_bytes))) return st;
+    if (!sl.flag.p) {
+        if ((st = sl.flag.ensure(sizeof(int))) || (st = sl.ready.ensure(sizeof(unsigned long long)))) return st;
+        CK(cudaMemset(sl.flag.p, 0, sizeof(int)));
+        CK(cudaMemset(sl.ready.p, 0xff, sizeof(unsigned long long)));  // no ticket has this value
+    }
+    if (!sl.h_cm) CK(cudaHostAlloc((void **)&sl.h_cm, cm_bytes, cudaHostAllocMapped));
+    if (!sl.h_flag) CK(cudaHostAlloc((void **)&sl.h_flag, sizeof(int), cudaHostAllocMapped));
+    if (!sl.h_ticket) CK(cudaHostAlloc((void **)&sl.h_ticket, sizeof(unsigned long long), cudaHostAllocDefault));
+    if (!sl.h_done) {
+        CK(cudaHostAlloc((void **)&sl.h_done, sizeof(unsigned long long), cudaHostAllocMapped));
+        *sl.h_done = ~0ull;
+    }
+    return LAT_OK;
+}
+
+static int device_view(void *host, void **dev) {
+    CK(cudaHostGetDevicePointer(dev, host, 0));
     return LAT_OK;
 }
 
@@ -537,28 +552,39 @@ int lat_ajtai_submit_w_ccs(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_len, 
     lat_ajtai::Slot &sl = h->slots[h->next_ticket % LAT_PIPELINE_DEPTH];
     if (sl.busy)
         return fail(LAT_E_INVALID_ARGUMENT, "pipeline full: lat_ajtai_wait(ticket " + std::to_string(sl.ticket) + ") first");
-    const size_t in_bytes = w_len * ELEM_BYTES, cm_bytes = (size_t)h->kappa * ELEM_BYTES;
+    const size_t in_bytes = w_len * ELEM_BYTES;
     if ((st = slot_prepare(h, sl, in_bytes))) return st;
-    // upload on the copy stream (the slot's previous user was waited for, so its staging buffer is free)
+    const unsigned long long tk = h->next_ticket;
+    // Upload on the copy stream, followed by a copy of the ticket: the witness kernel polls that word instead of the
+    // compute stream waiting for an event, so the compute stream is a pure chain of kernels -- witness, matrix-vector,
+    // witness, ... -- that overlap through programmatic dependent launches (see witness_kernel / mac_kernel).
+    *sl.h_ticket = tk;
     CK(cudaMemcpyAsync(sl.in.p, w_ccs, in_bytes, cudaMemcpyHostToDevice, h->copy_stream));
-    CK(cudaEventRecord(sl.uploaded, h->copy_stream));
-    // compute on the handle's stream
-    CK(cudaStreamWaitEvent(h->stream, sl.uploaded, 0));
-    CK(cudaMemsetAsync(sl.flag.p, 0, sizeof(int), h->stream));
+    CK(cudaMemcpyAsync(sl.ready.p, sl.h_ticket, sizeof(unsigned long long), cudaMemcpyHostToDevice, h->copy_stream));
+    // this step's kernel may start under the previous step's draining matrix-vector kernel: other witness buffer
+    u64 *fxp = h->fx.as<u64>();
+    const bool chained = h->mac_was_last && !h->profiling;
+    if (chained && h->last_mac_src == h->fx.p) {
+        if ((st = h->fx_alt.ensure(h->n * lat::FX_WORDS * sizeof(u64)))) return st;
+        fxp = h->fx_alt.as<u64>();
+    }
     lat::launch_witness(sl.in.as<u64>(), w_len, (int)h->log2_B, (int)h->L, h->mont, false, h->f16.as<int16_t>(), nullptr, nullptr,
-                        h->fx.as<u64>(), sl.flag.as<int>(), h->stream);
+                        fxp, sl.flag.as<int>(), h->stream, chained, sl.ready.as<unsigned long long>(), tk);
     CK(cudaGetLastError());
     h->has_resident = true;
-    if ((st = h->mac_fx(h->fx.as<u64>(), h->n, 1, sl.cm.as<u64>()))) return st;
-    CK(cudaEventRecord(sl.computed, h->stream));
-    // download on the second copy stream
-    CK(cudaStreamWaitEvent(h->d2h_stream, sl.computed, 0));
-    CK(cudaMemcpyAsync(sl.h_cm, sl.cm.p, cm_bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
-    CK(cudaMemcpyAsync(sl.h_flag, sl.flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->d2h_stream));
-    CK(cudaEventRecord(sl.done, h->d2h_stream));
+    // the matrix-vector kernel reports straight into mapped host memory: commitment, overflow flag, then the ticket
+    lat::MacReport rep;
+    unsigned long long *done_dev = nullptr;
+    if ((st = device_view(sl.h_cm, (void **)&rep.cm_host)) || (st = device_view(sl.h_flag, (void **)&rep.flag_host)) ||
+        (st = device_view(const_cast<unsigned long long *>(sl.h_done), (void **)&done_dev)))
+        return st;
+    rep.flag_dev = sl.flag.as<int>();
+    rep.done_host = done_dev;
+    rep.done_value = tk;
+    if ((st = h->mac_fx(fxp, h->n, 1, sl.cm.as<u64>(), rep))) return st;
     sl.busy = true;
     sl.user_cm = cm;
-    sl.ticket = h->next_ticket;
+    sl.ticket = tk;
     *ticket = h->next_ticket++;
     return LAT_OK;
 }
@@ -567,10 +593,18 @@ int lat_ajtai_wait(lat_ajtai *h, uint64_t ticket) {
     if (!h) return fail(LAT_E_INVALID_ARGUMENT, "NULL handle");
     lat_ajtai::Slot &sl = h->slots[ticket % LAT_PIPELINE_DEPTH];
     if (!sl.busy || sl.ticket != ticket) return fail(LAT_E_INVALID_ARGUMENT, "no such ticket in flight");
-    int st = h->bind();
-    if (st) return st;
+    CK(cudaSetDevice(h->device));  // not bind(): waiting enqueues nothing, the kernel chain stays intact
     sl.busy = false;
-    CK(cudaEventSynchronize(sl.done));
+    // poll the ticket the last CTA publishes; look at the stream now and then so that a device fault cannot hang us
+    for (unsigned spins = 0; *sl.h_done != ticket; ++spins) {
+        if ((spins & 0xffff) == 0xffff) {
+            cudaError_t e = cudaStreamQuery(h->stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) return fail_cuda(e, "lat_ajtai_wait", __LINE__);
+            if (e == cudaSuccess && *sl.h_done != ticket)
+                return fail(LAT_E_CUDA, "stream idle but the step never reported completion");
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
     memcpy(sl.user_cm, sl.h_cm, (size_t)h->kappa * ELEM_BYTES);
     if (*sl.h_flag)
         return fail(LAT_E_DIGIT_OVERFLOW, "a coefficient needs more digits than the decomposition padding allows");

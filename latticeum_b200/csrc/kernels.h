@@ -21,7 +21,8 @@ void launch_icrt(const u64 *in, u64 *out, u64 count, cudaStream_t stream);
 //   fx       : CRT form in the MAC kernel's extended layout, w_len*L x 48, or nullptr
 //   flag     : device int, OR-ed with 1 when a coefficient does not fit in L digits
 void launch_witness(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool in_coeff, int16_t *f16, u64 *f_coeff,
-                    u64 *f_plain, u64 *fx, int *flag, cudaStream_t stream, bool overlap_previous = false);
+                    u64 *f_plain, u64 *fx, int *flag, cudaStream_t stream, bool overlap_previous = false,
+                    const unsigned long long *ready_flag = nullptr, unsigned long long ready_value = 0);
 
 // int16 coefficients -> K base-2 digit planes: plane k of element j = sign * bit_k(|c|).
 //   planes_f     : K x n x 24 CRT form, or nullptr
@@ -74,9 +75,19 @@ void launch_fext(const u64 *f, u64 count, u64 *fx, cudaStream_t stream);
 
 // cms[p][i][24] = sum_j A[i][j] * F[p][j]   for p < planes;  Fx: planes x f_stride x 48 in the extended layout
 // (f_stride >= n in elements; no padding needed).
+// Optional completion report straight into page-locked host memory (pipelined host-buffer steps): the last CTA also
+// stores the commitment to cm_host, moves the step's overflow flag to flag_host (clearing the device copy) and then
+// publishes done_value in *done_host with system scope -- no copy, no event, nothing between two kernels in the stream.
+struct MacReport {
+    u64 *cm_host = nullptr;
+    int *flag_dev = nullptr;
+    int *flag_host = nullptr;
+    unsigned long long *done_host = nullptr;
+    unsigned long long done_value = 0;
+};
 void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes, const MacPlan &plan,
                 u64 *workspace, u64 *cms, cudaStream_t stream, cudaEvent_t ev_begin = nullptr,
-                cudaEvent_t ev_end = nullptr);
+                cudaEvent_t ev_end = nullptr, const MacReport &report = MacReport());
 
 // cms[0] = cm - sum_{k=1..K-1} 2^k cms[k]      (LF/nifs/decomposition.rs:189-197)
 void launch_y0(const u64 *cm, u64 *cms, uint32_t K, uint32_t kappa, cudaStream_t stream);

@@ -203,7 +203,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 template <int PT, int RG>
 __global__ void __launch_bounds__(MacGeo<PT, RG>::THREADS, MacGeo<PT, RG>::MIN_CTAS)
 mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__ Fx, u64 f_stride, uint32_t planes,
-           uint32_t stages, u64 *__restrict__ ws, u64 *__restrict__ cms, uint32_t dependent_launch) {
+           uint32_t stages, u64 *__restrict__ ws, u64 *__restrict__ cms, uint32_t dependent_launch, MacReport report) {
     using G = MacGeo<PT, RG>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // after the stages: [full mbarrier x stages][release counter x stages]
@@ -367,11 +367,24 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
             u64 lo = __ldcg(ws + 2 * i), hi = __ldcg(ws + 2 * i + 1);   // sums of low / high halves
             u64 v_lo = lo + (hi << 32);
             u64 v_hi = (hi >> 32) + (v_lo < lo ? 1ull : 0ull);
-            cms[i] = gl::reduce128(v_lo, v_hi);
+            const u64 v = gl::reduce128(v_lo, v_hi);
+            cms[i] = v;
+            if (report.cm_host) report.cm_host[i] = v;
             ws[2 * i] = 0;
             ws[2 * i + 1] = 0;
         }
         if (threadIdx.x == 0) *counter = 0;
+        if (report.done_host) {  // results and flag first, then the ticket, each with system scope (the host polls it)
+            if (threadIdx.x == 0 && report.flag_dev) {
+                *report.flag_host = *reinterpret_cast<volatile int *>(report.flag_dev);
+                *report.flag_dev = 0;
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(report.done_host), "l"(report.done_value) : "memory");
+            }
+        }
     }
     TRACE(4);
 }
@@ -419,7 +432,7 @@ MacPlan plan_mac(const MatLayout &lay, uint32_t planes, int sm_count) {
 
 template <int PT, int RG>
 static void launch_mac_t(dim3 grid, const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes,
-                         const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream, bool pdl) {
+                         const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream, bool pdl, const MacReport &report) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(mac_kernel<PT, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // minus the static bytes
@@ -445,33 +458,34 @@ static void launch_mac_t(dim3 grid, const u64 *A_dev, const MatLayout &lay, cons
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, mac_kernel<PT, RG>, A_dev, lay, Fx, f_stride, planes, plan.stages, workspace, cms, (uint32_t)(pdl ? 1 : 0));
+    cudaLaunchKernelEx(&cfg, mac_kernel<PT, RG>, A_dev, lay, Fx, f_stride, planes, plan.stages, workspace, cms, (uint32_t)(pdl ? 1 : 0), report);
 }
 
 template <int PT>
 static void launch_mac_pt(dim3 grid, const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes,
-                          const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream, bool pdl) {
+                          const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream, bool pdl, const MacReport &report) {
     switch (lay.rg) {
-        case 1: launch_mac_t<PT, 1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl); break;
-        case 2: launch_mac_t<PT, 2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl); break;
-        case 3: launch_mac_t<PT, 3>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl); break;
-        case 4: launch_mac_t<PT, 4>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl); break;
-        case 5: launch_mac_t<PT, 5>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl); break;
-        case 6: launch_mac_t<PT, 6>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl); break;
-        case 7: launch_mac_t<PT, 7>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl); break;
-        default: launch_mac_t<PT, 8>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl); break;
+        case 1: launch_mac_t<PT, 1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 2: launch_mac_t<PT, 2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 3: launch_mac_t<PT, 3>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 4: launch_mac_t<PT, 4>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 5: launch_mac_t<PT, 5>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 6: launch_mac_t<PT, 6>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 7: launch_mac_t<PT, 7>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        default: launch_mac_t<PT, 8>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
     }
 }
 
 void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes, const MacPlan &plan,
-                u64 *workspace, u64 *cms, cudaStream_t stream, cudaEvent_t ev_begin, cudaEvent_t ev_end) {
+                u64 *workspace, u64 *cms, cudaStream_t stream, cudaEvent_t ev_begin, cudaEvent_t ev_end,
+                const MacReport &report) {
     dim3 grid(plan.grid_x, lay.nrb, planes / plan.pt);
     // overlap with the producer kernel's tail unless events bracket the launch (they would serialise it anyway)
     static const bool pdl_off = getenv("LAT_NO_PDL") != nullptr;
     const bool pdl = !ev_begin && !pdl_off;
     if (ev_begin) cudaEventRecord(ev_begin, stream);
-    if (plan.pt == 1) launch_mac_pt<1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl);
-    else launch_mac_pt<2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl);
+    if (plan.pt == 1) launch_mac_pt<1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report);
+    else launch_mac_pt<2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report);
     if (ev_end) cudaEventRecord(ev_end, stream);
 }
 
