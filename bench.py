@@ -225,7 +225,7 @@ def run_ours(args):
     partial = eng.new_commitment()
     # Consecutive steps may overlap on the device (the next step's witness kernel starts under the draining
     # matrix-vector kernel): legal here because every step's w_ccs is resident before the timed region starts.
-    step_overlap = world == 1 and os.environ.get("LAT_STEP_OVERLAP", "1") == "1"
+    step_overlap = os.environ.get("LAT_STEP_OVERLAP", "1") == "1"
     eng.set_step_overlap(step_overlap)
 
     def step():

@@ -590,6 +590,11 @@ void launch_recompose(const u64 *f, u64 count, int log2b, int L, u64 *out, cudaS
 __global__ void __launch_bounds__(256)
 exchange_kernel(const u64 *__restrict__ partial, u64 words, int rank, int world, PeerPtrs peers, u64 epoch,
                 u64 *__restrict__ out) {
+    // Programmatic dependent launch on both sides: this block may become resident while the matrix-vector kernel that
+    // produces `partial` is still running (it waits for it here), and the NEXT step's witness kernel may start behind
+    // it at once -- so the whole exchange, NVLink latency included, hides under that kernel (lat_ajtai_set_step_overlap).
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const u64 slot = epoch & 1;
     for (int r = 0; r < world; ++r) {
         u64 *dst = peers.recv[r] + (slot * world + rank) * words;
@@ -621,7 +626,16 @@ exchange_kernel(const u64 *__restrict__ partial, u64 words, int rank, int world,
 }
 void launch_exchange(const u64 *partial, u64 words, int rank, int world, const PeerPtrs &peers, u64 epoch, u64 *out,
                      cudaStream_t stream) {
-    exchange_kernel<<<1, 256, 0, stream>>>(partial, words, rank, world, peers, epoch, out);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(256);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, exchange_kernel, partial, words, rank, world, peers, epoch, out);
 }
 
 // Sum of `count` partial commitments mod q (column-sharded multi-GPU exchange).
