@@ -132,12 +132,12 @@ int lat_ajtai_witness_from_w_ccs_dev(lat_ajtai *h, const uint64_t *w_ccs_dev, ui
 
 /* Pipelined form of the same call for a stream of steps (the zkVM commits one witness per VM step,
  * ZKVM/main.rs:121-219,348-367, and knows step i+1's w_ccs before it needs step i's commitment):
- * lat_ajtai_submit_w_ccs queues upload -> iCRT/decompose/CRT -> A * f -> download of cm on separate copy and compute
- * streams and returns at once with a ticket; lat_ajtai_wait blocks until that ticket's cm has been written (and
- * reports its LAT_E_DIGIT_OVERFLOW, if any).  At most LAT_PIPELINE_DEPTH tickets may be outstanding; w_ccs and cm must
- * stay valid until the ticket has been waited for.  The transfers overlap the kernels only for page-locked w_ccs
- * (lat_host_alloc / cudaHostRegister); pageable memory works but serialises the upload.  The handle's "current
- * witness" is the one submitted last.                                                                          */
+ * lat_ajtai_submit_w_ccs queues upload -> iCRT/decompose/CRT -> A * f -> report of cm and returns at once with a
+ * ticket; lat_ajtai_wait blocks until that ticket's cm has been written (and reports its LAT_E_DIGIT_OVERFLOW, if
+ * any).  At most LAT_PIPELINE_DEPTH tickets may be outstanding; w_ccs and cm must stay valid until the ticket has
+ * been waited for.  The upload runs on a copy engine and the kernels of consecutive steps overlap on the device, so
+ * with page-locked w_ccs (lat_host_alloc / cudaHostRegister) the call sustains the device-resident rate; pageable
+ * memory works but serialises the upload.  The handle's "current witness" is the one submitted last.            */
 #define LAT_PIPELINE_DEPTH 4
 int lat_ajtai_submit_w_ccs(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_len, uint64_t *cm, uint64_t *ticket);
 int lat_ajtai_wait(lat_ajtai *h, uint64_t ticket);

@@ -509,49 +509,64 @@ void launch_y0(const u64 *cm, u64 *cms, uint32_t K, uint32_t kappa, cudaStream_t
 // consecutive slots), multiplies by rho_i's slot from shared memory and accumulates lazily with the same Karatsuba
 // accumulators as the MAC; one reduction at the end.  HBM-bound on reading the planes once (2K x n x 384 B).
 constexpr int FOLD_MAX_PLANES = 64;
+constexpr int FOLD_THREADS = 256, FOLD_STAGES = 4;
+constexpr u32 FOLD_STAGE_BYTES = FOLD_THREADS * 6 * 8;  // one plane's 48-byte slots of the block's 256 (element, slot) items
 template <bool MONT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FOLD_THREADS)
 fold_kernel(const u64 *__restrict__ s0, const u64 *__restrict__ s1, int nsides, int pps, u64 n, const u64 *__restrict__ rho,
             u64 *__restrict__ f0) {
+    // The block's items are consecutive (element, slot) pairs, so plane p's share of them is ONE contiguous run of
+    // 256 x 48 B: it is streamed with a TMA bulk copy into a ring of stages, FOLD_STAGES planes ahead of the
+    // arithmetic (plain loads left the kernel latency-bound at 4.1 TB/s: two 256-thread blocks per SM cannot keep
+    // enough 16-byte loads in flight).
+    extern __shared__ __align__(128) unsigned char fold_smem[];
     __shared__ u64 s_rho[FOLD_MAX_PLANES * ring::D];
+    __shared__ __align__(8) u64 bars[FOLD_STAGES];
     const int nplanes = nsides * pps;
+    const u64 total = n * ring::NSLOT;
+    const u64 item0 = (u64)blockIdx.x * FOLD_THREADS;
+    const u32 nitems = (u32)min((u64)FOLD_THREADS, total - item0);
+    const u32 bytes = nitems * 48;
+    auto plane_src = [&](int p) { return (p < pps ? s0 + (u64)p * n * FX : s1 + (u64)(p - pps) * n * FX) + item0 * 6; };
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < FOLD_STAGES; ++st) mbar_init(&bars[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int p = 0; p < FOLD_STAGES && p < nplanes; ++p) {
+            mbar_arrive_expect_tx(&bars[p], bytes);
+            tma_bulk_g2s(fold_smem + (size_t)p * FOLD_STAGE_BYTES, plane_src(p), bytes, &bars[p]);
+        }
+    }
     for (int i = threadIdx.x; i < nplanes * ring::D; i += blockDim.x) {
         u64 v = rho[i];
         s_rho[i] = MONT ? gl::from_mont(v) : gl::reduce128(v, 0);  // canonical(rho) * repr(f) = repr(rho * f)
     }
     __syncthreads();
-    const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;  // (element, slot)
-    if (idx >= n * ring::NSLOT) return;
+    const u64 idx = item0 + threadIdx.x;  // (element, slot)
+    const bool active = threadIdx.x < nitems;
     const u32 sl = (u32)(idx & 7);
     gl::Fq3Acc acc;
     acc.clear();
-    // HBM-bound (48 B per thread per plane, 2K planes): keep two planes' loads in flight ahead of the arithmetic
-    auto plane_ptr = [&](int p) {
-        const u64 *base = (p < pps ? s0 + (u64)p * n * FX : s1 + (u64)(p - pps) * n * FX) + idx * 6;
-        return reinterpret_cast<const ulonglong2 *>(base);
-    };
-    constexpr int AHEAD = 2;
-    ulonglong2 buf[AHEAD][3];
-#pragma unroll
-    for (int a = 0; a < AHEAD; ++a)
-        if (a < nplanes) {
-            const ulonglong2 *pf = plane_ptr(a);
-            buf[a][0] = __ldcs(pf); buf[a][1] = __ldcs(pf + 1); buf[a][2] = __ldcs(pf + 2);
-        }
-    for (int p0 = 0; p0 < nplanes; p0 += AHEAD) {
-#pragma unroll
-        for (int a = 0; a < AHEAD; ++a) {
-            const int p = p0 + a;
-            if (p >= nplanes) break;
-            const ulonglong2 x = buf[a][0], y = buf[a][1], z = buf[a][2];
-            if (p + AHEAD < nplanes) {
-                const ulonglong2 *pf = plane_ptr(p + AHEAD);
-                buf[a][0] = __ldcs(pf); buf[a][1] = __ldcs(pf + 1); buf[a][2] = __ldcs(pf + 2);
-            }
+    int st = 0;
+    u32 ph = 0;
+    for (int p = 0; p < nplanes; ++p) {
+        mbar_wait(&bars[st], ph);
+        if (active) {
+            const ulonglong2 *pf = reinterpret_cast<const ulonglong2 *>(fold_smem + (size_t)st * FOLD_STAGE_BYTES) + threadIdx.x * 3;
+            const ulonglong2 x = pf[0], y = pf[1], z = pf[2];
             const u64 *r = s_rho + p * ring::D + 3 * sl;
             acc.mac(r[0], r[1], r[2], x.x, x.y, y.x, y.y, z.x, z.y);
         }
+        __syncthreads();  // everyone has read the stage
+        if (threadIdx.x == 0 && p + FOLD_STAGES < nplanes) {
+            mbar_arrive_expect_tx(&bars[st], bytes);
+            tma_bulk_g2s(fold_smem + (size_t)st * FOLD_STAGE_BYTES, plane_src(p + FOLD_STAGES), bytes, &bars[st]);
+        }
+        if (++st == FOLD_STAGES) {
+            st = 0;
+            ph ^= 1;
+        }
     }
+    if (!active) return;
     u64 c0, c1, c2;
     acc.finish(c0, c1, c2);
     u64 *o = f0 + idx * 3;  // element * 24 + slot * 3
@@ -560,10 +575,17 @@ fold_kernel(const u64 *__restrict__ s0, const u64 *__restrict__ s1, int nsides, 
 void launch_fold(const u64 *const *sides_fx, int nsides, int planes_per_side, u64 n, const u64 *rho, bool mont, u64 *f0,
                  cudaStream_t stream) {
     if (!n) return;
-    unsigned grid = (unsigned)((n * ring::NSLOT + 255) / 256);
+    unsigned grid = (unsigned)((n * ring::NSLOT + FOLD_THREADS - 1) / FOLD_THREADS);
     const u64 *a = sides_fx[0], *b = nsides > 1 ? sides_fx[1] : nullptr;
-    if (mont) fold_kernel<true><<<grid, 256, 0, stream>>>(a, b, nsides, planes_per_side, n, rho, f0);
-    else fold_kernel<false><<<grid, 256, 0, stream>>>(a, b, nsides, planes_per_side, n, rho, f0);
+    const size_t smem = (size_t)FOLD_STAGES * FOLD_STAGE_BYTES;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    if (mont) fold_kernel<true><<<grid, FOLD_THREADS, smem, stream>>>(a, b, nsides, planes_per_side, n, rho, f0);
+    else fold_kernel<false><<<grid, FOLD_THREADS, smem, stream>>>(a, b, nsides, planes_per_side, n, rho, f0);
 }
 
 // ---- gadget_recompose in CRT form: Horner from the top limb, result = result * B + v_l ---------------------------------

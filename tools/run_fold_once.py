@@ -1,4 +1,5 @@
-"""One fold-side call (decompose_witness + commit_witnesses) at the zkVM shape: a small target for ncu."""
+"""Both fold sides (decompose_witness + commit_witnesses) and the fold of the 2K planes (compute_f_0 + iCRT) at the zkVM
+shape: a small target for ncu."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -16,7 +17,14 @@ fc_dev = eng.to_device(fc)
 cm = eng.new_commitment()
 cms = torch.empty((K, KAPPA, 24), dtype=torch.int64, device="cuda")
 eng.commit_ntt(eng.to_device(rng.integers(0, 2**63, size=(N, 24), dtype=np.uint64)), cm)
-for _ in range(3):
+from latticeum_b200 import _capi as capi
+L = capi.lib()
+for side in (0, 1):
+    assert L.lat_ajtai_select_side(scheme._h, side) == 0
     eng.decompose_commit(fc_dev, cm, cms)
+rho = eng.to_device(rng.integers(0, 2**63, size=(2 * K, 24), dtype=np.uint64))
+f0 = torch.empty((N, 24), dtype=torch.int64, device="cuda")
+f0c = torch.empty_like(f0)
+assert L.lat_ajtai_fold_witness_dev(scheme._h, rho.data_ptr(), f0.data_ptr(), f0c.data_ptr()) == 0
 eng.synchronize()
 print("ok")
