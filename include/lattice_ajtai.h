@@ -211,6 +211,22 @@ int lat_commitment_exchange_dev(const uint64_t *partial_dev, uint64_t words, int
                                 const uint64_t *recv_ptrs, const uint64_t *flag_ptrs, uint64_t epoch,
                                 uint64_t *out_dev, void *cuda_stream);
 
+/* ---- building blocks of a host-buffer pipeline that enqueues nothing but kernels (sharded callers; the single-GPU
+ * form is lat_ajtai_submit_w_ccs).  Both keep event waits and copies out of the compute stream, so the kernels of
+ * consecutive steps keep overlapping (lat_ajtai_set_step_overlap):
+ *  - the gated witness call starts iCRT/decompose/CRT + A * f as usual, but its kernel first polls *ready_flag_dev
+ *    until it equals ready_value -- the caller uploads w_ccs_dev on another stream and then copies ready_value there.
+ *    Enqueue those copies BEFORE this call: a kernel must never wait for work submitted after it (streams can share
+ *    a hardware queue, and the copy would then sit behind the waiting kernel);
+ *  - the reporting exchange additionally stores the folded commitment to cm_host and then publishes done_value in
+ *    *done_host (both page-locked host memory, e.g. lat_host_alloc), which the host polls instead of synchronising. */
+int lat_ajtai_witness_from_w_ccs_gated_dev(lat_ajtai *h, const uint64_t *w_ccs_dev, uint64_t w_len, uint64_t *cm_dev,
+                                           const uint64_t *ready_flag_dev, uint64_t ready_value);
+int lat_commitment_exchange_report_dev(const uint64_t *partial_dev, uint64_t words, int rank, int world,
+                                       const uint64_t *recv_ptrs, const uint64_t *flag_ptrs, uint64_t epoch,
+                                       uint64_t *out_dev, uint64_t *cm_host, uint64_t *done_host, uint64_t done_value,
+                                       void *cuda_stream);
+
 /* ---- overlap of consecutive steps on the device ---------------------------------------------------------------------
  * With the option enabled, the iCRT/decompose/CRT kernel of a lat_ajtai_witness_from_w_ccs_dev call that directly
  * follows a commitment on the same handle starts while that commitment's matrix-vector kernel is still draining

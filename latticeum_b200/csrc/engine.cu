@@ -280,6 +280,7 @@ void lat_ajtai_destroy(lat_ajtai *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+    if (h->stream && h->stream != h->own_stream) cudaStreamSynchronize(h->stream);  // steps in flight write into our buffers
     DevBuf *bufs[] = {&h->A, &h->stage, &h->in, &h->f16, &h->f, &h->fx, &h->fcoeff64, &h->planes, &h->planes_fx[0], &h->planes_fx[1],
                       &h->rho, &h->f0, &h->planes_coeff, &h->cms, &h->cm_in, &h->ws, &h->flag, &h->fx_alt};
     for (DevBuf *b : bufs) b->release();
@@ -411,7 +412,7 @@ int lat_ajtai_commit_coeff(lat_ajtai *h, const uint64_t *f_coeff, uint64_t f_len
 
 // shared by from_w_ccs and decompose_and_commit_*: device input -> digits -> CRT -> (commit)
 static int witness_core(lat_ajtai *h, const u64 *w_dev, u64 w_len, bool in_coeff, u64 *f_coeff_dev, u64 *f_dev,
-                        u64 *cm_dev) {
+                        u64 *cm_dev, const unsigned long long *ready_flag = nullptr, unsigned long long ready_value = 0) {
     // one kernel: iCRT -> digits -> CRT; the extended layout feeds the MAC, the plain layout only if the caller wants f
     // With step overlap this kernel may start while the previous commitment's matrix-vector kernel is draining: it
     // then writes the witness buffer that kernel is NOT reading (the protocol in ring_kernels.cu / mac_kernels.cu
@@ -424,7 +425,7 @@ static int witness_core(lat_ajtai *h, const u64 *w_dev, u64 w_len, bool in_coeff
         fxp = h->fx_alt.as<u64>();
     }
     lat::launch_witness(w_dev, w_len, (int)h->log2_B, (int)h->L, h->mont, in_coeff, h->f16.as<int16_t>(), f_coeff_dev,
-                        f_dev, cm_dev ? fxp : nullptr, h->flag.as<int>(), h->stream, chained);
+                        f_dev, cm_dev ? fxp : nullptr, h->flag.as<int>(), h->stream, chained, ready_flag, ready_value);
     CK(cudaGetLastError());
     h->has_resident = true;
     if (cm_dev) return h->mac_fx(fxp, h->n, 1, cm_dev);
@@ -439,6 +440,16 @@ int lat_ajtai_witness_from_w_ccs_dev(lat_ajtai *h, const uint64_t *w_ccs_dev, ui
     if (st) return st;
     if (cm_dev && (st = h->matrix_ready())) return st;
     return witness_core(h, (const u64 *)w_ccs_dev, w_len, false, (u64 *)f_coeff_dev, (u64 *)f_dev, (u64 *)cm_dev);
+}
+
+int lat_ajtai_witness_from_w_ccs_gated_dev(lat_ajtai *h, const uint64_t *w_ccs_dev, uint64_t w_len, uint64_t *cm_dev,
+                                           const uint64_t *ready_flag_dev, uint64_t ready_value) {
+    if (!h || !w_ccs_dev || !cm_dev || !ready_flag_dev) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (w_len * h->L != h->n) return h->wrong_len(w_len * h->L);
+    int st = h->bind();
+    if (st || (st = h->matrix_ready())) return st;
+    return witness_core(h, (const u64 *)w_ccs_dev, w_len, false, nullptr, nullptr, (u64 *)cm_dev,
+                        (const unsigned long long *)ready_flag_dev, ready_value);
 }
 
 static int witness_host(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool in_coeff, uint64_t *f_coeff, uint64_t *f,
@@ -880,9 +891,10 @@ int lat_commitment_sum_dev(const uint64_t *parts_dev, uint32_t count, uint64_t w
     CK(cudaGetLastError());
     return LAT_OK;
 }
-int lat_commitment_exchange_dev(const uint64_t *partial_dev, uint64_t words, int rank, int world,
-                                const uint64_t *recv_ptrs, const uint64_t *flag_ptrs, uint64_t epoch,
-                                uint64_t *out_dev, void *cuda_stream) {
+int lat_commitment_exchange_report_dev(const uint64_t *partial_dev, uint64_t words, int rank, int world,
+                                       const uint64_t *recv_ptrs, const uint64_t *flag_ptrs, uint64_t epoch,
+                                       uint64_t *out_dev, uint64_t *cm_host, uint64_t *done_host, uint64_t done_value,
+                                       void *cuda_stream) {
     if (!partial_dev || !recv_ptrs || !flag_ptrs || !out_dev) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
     if (world < 1 || world > lat::MAX_PEERS || rank < 0 || rank >= world || epoch == 0)
         return fail(LAT_E_INVALID_ARGUMENT, "need 1 <= world <= 16, 0 <= rank < world, epoch >= 1");
@@ -891,9 +903,21 @@ int lat_commitment_exchange_dev(const uint64_t *partial_dev, uint64_t words, int
         peers.recv[r] = reinterpret_cast<u64 *>(recv_ptrs[r]);
         peers.flags[r] = reinterpret_cast<u64 *>(flag_ptrs[r]);
     }
-    lat::launch_exchange((const u64 *)partial_dev, words, rank, world, peers, epoch, (u64 *)out_dev, (cudaStream_t)cuda_stream);
+    u64 *cm_map = nullptr;
+    unsigned long long *done_map = nullptr;
+    if (cm_host) CK(cudaHostGetDevicePointer((void **)&cm_map, cm_host, 0));
+    if (done_host) CK(cudaHostGetDevicePointer((void **)&done_map, done_host, 0));
+    lat::launch_exchange((const u64 *)partial_dev, words, rank, world, peers, epoch, (u64 *)out_dev, (cudaStream_t)cuda_stream,
+                         cm_map, done_map, done_value);
     CK(cudaGetLastError());
     return LAT_OK;
+}
+
+int lat_commitment_exchange_dev(const uint64_t *partial_dev, uint64_t words, int rank, int world,
+                                const uint64_t *recv_ptrs, const uint64_t *flag_ptrs, uint64_t epoch,
+                                uint64_t *out_dev, void *cuda_stream) {
+    return lat_commitment_exchange_report_dev(partial_dev, words, rank, world, recv_ptrs, flag_ptrs, epoch, out_dev, nullptr,
+                                              nullptr, 0, cuda_stream);
 }
 
 int lat_commitment_sum(const uint64_t *parts, uint32_t count, uint64_t words, uint64_t *out, int device) {

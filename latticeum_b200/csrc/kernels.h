@@ -110,6 +110,7 @@ struct PeerPtrs {
     u64 *flags[MAX_PEERS];
 };
 void launch_exchange(const u64 *partial, u64 words, int rank, int world, const PeerPtrs &peers, u64 epoch, u64 *out,
-                     cudaStream_t stream);
+                     cudaStream_t stream, u64 *report_cm = nullptr,
+                     unsigned long long *report_done = nullptr, unsigned long long done_value = 0);
 
 }  // namespace lat

@@ -611,7 +611,8 @@ void launch_recompose(const u64 *f, u64 count, int log2b, int L, u64 *out, cudaS
 // was written by other GPUs).
 __global__ void __launch_bounds__(256)
 exchange_kernel(const u64 *__restrict__ partial, u64 words, int rank, int world, PeerPtrs peers, u64 epoch,
-                u64 *__restrict__ out) {
+                u64 *__restrict__ out, u64 *__restrict__ report_cm, unsigned long long *report_done,
+                unsigned long long done_value) {
     // Programmatic dependent launch on both sides: this block may become resident while the matrix-vector kernel that
     // produces `partial` is still running (it waits for it here), and the NEXT step's witness kernel may start behind
     // it at once -- so the whole exchange, NVLink latency included, hides under that kernel (lat_ajtai_set_step_overlap).
@@ -643,11 +644,18 @@ exchange_kernel(const u64 *__restrict__ partial, u64 words, int rank, int world,
             lo += v;
             hi += (lo < v);
         }
-        out[i] = gl::reduce128(lo, hi);
+        const u64 r = gl::reduce128(lo, hi);
+        out[i] = r;
+        if (report_cm) report_cm[i] = r;  // mapped host memory
+    }
+    if (report_done) {  // the host polls this word (see MacReport)
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(report_done), "l"(done_value) : "memory");
     }
 }
 void launch_exchange(const u64 *partial, u64 words, int rank, int world, const PeerPtrs &peers, u64 epoch, u64 *out,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, u64 *report_cm, unsigned long long *report_done, unsigned long long done_value) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(1);
     cfg.blockDim = dim3(256);
@@ -657,7 +665,7 @@ void launch_exchange(const u64 *partial, u64 words, int rank, int world, const P
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, exchange_kernel, partial, words, rank, world, peers, epoch, out);
+    cudaLaunchKernelEx(&cfg, exchange_kernel, partial, words, rank, world, peers, epoch, out, report_cm, report_done, done_value);
 }
 
 // Sum of `count` partial commitments mod q (column-sharded multi-GPU exchange).

@@ -62,6 +62,16 @@ class DeviceScheme:
         _raise(st, w_ccs.shape[0] * self.L, self.n)
         return cm
 
+    def witness_commit_gated(self, w_ccs: torch.Tensor, cm: torch.Tensor, ready_flag: torch.Tensor, ready_value: int) -> torch.Tensor:
+        """witness_commit whose kernel first polls `ready_flag` (a 1-element int64 CUDA tensor) until it holds
+        `ready_value`: the caller uploads w_ccs on another stream and copies the value there afterwards, so the compute
+        stream needs no event wait (lat_ajtai_witness_from_w_ccs_gated_dev)."""
+        self.bind_stream()
+        st = capi.lib().lat_ajtai_witness_from_w_ccs_gated_dev(self.scheme._h, self._check(w_ccs, "w_ccs"), w_ccs.shape[0],
+                                                               self._check(cm, "cm"), ready_flag.data_ptr(), ready_value)
+        _raise(st, w_ccs.shape[0] * self.L, self.n)
+        return cm
+
     def commit_ntt(self, f: torch.Tensor, cm: torch.Tensor) -> torch.Tensor:
         self.bind_stream()
         if f.dim() == 3:
@@ -89,16 +99,18 @@ class DeviceScheme:
         _raise(capi.lib().lat_commitment_sum_dev(parts.data_ptr(), parts.shape[0], words, out.data_ptr(), C.c_void_p(s)))
         return out
 
-    def exchange_partials(self, partial: torch.Tensor, out: torch.Tensor, peer) -> torch.Tensor:
+    def exchange_partials(self, partial: torch.Tensor, out: torch.Tensor, peer, report=None) -> torch.Tensor:
         """Fused NVLink exchange + mod-q fold of this rank's partial commitment with all peers (`peer` is a
-        latticeum_b200.sharded.PeerExchange).  Asynchronous on torch's current stream."""
+        latticeum_b200.sharded.PeerExchange).  Asynchronous on torch's current stream.  `report` = (cm_host, done_host,
+        value): pinned host tensors the kernel also writes the result and then `value` to (the host polls done_host)."""
         peer.epoch += 1
         n = peer.world
         recv = (C.c_uint64 * n)(*peer.recv_ptrs)
         flags = (C.c_uint64 * n)(*peer.flag_ptrs)
         s = torch.cuda.current_stream(self.device).cuda_stream or 1
-        _raise(capi.lib().lat_commitment_exchange_dev(partial.data_ptr(), partial.numel(), peer.rank, n, recv, flags,
-                                                      peer.epoch, out.data_ptr(), C.c_void_p(s)))
+        cm_host, done_host, value = (report[0].data_ptr(), report[1].data_ptr(), report[2]) if report else (None, None, 0)
+        _raise(capi.lib().lat_commitment_exchange_report_dev(partial.data_ptr(), partial.numel(), peer.rank, n, recv, flags,
+                                                             peer.epoch, out.data_ptr(), cm_host, done_host, value, C.c_void_p(s)))
         return out
 
     def synchronize(self) -> None:

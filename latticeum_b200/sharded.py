@@ -107,17 +107,23 @@ class ShardedAjtaiScheme:
 
 class ShardedCommitPipeline:
     """A stream of per-step sharded commitments with HOST buffers: `submit(w_host)` queues, on this rank, the upload of
-    its block of the step's w_ccs (copy stream), witness_commit + the partial exchange (the engine's stream) and the
-    download of the full commitment (second copy stream), and returns a ticket; `wait(ticket)` returns the pinned
-    host tensor holding that step's commitment.  `depth` steps are in flight, so the PCIe transfers of neighbouring
-    steps hide under the kernels.  Every rank must submit the same sequence of steps (the exchange is collective).
-    On a CPU device (gloo tests) the same calls run synchronously."""
+    its block of the step's w_ccs, witness_commit + the partial exchange and the return of the full commitment, and
+    returns a ticket; `wait(ticket)` returns the pinned host tensor holding that step's commitment.  `depth` steps are
+    in flight, so the PCIe transfers of neighbouring steps hide under the kernels.  Every rank must submit the same
+    sequence of steps (the exchange is collective).
+
+    With the fused peer-memory exchange the compute stream carries nothing but kernels: the upload (copy stream) is
+    followed by a copy of the ticket that the witness kernel polls, and the exchange kernel writes the commitment and
+    then the ticket into pinned host memory that `wait` polls -- no event waits, so consecutive steps overlap on the
+    device (DeviceScheme.set_step_overlap).  With NCCL, or without an engine that offers the gated call, uploads and
+    downloads are ordered with events instead.  On a CPU device (gloo tests) the same calls run synchronously."""
 
     def __init__(self, sharded: ShardedAjtaiScheme, w_len_local: int, depth: int = 4):
         self.sharded, self.depth = sharded, depth
         eng = sharded.engine
         dev = getattr(eng, "device", torch.device("cpu"))
         self.cuda = dev.type == "cuda"
+        self.chain = self.cuda and sharded.peer is not None and hasattr(eng, "witness_commit_gated")
         self.next_ticket = 0
         self.slots = []
         for _ in range(depth):
@@ -130,20 +136,37 @@ class ShardedCommitPipeline:
             if self.cuda:
                 sl["cm_host"] = sl["cm_host"].pin_memory()
                 sl["uploaded"], sl["computed"], sl["done"] = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+            if self.chain:
+                sl["out"] = eng.new_commitment()
+                sl["ready"] = torch.full((1,), -1, dtype=torch.int64, device=dev)
+                sl["ticket_host"] = torch.zeros((1,), dtype=torch.int64).pin_memory()
+                sl["done_host"] = torch.full((1,), -1, dtype=torch.int64).pin_memory()
             self.slots.append(sl)
         if self.cuda:
             self.up, self.down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        if self.chain:
+            eng.set_step_overlap(True)
+            torch.cuda.synchronize(dev)
 
     def submit(self, w_host: torch.Tensor) -> int:
         sl = self.slots[self.next_ticket % self.depth]
         if sl["ticket"] is not None:
             raise RuntimeError(f"pipeline full: wait for ticket {sl['ticket']} first")
+        tk = self.next_ticket
+        eng = self.sharded.engine
         if not self.cuda:
             sl["w"].copy_(w_host)
             sl["cm_host"].copy_(self.sharded.witness_commit(sl["w"], sl["partial"]))
+        elif self.chain:
+            sl["ticket_host"][0] = tk
+            with torch.cuda.stream(self.up):  # the slot's previous user has been waited for: its buffers are free
+                sl["w"].copy_(w_host, non_blocking=True)
+                sl["ready"].copy_(sl["ticket_host"], non_blocking=True)
+            eng.witness_commit_gated(sl["w"], sl["partial"], sl["ready"], tk)
+            eng.exchange_partials(sl["partial"], sl["out"], self.sharded.peer, report=(sl["cm_host"], sl["done_host"], tk))
         else:
             compute = torch.cuda.current_stream()
-            with torch.cuda.stream(self.up):  # the slot's previous user has been waited for: its staging buffer is free
+            with torch.cuda.stream(self.up):
                 sl["w"].copy_(w_host, non_blocking=True)
                 sl["uploaded"].record(self.up)
             compute.wait_event(sl["uploaded"])
@@ -154,15 +177,21 @@ class ShardedCommitPipeline:
                 sl["cm_host"].copy_(cm, non_blocking=True)
                 sl["done"].record(self.down)
             cm.record_stream(self.down)
-        sl["ticket"] = self.next_ticket
+        sl["ticket"] = tk
         self.next_ticket += 1
-        return sl["ticket"]
+        return tk
 
     def wait(self, ticket: int) -> torch.Tensor:
         sl = self.slots[ticket % self.depth]
         if sl["ticket"] != ticket:
             raise KeyError(f"no such ticket in flight: {ticket}")
-        if self.cuda:
+        if self.chain:
+            done, spins = sl["done_host"], 0
+            while int(done[0]) != ticket:  # written by the exchange kernel after the commitment
+                spins += 1
+                if spins % 200000 == 0 and torch.cuda.current_stream().query() and int(done[0]) != ticket:
+                    raise RuntimeError("stream idle but the step never reported completion")
+        elif self.cuda:
             sl["done"].synchronize()
         sl["ticket"] = None
         return sl["cm_host"]

@@ -582,6 +582,46 @@ def test_commitment_sum_and_single_rank_exchange():
         assert torch.equal(res, partial)
     assert flags.tolist() == [2, 3]
     assert L.lat_commitment_exchange_dev(partial.data_ptr(), words, 0, 1, rp, fp, 0, res.data_ptr(), stream) == capi.LAT_E_INVALID_ARGUMENT
+    # reporting form: the kernel also writes the result and then the ticket into pinned host memory
+    cm_host = torch.zeros(words, dtype=torch.int64).pin_memory()
+    done_host = torch.full((1,), -1, dtype=torch.int64).pin_memory()
+    st = L.lat_commitment_exchange_report_dev(partial.data_ptr(), words, 0, 1, rp, fp, 4, res.data_ptr(), cm_host.data_ptr(),
+                                              done_host.data_ptr(), 77, stream)
+    assert st == 0, capi.last_error()
+    while int(done_host[0]) != 77:
+        pass
+    assert torch.equal(cm_host, partial.cpu())
+
+
+def test_gated_witness_call_waits_for_the_ticket():
+    # lat_ajtai_witness_from_w_ccs_gated_dev: the kernel polls a device word that the uploading stream writes after the
+    # data.  The copies are ENQUEUED before the call (the header's rule: a kernel must never wait for work submitted
+    # after it) but held back on their stream by a few milliseconds, so the kernel really has to wait.
+    import torch
+    from latticeum_b200.device import DeviceScheme
+
+    kappa, wl = 8, 500
+    n = wl * DP.L
+    A = CO.fill_uniform((kappa, n, 24), 130)
+    w = CO.fill_uniform((wl, 24), 131)
+    scheme = make_scheme(A)
+    eng = DeviceScheme(scheme)
+    w_pin = torch.from_numpy(w.view(np.int64)).pin_memory()
+    w_dev = torch.zeros((wl, 24), dtype=torch.int64, device="cuda")
+    ready = torch.full((1,), -1, dtype=torch.int64, device="cuda")
+    ticket = torch.tensor([41], dtype=torch.int64).pin_memory()
+    cm = eng.new_commitment()
+    up = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(up):
+        torch.cuda._sleep(10_000_000)  # ~5 ms on the upload stream: w_dev is still all zero when the kernel starts
+        w_dev.copy_(w_pin, non_blocking=True)
+        ready.copy_(ticket, non_blocking=True)
+    eng.witness_commit_gated(w_dev, cm, ready, 41)
+    torch.cuda.synchronize()
+    _, f = CO.witness_from_w_ccs(w, DP.B, DP.L)
+    assert np.array_equal(cm.cpu().numpy().view(np.uint64), CO.commit(A, f))
+    scheme.close()
 
 
 def test_cpp_host_mirror_example():
