@@ -211,6 +211,14 @@ int lat_commitment_exchange_dev(const uint64_t *partial_dev, uint64_t words, int
                                 const uint64_t *recv_ptrs, const uint64_t *flag_ptrs, uint64_t epoch,
                                 uint64_t *out_dev, void *cuda_stream);
 
+/* Column-sharded form of lat_ajtai_submit_w_ccs: once peers are set, every submitted step ends with the fused exchange
+ * (as lat_commitment_exchange_dev, with the given mailbox and flag addresses of all ranks) and lat_ajtai_wait returns
+ * the FULL commitment, summed over the ranks.  next_epoch is the epoch of the next exchange (the engine counts on from
+ * there; pass it again whenever other exchanges used the same mailboxes in between).  world <= 1 or NULL addresses
+ * switch back to the single-GPU behaviour.  Every rank must submit the same sequence of steps.                  */
+int lat_ajtai_set_peers(lat_ajtai *h, int rank, int world, const uint64_t *recv_ptrs, const uint64_t *flag_ptrs,
+                        uint64_t next_epoch);
+
 /* ---- building blocks of a host-buffer pipeline that enqueues nothing but kernels (sharded callers; the single-GPU
  * form is lat_ajtai_submit_w_ccs).  Both keep event waits and copies out of the compute stream, so the kernels of
  * consecutive steps keep overlapping (lat_ajtai_set_step_overlap):

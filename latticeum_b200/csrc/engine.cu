@@ -110,6 +110,7 @@ struct lat_ajtai {
     // pipelined host-buffer steps (lat_ajtai_submit_w_ccs / lat_ajtai_wait): per-slot input staging, result and flag
     struct Slot {
         DevBuf in, cm, flag, ready;   // w_ccs staging, kappa x 24 result, overflow flag, "upload landed" ticket
+        DevBuf out;                   // sharded steps: the full commitment after the exchange
         // page-locked and mapped into the device address space: the last CTA of the matrix-vector kernel writes the
         // commitment, the overflow flag and finally the ticket here; lat_ajtai_wait polls the ticket
         u64 *h_cm = nullptr;
@@ -121,6 +122,11 @@ struct lat_ajtai {
         bool busy = false;
     };
     Slot slots[LAT_PIPELINE_DEPTH];
+    // column sharding of the pipelined steps (lat_ajtai_set_peers)
+    bool has_peers = false;
+    int peer_rank = 0, peer_world = 1;
+    lat::PeerPtrs peers{};
+    uint64_t peer_epoch = 1;
     uint64_t next_ticket = 0;
     // profiling: pool of event pairs around mac_kernel launches, drained lazily
     static constexpr int EV_POOL = 256;
@@ -291,6 +297,7 @@ void lat_ajtai_destroy(lat_ajtai *h) {
         sl.cm.release();
         sl.flag.release();
         sl.ready.release();
+        sl.out.release();
         if (sl.h_cm) cudaFreeHost(sl.h_cm);
         if (sl.h_flag) cudaFreeHost(sl.h_flag);
         if (sl.h_done) cudaFreeHost((void *)sl.h_done);
@@ -590,13 +597,45 @@ int lat_ajtai_submit_w_ccs(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_len, 
         (st = device_view(const_cast<unsigned long long *>(sl.h_done), (void **)&done_dev)))
         return st;
     rep.flag_dev = sl.flag.as<int>();
-    rep.done_host = done_dev;
-    rep.done_value = tk;
-    if ((st = h->mac_fx(fxp, h->n, 1, sl.cm.as<u64>(), rep))) return st;
+    if (!h->has_peers) {
+        rep.done_host = done_dev;
+        rep.done_value = tk;
+        if ((st = h->mac_fx(fxp, h->n, 1, sl.cm.as<u64>(), rep))) return st;
+    } else {
+        // sharded: the matrix-vector kernel only moves the overflow flag; the exchange kernel behind it (part of the
+        // same kernel chain) sums the partial commitments of all ranks and reports the full one
+        u64 *cm_map = rep.cm_host;
+        rep.cm_host = nullptr;
+        if ((st = sl.out.ensure((size_t)h->kappa * ELEM_BYTES))) return st;
+        if ((st = h->mac_fx(fxp, h->n, 1, sl.cm.as<u64>(), rep))) return st;
+        lat::launch_exchange(sl.cm.as<u64>(), (u64)h->kappa * LAT_RING_DEGREE, h->peer_rank, h->peer_world, h->peers,
+                             h->peer_epoch++, sl.out.as<u64>(), h->stream, cm_map, done_dev, tk);
+        CK(cudaGetLastError());
+    }
     sl.busy = true;
     sl.user_cm = cm;
     sl.ticket = tk;
     *ticket = h->next_ticket++;
+    return LAT_OK;
+}
+
+int lat_ajtai_set_peers(lat_ajtai *h, int rank, int world, const uint64_t *recv_ptrs, const uint64_t *flag_ptrs,
+                        uint64_t next_epoch) {
+    if (!h) return fail(LAT_E_INVALID_ARGUMENT, "NULL handle");
+    if (world <= 1 || !recv_ptrs || !flag_ptrs) {
+        h->has_peers = false;
+        return LAT_OK;
+    }
+    if (world > lat::MAX_PEERS || rank < 0 || rank >= world || next_epoch == 0)
+        return fail(LAT_E_INVALID_ARGUMENT, "need world <= 16, 0 <= rank < world, next_epoch >= 1");
+    for (int r = 0; r < world; ++r) {
+        h->peers.recv[r] = reinterpret_cast<u64 *>(recv_ptrs[r]);
+        h->peers.flags[r] = reinterpret_cast<u64 *>(flag_ptrs[r]);
+    }
+    h->peer_rank = rank;
+    h->peer_world = world;
+    h->peer_epoch = next_epoch;
+    h->has_peers = true;
     return LAT_OK;
 }
 

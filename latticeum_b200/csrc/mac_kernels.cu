@@ -374,11 +374,11 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
             ws[2 * i + 1] = 0;
         }
         if (threadIdx.x == 0) *counter = 0;
+        if (threadIdx.x == 0 && report.flag_dev) {  // the step's overflow flag moves to the host, the device copy is cleared
+            *report.flag_host = *reinterpret_cast<volatile int *>(report.flag_dev);
+            *report.flag_dev = 0;
+        }
         if (report.done_host) {  // results and flag first, then the ticket, each with system scope (the host polls it)
-            if (threadIdx.x == 0 && report.flag_dev) {
-                *report.flag_host = *reinterpret_cast<volatile int *>(report.flag_dev);
-                *report.flag_dev = 0;
-            }
             __threadfence_system();
             __syncthreads();
             if (threadIdx.x == 0) {

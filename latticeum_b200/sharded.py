@@ -14,6 +14,12 @@ import torch
 import torch.distributed as dist
 
 
+def _capi():
+    from . import _capi as capi  # deferred: the CPU (gloo) tests use this module without the CUDA library
+
+    return capi
+
+
 def shard_bounds(total: int, world: int, rank: int) -> Tuple[int, int]:
     """Contiguous block [lo, hi) of `total` units owned by `rank`; the first total % world ranks get one extra."""
     if not 0 <= rank < world:
@@ -124,6 +130,9 @@ class ShardedCommitPipeline:
         dev = getattr(eng, "device", torch.device("cpu"))
         self.cuda = dev.type == "cuda"
         self.chain = self.cuda and sharded.peer is not None and hasattr(eng, "witness_commit_gated")
+        # preferred: the engine's own pipelined submit/wait made sharding-aware (lat_ajtai_set_peers) -- one C call per
+        # step instead of several Python-level launches, which matters once 8 ranks share the host's cores
+        self.native = self.chain and hasattr(eng, "scheme") and depth <= _capi().LAT_PIPELINE_DEPTH
         self.next_ticket = 0
         self.slots = []
         for _ in range(depth):
@@ -157,6 +166,20 @@ class ShardedCommitPipeline:
         if not self.cuda:
             sl["w"].copy_(w_host)
             sl["cm_host"].copy_(self.sharded.witness_commit(sl["w"], sl["partial"]))
+        elif self.native:
+            import ctypes as C
+
+            L, peer, h = _capi().lib(), self.sharded.peer, eng.scheme._h
+            eng.bind_stream()
+            n = peer.world
+            st = L.lat_ajtai_set_peers(h, peer.rank, n, (C.c_uint64 * n)(*peer.recv_ptrs), (C.c_uint64 * n)(*peer.flag_ptrs),
+                                       peer.epoch + 1)
+            et = C.c_uint64(0)
+            st = st or L.lat_ajtai_submit_w_ccs(h, w_host.data_ptr(), w_host.shape[0], sl["cm_host"].data_ptr(), C.byref(et))
+            if st:
+                raise RuntimeError(_capi().last_error())
+            peer.epoch += 1
+            sl["engine_ticket"] = et.value
         elif self.chain:
             sl["ticket_host"][0] = tk
             with torch.cuda.stream(self.up):  # the slot's previous user has been waited for: its buffers are free
@@ -185,7 +208,10 @@ class ShardedCommitPipeline:
         sl = self.slots[ticket % self.depth]
         if sl["ticket"] != ticket:
             raise KeyError(f"no such ticket in flight: {ticket}")
-        if self.chain:
+        if self.native:
+            if _capi().lib().lat_ajtai_wait(self.sharded.engine.scheme._h, sl["engine_ticket"]):
+                raise RuntimeError(_capi().last_error())
+        elif self.chain:
             done, spins = sl["done_host"], 0
             while int(done[0]) != ticket:  # written by the exchange kernel after the commitment
                 spins += 1
