@@ -24,6 +24,8 @@ extern "C" {
     fn lat_ajtai_commit_ntt_batch(h: *mut LatAjtai, fs: *const u64, count: u32, f_len: u64, cms: *mut u64) -> c_int;
     fn lat_ajtai_witness_from_w_ccs(h: *mut LatAjtai, w_ccs: *const u64, w_len: u64, f_coeff: *mut u64, f: *mut u64, cm: *mut u64) -> c_int;
     fn lat_ajtai_decompose_commit(h: *mut LatAjtai, f_coeff: *const u64, n: u64, cm: *const u64, planes_coeff: *mut u64, planes_f: *mut u64, cms: *mut u64) -> c_int;
+    fn lat_ajtai_submit_w_ccs(h: *mut LatAjtai, w_ccs: *const u64, w_len: u64, cm: *mut u64, ticket: *mut u64) -> c_int;
+    fn lat_ajtai_wait(h: *mut LatAjtai, ticket: u64) -> c_int;
     fn lat_ajtai_select_side(h: *mut LatAjtai, side: c_int) -> c_int;
     fn lat_ajtai_fold_witness(h: *mut LatAjtai, rho: *const u64, f0: *mut u64, f0_coeff: *mut u64) -> c_int;
     fn lat_ring_gadget_recompose(f: *const u64, count: u64, log2_b: u32, l: u32, out: *mut u64, repr: c_int, device: c_int) -> c_int;
@@ -122,6 +124,19 @@ impl CudaAjtai {
         )?;
         Ok((pc.chunks(n).map(|c| c.to_vec()).collect(), pf.chunks(n).map(|c| c.to_vec()).collect(), cms.chunks(kappa).map(|c| c.to_vec()).collect()))
     }
+    /// Pipelined form of `witness_from_w_ccs` + commit for a stream of VM steps (main.rs:121-219): returns at once;
+    /// `w_ccs` and the returned buffer must stay alive until `wait`.  Up to 4 steps may be in flight.
+    pub fn submit_w_ccs<'a>(&'a self, w_ccs: &'a [NTT]) -> Result<PendingCommit<'a>, CudaCommitError> {
+        let mut cm = vec![NTT::default(); self.kappa].into_boxed_slice();
+        let mut ticket = 0u64;
+        check(
+            unsafe { lat_ajtai_submit_w_ccs(self.h, limbs(w_ccs), w_ccs.len() as u64, cm.as_mut_ptr() as *mut u64, &mut ticket) },
+            w_ccs.len() * (self.n / w_ccs.len().max(1)),
+            self.n,
+        )?;
+        Ok(PendingCommit { engine: self, ticket, cm, _input: std::marker::PhantomData })
+    }
+
     /// Which side (0 = accumulator, 1 = step witness) the following `decompose_commit` calls fill; both sides' planes
     /// stay resident for `fold_witness`.
     pub fn select_side(&self, side: i32) -> Result<(), CudaCommitError> {
@@ -135,6 +150,20 @@ impl CudaAjtai {
         let mut f0_coeff = vec![Coeff::default(); self.n];
         check(unsafe { lat_ajtai_fold_witness(self.h, limbs(rho_s), limbs_mut(&mut f0), limbs_mut(&mut f0_coeff)) }, 0, 0)?;
         Ok((f0, f0_coeff))
+    }
+}
+
+/// A commitment in flight (`CudaAjtai::submit_w_ccs`); borrows the input so that it cannot be dropped early.
+pub struct PendingCommit<'a> {
+    engine: &'a CudaAjtai,
+    ticket: u64,
+    cm: Box<[NTT]>,
+    _input: std::marker::PhantomData<&'a [NTT]>,
+}
+impl<'a> PendingCommit<'a> {
+    pub fn wait(self) -> Result<Vec<NTT>, CudaCommitError> {
+        check(unsafe { lat_ajtai_wait(self.engine.h, self.ticket) }, 0, 0)?;
+        Ok(self.cm.into_vec())
     }
 }
 

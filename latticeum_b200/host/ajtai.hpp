@@ -90,6 +90,14 @@ class AjtaiCommitmentScheme {
             out[k].val.assign(cms.begin() + (size_t)k * kappa_ * LAT_RING_DEGREE, cms.begin() + (size_t)(k + 1) * kappa_ * LAT_RING_DEGREE);
         return out;
     }
+    // Pipelined Witness::from_w_ccs + commit for a stream of steps: submit returns a ticket at once, wait blocks for that
+    // step's commitment (written to `cm`, kappa x 24, which like w_ccs must stay valid until then).
+    uint64_t submit_w_ccs(const uint64_t *w_ccs, size_t w_len, uint64_t *cm) const {
+        uint64_t ticket = 0;
+        check(lat_ajtai_submit_w_ccs(h_, w_ccs, w_len, cm, &ticket), w_len * p_.L, n_);
+        return ticket;
+    }
+    void wait(uint64_t ticket) const { check(lat_ajtai_wait(h_, ticket)); }
     // Which side (0 = accumulator, 1 = step witness) the following decompose_commit calls fill (kept resident).
     void select_side(int side) const { check(lat_ajtai_select_side(h_, side)); }
     // LFFoldingProver::compute_f_0 (nifs/folding/utils.rs:351-376) + Witness::from_f's iCRT (arith.rs:275-289) over
