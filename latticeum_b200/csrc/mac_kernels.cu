@@ -433,7 +433,11 @@ MacPlan plan_mac(const MatLayout &lay, uint32_t planes, int sm_count) {
 template <int PT, int RG>
 static void launch_mac_t(dim3 grid, const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes,
                          const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream, bool pdl, const MacReport &report) {
-    static bool attr_set = false;
+    // function attributes are per device: a process may hold handles on several GPUs
+    static bool attr_set_on[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool &attr_set = attr_set_on[dev & 63];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(mac_kernel<PT, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // minus the static bytes
         if (e != cudaSuccess) fprintf(stderr, "lattice_ajtai: cudaFuncSetAttribute(mac_kernel<%d,%d>): %s\n", PT, RG, cudaGetErrorString(e));
@@ -578,7 +582,10 @@ void launch_fold(const u64 *const *sides_fx, int nsides, int planes_per_side, u6
     unsigned grid = (unsigned)((n * ring::NSLOT + FOLD_THREADS - 1) / FOLD_THREADS);
     const u64 *a = sides_fx[0], *b = nsides > 1 ? sides_fx[1] : nullptr;
     const size_t smem = (size_t)FOLD_STAGES * FOLD_STAGE_BYTES;
-    static bool attr_set = false;
+    static bool attr_set_on[64] = {};  // per device, as for mac_kernel
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool &attr_set = attr_set_on[dev & 63];
     if (!attr_set) {
         cudaFuncSetAttribute(fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
