@@ -235,6 +235,19 @@ int lat_commitment_exchange_report_dev(const uint64_t *partial_dev, uint64_t wor
                                        uint64_t *out_dev, uint64_t *cm_host, uint64_t *done_host, uint64_t done_value,
                                        void *cuda_stream);
 
+/* ---- standalone negacyclic NTT over Z_q[X]/(X^d + 1), d = 2^log2_d (BASELINE configs[3]) -------------------
+ * NOT part of the drop-in path and ABSENT from the reference, whose ring is Z_q[X]/(X^24 - X^12 + 1): nothing in the
+ * reference fixes these values, so this header is the specification and parity is pinned only against the O(d^2)
+ * restatement in oracle/ and the transform's algebraic properties.  With psi = 7^((q - 1) / 2d):
+ *   forward (inverse = 0): out[i] = sum_j in[j] * psi^((2 i + 1) j)        natural order in and out
+ *   inverse (inverse = 1): out[j] = d^-1 * sum_i in[i] * psi^(-(2 i + 1) j)
+ * hence forward(a * b mod X^d + 1) = forward(a) (.) forward(b).  `batch` polynomials of d coefficients each, contiguous;
+ * in-place allowed.  Linear with canonical constants: Montgomery-form input gives Montgomery-form output.       */
+#define LAT_NTT_MAX_LOG2_D 14
+int lat_ntt_negacyclic(const uint64_t *in, uint64_t batch, uint32_t log2_d, int inverse, uint64_t *out, int device);
+int lat_ntt_negacyclic_dev(const uint64_t *in_dev, uint64_t batch, uint32_t log2_d, int inverse, uint64_t *out_dev,
+                           void *cuda_stream);
+
 /* ---- overlap of consecutive steps on the device ---------------------------------------------------------------------
  * With the option enabled, the iCRT/decompose/CRT kernel of a lat_ajtai_witness_from_w_ccs_dev call that directly
  * follows a commitment on the same handle starts while that commitment's matrix-vector kernel is still draining

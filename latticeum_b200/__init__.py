@@ -27,12 +27,13 @@ from .scheme import (  # noqa: F401
     gadget_recompose,
     get_fhat,
     ntt_from_scalar,
+    ntt_negacyclic,
     pinned_empty,
     to_mont,
 )
 
 __all__ = [
-    "AjtaiCommitmentScheme", "Commitment", "CommitPipeline", "pinned_empty", "CommitmentError", "DecompositionParams", "DigitOverflow", "EngineError",
+    "AjtaiCommitmentScheme", "Commitment", "ntt_negacyclic", "CommitPipeline", "pinned_empty", "CommitmentError", "DecompositionParams", "DigitOverflow", "EngineError",
     "GoldiLocksDP", "KAPPA", "LFDecompositionProver", "LFFoldingProver", "gadget_recompose", "N", "W_SIZE", "Witness", "WrongAjtaiMatrixDimensions",
     "WrongCommitmentLength", "WrongWitnessLength", "from_mont", "get_fhat", "ntt_from_scalar", "to_mont",
 ]

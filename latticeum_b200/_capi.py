@@ -72,6 +72,8 @@ SIGNATURES = {
     "lat_ajtai_witness_from_w_ccs_gated_dev": (C.c_int, [_H, _u64p, C.c_uint64, _u64p, _u64p, C.c_uint64]),
     "lat_commitment_exchange_report_dev": (C.c_int, [_u64p, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                                      C.c_uint64, _u64p, _u64p, _u64p, C.c_uint64, C.c_void_p]),
+    "lat_ntt_negacyclic": (C.c_int, [_u64p, C.c_uint64, C.c_uint32, C.c_int, _u64p, C.c_int]),
+    "lat_ntt_negacyclic_dev": (C.c_int, [_u64p, C.c_uint64, C.c_uint32, C.c_int, _u64p, C.c_void_p]),
     "lat_ajtai_set_step_overlap": (C.c_int, [_H, C.c_int]),
     "lat_ajtai_set_profiling": (C.c_int, [_H, C.c_int]),
     "lat_ajtai_mac_profile": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

@@ -888,6 +888,37 @@ int lat_ring_gadget_decompose(const uint64_t *in, uint64_t count, uint32_t log2_
     return LAT_OK;
 }
 
+// ---- standalone power-of-two negacyclic NTT (absent from the reference) ----------------------------------------
+int lat_ntt_negacyclic_dev(const uint64_t *in_dev, uint64_t batch, uint32_t log2_d, int inverse, uint64_t *out_dev,
+                           void *cuda_stream) {
+    if (batch == 0) return LAT_OK;
+    if (!in_dev || !out_dev) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (log2_d < 1 || log2_d > LAT_NTT_MAX_LOG2_D) return fail(LAT_E_INVALID_ARGUMENT, "need 1 <= log2_d <= 14");
+    int e = lat::launch_ntt_pow2((const u64 *)in_dev, (u64 *)out_dev, batch, log2_d, inverse != 0, (cudaStream_t)cuda_stream);
+    if (e) return fail_cuda((cudaError_t)e, "lat_ntt_negacyclic", __LINE__);
+    return LAT_OK;
+}
+
+int lat_ntt_negacyclic(const uint64_t *in, uint64_t batch, uint32_t log2_d, int inverse, uint64_t *out, int device) {
+    if (batch == 0) return LAT_OK;
+    if (!in || !out) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (log2_d < 1 || log2_d > LAT_NTT_MAX_LOG2_D) return fail(LAT_E_INVALID_ARGUMENT, "need 1 <= log2_d <= 14");
+    CK(cudaSetDevice(device));
+    const size_t bytes = (size_t)(batch << log2_d) * sizeof(uint64_t);
+    DevBuf buf;
+    int st = buf.ensure(bytes);
+    if (st) return st;
+    cudaError_t e = cudaMemcpy(buf.p, in, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        st = lat_ntt_negacyclic_dev(buf.as<uint64_t>(), batch, log2_d, inverse, buf.as<uint64_t>(), nullptr);
+        if (st == LAT_OK) e = cudaMemcpy(out, buf.p, bytes, cudaMemcpyDeviceToHost);  // synchronises the default stream
+    }
+    buf.release();
+    if (st) return st;
+    if (e != cudaSuccess) return fail_cuda(e, "lat_ntt_negacyclic", __LINE__);
+    return LAT_OK;
+}
+
 int lat_ajtai_set_step_overlap(lat_ajtai *h, int enabled) {
     if (!h) return fail(LAT_E_INVALID_ARGUMENT, "NULL handle");
     h->step_overlap = enabled != 0;

@@ -113,4 +113,8 @@ void launch_exchange(const u64 *partial, u64 words, int rank, int world, const P
                      cudaStream_t stream, u64 *report_cm = nullptr,
                      unsigned long long *report_done = nullptr, unsigned long long done_value = 0);
 
+// Standalone negacyclic NTT over Z_q[X]/(X^d + 1), d = 2^logd (ntt_pow2.cu; not on the drop-in path).  Returns 0 or a
+// cudaError_t as int.
+int launch_ntt_pow2(const u64 *in, u64 *out, u64 batch, uint32_t logd, bool inverse, cudaStream_t stream);
+
 }  // namespace lat

@@ -521,6 +521,22 @@ def _to_mont_np(x: np.ndarray) -> np.ndarray:
     return res
 
 
+def ntt_negacyclic(a, inverse: bool = False, device: int = 0) -> np.ndarray:
+    """Standalone negacyclic NTT over Z_q[X]/(X^d + 1), d = 2^k = a.shape[-1] (lat_ntt_negacyclic).  NOT on
+    the drop-in path and absent from the reference -- see the header for the definition.  a: (..., d) uint64."""
+    x = np.ascontiguousarray(a, dtype=np.uint64)
+    if x.ndim < 1:
+        raise ValueError("a: need at least one axis")
+    d = x.shape[-1]
+    log2_d = d.bit_length() - 1
+    if d < 2 or (1 << log2_d) != d:
+        raise ValueError("the last dimension must be a power of two >= 2")
+    x = x.reshape(-1, d)
+    out = np.empty_like(x)
+    _raise(capi.lib().lat_ntt_negacyclic(_ptr(x), x.shape[0], log2_d, int(inverse), _ptr(out), device))
+    return out.reshape(np.shape(a))
+
+
 def to_mont(x) -> np.ndarray:
     return _to_mont_np(np.ascontiguousarray(x, dtype=np.uint64))
 

@@ -454,3 +454,55 @@ def compute_f_0(rho_s, f_s):
     for rho, f in zip(rho_s, f_s):
         acc = [ntt_add(a, ntt_mul(rho, w)) for a, w in zip(acc, f)]
     return acc
+
+
+# ---------------------------------------------------------------------------------------------
+# f4. Negacyclic NTT over Z_q[X]/(X^d + 1), d = 2^k            (ABSENT from the reference)
+# ---------------------------------------------------------------------------------------------
+# PARITY UNPINNED BY CONSTRUCTION: the reference's ring is Z_q[X]/(X^24 - X^12 + 1) and it contains no
+# power-of-two transform, so no golden vector or reference output can exist.  The definition below (also in
+# include/lattice_ajtai.h) is the specification; this O(d^2) restatement and the algebraic properties checked in
+# tests/test_oracle_ntt.py are the only anchors.
+GENERATOR = 7  # generates Z_q^* (q - 1 = 2^32 * 3 * 5 * 17 * 257 * 65537)
+
+
+def ntt_psi(d: int) -> int:
+    """A primitive 2d-th root of unity: 7^((q-1)/2d)."""
+    assert d >= 1 and d & (d - 1) == 0 and (Q - 1) % (2 * d) == 0
+    return pow(GENERATOR, (Q - 1) // (2 * d), Q)
+
+
+def ntt_eval_at(a: Sequence[int], i: int, inverse: bool = False) -> int:
+    """One output of the transform: forward A[i] = sum_j a[j] psi^((2i+1)j); inverse a[i] = d^-1 sum_k A[k] psi^(-(2k+1)i)."""
+    d = len(a)
+    psi = ntt_psi(d)
+    if not inverse:
+        r = pow(psi, 2 * i + 1, Q)
+        acc, p = 0, 1
+        for x in a:
+            acc = (acc + x * p) % Q
+            p = p * r % Q
+        return acc
+    psi_inv = pow(psi, Q - 2, Q)
+    acc = 0
+    for k, x in enumerate(a):
+        acc = (acc + x * pow(psi_inv, (2 * k + 1) * i, Q)) % Q
+    return acc * pow(d, Q - 2, Q) % Q
+
+
+def ntt_negacyclic(a: Sequence[int], inverse: bool = False) -> List[int]:
+    return [ntt_eval_at(a, i, inverse) for i in range(len(a))]
+
+
+def negacyclic_mul(a: Sequence[int], b: Sequence[int]) -> List[int]:
+    """a * b mod (X^d + 1), schoolbook."""
+    d = len(a)
+    out = [0] * d
+    for i, x in enumerate(a):
+        for j, y in enumerate(b):
+            k = i + j
+            if k < d:
+                out[k] = (out[k] + x * y) % Q
+            else:
+                out[k - d] = (out[k - d] - x * y) % Q
+    return out

@@ -624,6 +624,61 @@ def test_gated_witness_call_waits_for_the_ticket():
     scheme.close()
 
 
+# ---- standalone power-of-two negacyclic NTT (absent from the reference, parity unpinned by construction) ----
+@pytest.mark.parametrize("log2_d", [1, 2, 3, 6, 8])
+def test_ntt_negacyclic_vs_direct_evaluation(log2_d):
+    from oracle import lattice_oracle as PO
+
+    d = 1 << log2_d
+    batch = 5 if d > 8 else 130  # 130 small polynomials: several per block and a ragged last block
+    a = CO.fill_uniform((batch, d), 140 + log2_d)
+    a[0] = 0
+    a[1] = Q - 1
+    fwd = LB.ntt_negacyclic(a)
+    for p in range(min(batch, 6)):
+        assert fwd[p].tolist() == PO.ntt_negacyclic([int(v) for v in a[p]]), p
+    assert np.array_equal(LB.ntt_negacyclic(fwd, inverse=True), a)
+    assert LB.ntt_negacyclic(a, inverse=True)[2].tolist() == PO.ntt_negacyclic([int(v) for v in a[2]], inverse=True)
+
+
+@pytest.mark.parametrize("log2_d", [9, 10, 12, 13, 14])
+def test_ntt_negacyclic_large_properties(log2_d):
+    from oracle import lattice_oracle as PO
+
+    d = 1 << log2_d
+    batch = 3
+    rng = np.random.default_rng(log2_d)
+    a = CO.fill_uniform((batch, d), 150 + log2_d)
+    b = CO.fill_uniform((batch, d), 160 + log2_d)
+    A, B = LB.ntt_negacyclic(a), LB.ntt_negacyclic(b)
+    # spot checks against the definition (O(d) each)
+    for p in range(batch):
+        row = [int(v) for v in a[p]]
+        for i in [0, 1, d - 1] + rng.integers(0, d, size=5).tolist():
+            assert int(A[p, i]) == PO.ntt_eval_at(row, int(i)), (p, i)
+    # inverse o forward = id, linearity, and the convolution theorem against sparse products (X^k * a)
+    assert np.array_equal(LB.ntt_negacyclic(A, inverse=True), a)
+    s = ((a.astype(object) + b.astype(object)) % Q).astype(np.uint64)
+    assert np.array_equal(LB.ntt_negacyclic(s).astype(object), (A.astype(object) + B.astype(object)) % Q)
+    k = int(rng.integers(1, d))
+    xk = np.zeros((batch, d), np.uint64)
+    xk[:, k] = 1
+    prod = ((LB.ntt_negacyclic(xk).astype(object) * A.astype(object)) % Q).astype(np.uint64)
+    shifted = np.concatenate([(np.uint64(Q) - a[:, d - k:]) % np.uint64(Q), a[:, : d - k]], axis=1)  # X^k * a mod X^d + 1
+    assert np.array_equal(LB.ntt_negacyclic(prod, inverse=True), shifted)
+
+
+def test_ntt_negacyclic_argument_checks():
+    x = np.zeros((2, 8), np.uint64)
+    out = np.empty_like(x)
+    L = capi.lib()
+    assert L.lat_ntt_negacyclic(x.ctypes.data, 2, 0, 0, out.ctypes.data, 0) == capi.LAT_E_INVALID_ARGUMENT
+    assert L.lat_ntt_negacyclic(x.ctypes.data, 2, 15, 0, out.ctypes.data, 0) == capi.LAT_E_INVALID_ARGUMENT
+    assert L.lat_ntt_negacyclic(x.ctypes.data, 0, 3, 0, out.ctypes.data, 0) == 0
+    with pytest.raises(ValueError):
+        LB.ntt_negacyclic(np.zeros((2, 12), np.uint64))
+
+
 def test_cpp_host_mirror_example():
     # latticeum_b200/host/ajtai.hpp: the C++ mirror of the reference API, on the reference's closed-form commit test
     import subprocess

@@ -47,6 +47,22 @@ for lg in range(10, 23, 2):
     del x, y
 out["transform_sweep"] = sweep
 
+# ---- standalone power-of-two negacyclic NTT (not on the drop-in path) ---------------------------------------
+ntt = []
+for lg_d, lg_total in ((6, 24), (8, 24), (10, 24), (12, 24), (14, 24)):
+    d, polys = 1 << lg_d, 1 << (lg_total - lg_d)
+    x = torch.from_numpy(rng.integers(0, 2**63, size=(polys, d), dtype=np.int64)).cuda()
+    y = torch.empty_like(x)
+    t_f = timeit(lambda: L.lat_ntt_negacyclic_dev(x.data_ptr(), polys, lg_d, 0, y.data_ptr(), stream))
+    t_i = timeit(lambda: L.lat_ntt_negacyclic_dev(x.data_ptr(), polys, lg_d, 1, y.data_ptr(), stream))
+    wide = polys * (d // 2) * lg_d * 4  # one general multiplication = 4 IMAD.WIDE per butterfly
+    ntt.append({"log2_d": lg_d, "polys": polys, "fwd_us": t_f * 1e3, "inv_us": t_i * 1e3,
+                "coeffs_per_s": polys * d / (t_f * 1e-3), "GBps": polys * d * 16 / t_f / 1e6,
+                "imad_pipe_frac": wide / (t_f * 1e-3) / 9.154e12})
+    print(ntt[-1], flush=True)
+    del x, y
+out["ntt_negacyclic"] = ntt
+
 # ---- fold-step batch (config 2) ---------------------------------------------------------------------------------------
 scheme = LB.AjtaiCommitmentScheme(KAPPA, N)
 for i in range(KAPPA):
