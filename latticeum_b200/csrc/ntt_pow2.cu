@@ -9,10 +9,11 @@
 //   inverse:  a[j] = d^-1 sum_i A[i] psi^(-(2 i + 1) j)
 //   so NTT(a * b mod X^d + 1) = NTT(a) (.) NTT(b).
 //
-// Kernel: one block holds max(d, 512) coefficients in shared memory (several polynomials when d < 512) and runs the
-// log2(d) radix-2 stages with the psi powers merged into the butterflies (Cooley-Tukey forward, natural -> bit-reversed;
-// Gentleman-Sande inverse, bit-reversed -> natural), so there is no separate twist pass; the bit reversal is folded
-// into the global store (forward) / load (inverse).  A butterfly is one general modular multiplication (4 IMAD.WIDE +
+// Kernel: one block holds max(d, 2048) coefficients in (padded) shared memory (several polynomials when d < 2048) and
+// runs the log2(d) stages three at a time, eight coefficients per thread in registers (radix-8 passes, then one
+// radix-4 or radix-2 pass for the remainder), with the psi powers merged into the butterflies (Cooley-Tukey forward,
+// natural -> bit-reversed; Gentleman-Sande inverse, bit-reversed -> natural), so there is no separate twist pass; the
+// bit reversal is folded into the shared-memory side of the final store (forward) / first load (inverse).  A butterfly is one general modular multiplication (4 IMAD.WIDE +
 // special-form reduction) plus a canonical add and sub: the transform is bound by the integer multiply pipe, not by
 // the 16 bytes per coefficient it moves.  Twiddle tables (psi^bitrev(k), psi^-bitrev(k); d words each) are built on the
 // device once per (device, log2 d) and stay resident.
@@ -33,7 +34,7 @@ using gl::u32;
 using gl::u64;
 
 constexpr int NTT_THREADS = 256;
-constexpr u32 NTT_MIN_ELEMS = 512;  // coefficients per block when d is small
+constexpr u32 NTT_MIN_ELEMS = 2048;  // coefficients per block when d is small (one radix-8 unit per thread)
 
 __host__ u64 host_mulmod(u64 a, u64 b) { return (u64)(((unsigned __int128)a * b) % gl::Q); }
 __host__ u64 host_powmod(u64 base, u64 e) {
@@ -63,6 +64,69 @@ __global__ void __launch_bounds__(256) ntt_table_kernel(u64 root, u32 logd, u64 
     table[k] = dev_pow(root, __brev(k) >> (32 - logd));
 }
 
+// Shared-memory index with padding: one extra word per 16, per 256 and per 4096 words, so that the strided accesses of
+// the late stages and the bit-reversed access of the final store spread over the banks.
+__device__ __forceinline__ u32 pad(u32 i) { return i + (i >> 4) + (i >> 8) + (i >> 12); }
+
+// Cooley-Tukey / Gentleman-Sande butterflies with the psi power merged in
+__device__ __forceinline__ void ct(u64 &u, u64 &v, u64 s) {
+    const u64 t = gl::mul(v, s);
+    v = gl::sub(u, t);
+    u = gl::add(u, t);
+}
+__device__ __forceinline__ void gs(u64 &u, u64 &v, u64 s) {
+    const u64 t = gl::sub(u, v);
+    u = gl::add(u, v);
+    v = gl::mul(t, s);
+}
+
+// One pass over R = 1, 2 or 3 consecutive stages with 2^R coefficients per thread in registers.
+// Forward (CT): first stage has m blocks of 2t coefficients, strides t, t/2, t/4; twiddle of block i is tw[m + i].
+// Inverse (GS): first stage has stride q, then 2q, 4q; h = (coefficients per polynomial) / (2q) blocks.
+template <bool INVERSE, int R>
+__device__ __forceinline__ void ntt_pass(u64 *a, const u64 *__restrict__ tw, u32 elems, u32 logd, u32 m_or_h, u32 logq) {
+    constexpr int N = 1 << R;
+    const u32 q = 1u << logq;                  // distance between the coefficients a thread holds
+    const u32 units_per_poly_log = logd - R;   // d / N units per polynomial
+    for (u32 u = threadIdx.x; u < (elems >> R); u += NTT_THREADS) {
+        const u32 p = u >> units_per_poly_log, uu = u & ((1u << units_per_poly_log) - 1);
+        const u32 blk = uu >> logq, j0 = uu & (q - 1);        // block of N*q coefficients, offset inside it
+        const u32 base = (p << logd) + blk * (N * q) + j0;
+        u64 x[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) x[k] = a[pad(base + k * q)];
+        if (!INVERSE) {
+            const u32 m = m_or_h;  // blocks of the first stage; blk is its block index
+#pragma unroll
+            for (int r = 0; r < R; ++r) {      // stage r: 2^r sub-blocks, pairs (k, k + N / 2^(r+1))
+                const int span = N >> (r + 1);
+#pragma unroll
+                for (int sb = 0; sb < (1 << r); ++sb) {
+                    const u64 w = __ldg(tw + (m << r) + (blk << r) + sb);
+#pragma unroll
+                    for (int k = 0; k < span; ++k) ct(x[sb * 2 * span + k], x[sb * 2 * span + k + span], w);
+                }
+            }
+        } else {
+            const u32 h = m_or_h;  // blocks (pairs at distance q) of the first stage: d / 2q
+#pragma unroll
+            for (int r = 0; r < R; ++r) {      // stage r: stride 2^r (in held coefficients), N / 2^(r+1) sub-blocks
+                const int span = 1 << r;
+                const int nsb = N >> (r + 1);
+#pragma unroll
+                for (int sb = 0; sb < nsb; ++sb) {
+                    const u64 w = __ldg(tw + (h >> r) + blk * nsb + sb);
+#pragma unroll
+                    for (int k = 0; k < span; ++k) gs(x[sb * 2 * span + k], x[sb * 2 * span + k + span], w);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) a[pad(base + k * q)] = x[k];
+    }
+    __syncthreads();
+}
+
 template <bool INVERSE>
 __global__ void __launch_bounds__(NTT_THREADS)
 ntt_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, u64 batch, u32 logd, const u64 *__restrict__ tw, u64 d_inv) {
@@ -76,51 +140,37 @@ ntt_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, u64 batch, u32 log
     // load (the inverse transform wants its input in bit-reversed order)
     for (u32 i = threadIdx.x; i < elems; i += NTT_THREADS) {
         const u32 p = i >> logd, k = i & (d - 1);
-        const u32 src = INVERSE ? (__brev(k) >> (32 - logd)) : k;
-        const u64 g = base + ((u64)p << logd) + src;
-        a[i] = g < total ? in[g] : 0ull;
+        const u64 g = base + i;
+        const u32 dst = INVERSE ? (p << logd) + (__brev(k) >> (32 - logd)) : i;
+        a[pad(dst)] = g < total ? in[g] : 0ull;
     }
     __syncthreads();
-    const u32 half = elems >> 1, hmask = (d >> 1) - 1;
     if (!INVERSE) {
-        u32 logt = logd;
-        for (u32 m = 1; m < d; m <<= 1) {
-            --logt;  // t = d / (2 m)
-            for (u32 b = threadIdx.x; b < half; b += NTT_THREADS) {
-                const u32 p = b >> (logd - 1), bb = b & hmask;
-                const u32 i = bb >> logt, j = bb & ((1u << logt) - 1);
-                const u32 i1 = (p << logd) + (i << (logt + 1)) + j, i2 = i1 + (1u << logt);
-                const u64 s = __ldg(tw + m + i);
-                const u64 u = a[i1], v = gl::mul(a[i2], s);
-                a[i1] = gl::add(u, v);
-                a[i2] = gl::sub(u, v);
-            }
-            __syncthreads();
+        // stages s = 0 .. logd-1: m = 2^s blocks, stride t = d / 2^(s+1); radix-8 passes while three stages remain
+        u32 s = 0;
+        while (logd - s >= 3) {
+            ntt_pass<false, 3>(a, tw, elems, logd, 1u << s, logd - s - 3);
+            s += 3;
         }
+        if (logd - s == 2) ntt_pass<false, 2>(a, tw, elems, logd, 1u << s, 0);
+        else if (logd - s == 1) ntt_pass<false, 1>(a, tw, elems, logd, 1u << s, 0);
     } else {
-        u32 logt = 0;
-        for (u32 m = d; m > 1; m >>= 1) {
-            const u32 h = m >> 1;
-            for (u32 b = threadIdx.x; b < half; b += NTT_THREADS) {
-                const u32 p = b >> (logd - 1), bb = b & hmask;
-                const u32 i = bb >> logt, j = bb & ((1u << logt) - 1);
-                const u32 i1 = (p << logd) + (i << (logt + 1)) + j, i2 = i1 + (1u << logt);
-                const u64 s = __ldg(tw + h + i);
-                const u64 u = a[i1], v = a[i2];
-                a[i1] = gl::add(u, v);
-                a[i2] = gl::mul(gl::sub(u, v), s);
-            }
-            ++logt;
-            __syncthreads();
+        // stages with stride q = 1, 2, 4, ...: h = d / 2q blocks
+        u32 lq = 0;
+        while (logd - lq >= 3) {
+            ntt_pass<true, 3>(a, tw, elems, logd, d >> (lq + 1), lq);
+            lq += 3;
         }
+        if (logd - lq == 2) ntt_pass<true, 2>(a, tw, elems, logd, d >> (lq + 1), lq);
+        else if (logd - lq == 1) ntt_pass<true, 1>(a, tw, elems, logd, d >> (lq + 1), lq);
     }
     // store (the forward transform leaves its output in bit-reversed order)
     for (u32 i = threadIdx.x; i < elems; i += NTT_THREADS) {
         const u32 p = i >> logd, k = i & (d - 1);
-        const u64 g = base + ((u64)p << logd) + k;
+        const u64 g = base + i;
         if (g >= total) continue;
-        if (INVERSE) out[g] = gl::mul(a[i], d_inv);
-        else out[g] = a[(p << logd) + (__brev(k) >> (32 - logd))];
+        if (INVERSE) out[g] = gl::mul(a[pad(i)], d_inv);
+        else out[g] = a[pad((p << logd) + (__brev(k) >> (32 - logd)))];
     }
 }
 
@@ -165,12 +215,12 @@ int launch_ntt_pow2(const u64 *in, u64 *out, u64 batch, u32 logd, bool inverse, 
     const u64 elems = d > NTT_MIN_ELEMS ? d : NTT_MIN_ELEMS;
     const u64 ppb = elems >> logd;
     const unsigned grid = (unsigned)((batch + ppb - 1) / ppb);
-    const size_t smem = elems * sizeof(u64);
+    const size_t smem = (elems + (elems >> 4) + (elems >> 8) + (elems >> 12) + 4) * sizeof(u64);  // padded, see pad()
     if (smem > 48 * 1024) {
         static bool set_on[64] = {};
         if (!set_on[dev & 63]) {
-            cudaFuncSetAttribute(ntt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-            cudaFuncSetAttribute(ntt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+            cudaFuncSetAttribute(ntt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 1024);
+            cudaFuncSetAttribute(ntt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 1024);
             set_on[dev & 63] = true;
         }
     }
