@@ -7,17 +7,21 @@
 //  * The matrix is re-laid out ONCE at upload into column tiles  [row block][tile][column jj][component c][row i][slot s]
 //    (canonical form), so that a tile is one contiguous run of bytes in HBM and a warp's shared-memory read of
 //    (jj, c) is 32 consecutive u64 (conflict-free).  Tiles are streamed with TMA bulk copies (cp.async.bulk ->
-//    UBLKCP) into a multi-stage shared-memory ring guarded by mbarriers; one producer warp, RG*CG consumer warps.
+//    UBLKCP) into a multi-stage shared-memory ring guarded by mbarriers; RG*CG warps, all of them consumers -- the
+//    last warp to release a stage issues its refill (no producer warp: a 9th warp halves the occupancy).
 //  * The witness side comes in the "extended" layout [element][slot][6] = (f0, f1, f2, f0+f1, f0+f2, f1+f2): the
 //    Karatsuba pre-additions of the witness are done once by whoever produces it (the CRT kernels, or fext_kernel
 //    for a caller-supplied witness), not once per matrix row.  The matrix-side pre-additions are 3 lazy adds per
-//    thread per column on the ALU pipe, which is otherwise idle.
+//    thread per column (exact 65-bit sums for one witness; folded to 64 bits once per entry when several
+//    witnesses share it).
 //  * Split-K over columns: every CTA owns a contiguous range of tiles and keeps, per thread, the UNREDUCED
 //    accumulators of one output (row, slot) for PT witnesses ("planes"): 6 sums x 3 columns x (64+32) bits
 //    (gl::Fq3Acc).  One 64x64 product = 4 IMAD.WIDE.U32 with carry-out + 2 IADD3.X; 6 products per Fq3 MAC
 //    (Karatsuba) = 24 IMAD.WIDE.U32; a single special-form reduction per output at the end.  IMAD.WIDE.U32 runs at
 //    31.5 /clk/SM (measured), so this multiply count, not HBM, is what the batched (PT > 1) case is bound by.
 //    No tensor cores: this is exact 64-bit modular integer work.
+//  * Programmatic dependent launch: the prologue and the first matrix tiles do not wait for the kernel that
+//    produces the witness, and the next call's kernels may start while this one drains.
 //  * Cross-CTA sum inside the same kernel: canonical partials are added as 32-bit halves with 64-bit REDs into a
 //    (zeroed, self-cleaning) workspace and the last CTA folds them mod q into the commitment.
 //  * A is canonical and F is in the caller's representation, so canonical(A) * repr(F) = repr(A*F): the
@@ -163,7 +167,7 @@ void launch_fext(const u64 *f, u64 count, u64 *fx, cudaStream_t stream) {
 }
 
 // ---- the MAC kernel --------------------------------------------------------------------------------------------
-// grid = (column chunks, row blocks, plane groups); block = (RG*CG consumer warps + 1 producer warp) * 32.
+// grid = (column chunks, row blocks, plane groups); block = RG*CG warps.
 // Shared memory: STAGES x { A tile | PT x TJ x 48 u64 of extended witness } + 2*STAGES mbarriers.
 // Workspace: ws[2*i], ws[2*i+1] = sums of the low / high 32-bit halves of output i = (p * kappa + row) * 24 + s*3 + c;
 // ws[2 * nout] = finished-CTA counter.  Must be zero before the first launch; every launch leaves it zero again.
