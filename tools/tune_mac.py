@@ -1,5 +1,7 @@
 """Sweeps the MAC kernel's launch knobs (stages / resident CTAs / grid) at the zkVM shape and prints the CUDA-event
-duration of mac_kernel alone for each setting.  Run on a GPU box: python tools/tune_mac.py [planes]"""
+duration of mac_kernel alone for each setting.  Run on a GPU box: python tools/tune_mac.py [planes]
+Compile-time knobs (tile size LAT_TJ_BYTES, LAT_MAC_TRACE, ...) go through latticeum_b200.build.build_variant(tag, defines)
+and LAT_LIB=latticeum_b200/lib/variants/<tag>/liblattice_ajtai.so; tools/ab_mac.py times the default plan of a library."""
 import os
 import sys
 
