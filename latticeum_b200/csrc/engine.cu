@@ -8,6 +8,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/lattice_ajtai.h"
@@ -647,6 +648,7 @@ int lat_ajtai_wait(lat_ajtai *h, uint64_t ticket) {
     sl.busy = false;
     // poll the ticket the last CTA publishes; look at the stream now and then so that a device fault cannot hang us
     for (unsigned spins = 0; *sl.h_done != ticket; ++spins) {
+        if ((spins & 0x3ff) == 0x3ff) std::this_thread::yield();  // several ranks may share the host's cores
         if ((spins & 0xffff) == 0xffff) {
             cudaError_t e = cudaStreamQuery(h->stream);
             if (e != cudaSuccess && e != cudaErrorNotReady) return fail_cuda(e, "lat_ajtai_wait", __LINE__);
