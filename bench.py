@@ -159,6 +159,9 @@ def run_reference(args):
         return  # rank 0 alone runs the CPU arm
     from oracle import c_oracle as CO  # the CPU arm IS the oracle port (kind = "port": no Rust toolchain here)
 
+    if os.environ.get("OMP_NUM_THREADS") == "1" and "LOCAL_RANK" in os.environ:
+        # torchrun exports OMP_NUM_THREADS=1 to its workers; rank 0 alone runs this arm, so it takes all host cores
+        CO.set_num_threads(len(os.sched_getaffinity(0)))
     cores = CO.num_threads()
     # calibrate on a small sample, then bound every step so that the whole run ends within ~2 minutes
     cal_w = 2000

@@ -37,6 +37,7 @@ def lib():
         sigs = {
             "lo_roots": (None, [_P]),
             "lo_num_threads": (i32, []),
+            "lo_set_num_threads": (None, [i32]),
             "lo_homogenize": (None, [_P]),
             "lo_dehomogenize": (None, [_P]),
             "lo_crt": (None, [_P, u64, _P]),
@@ -78,6 +79,11 @@ class OracleError(Exception):
 
 def num_threads() -> int:
     return lib().lo_num_threads()
+
+
+def set_num_threads(n: int) -> None:
+    """OpenMP team size for the following calls (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    lib().lo_set_num_threads(int(n))
 
 
 def roots() -> np.ndarray:

@@ -88,6 +88,15 @@ int lo_num_threads(void) {
     return 1;
 #endif
 }
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm of the benchmark asks for all cores explicitly */
+void lo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 
 /* ---- a1. Fq3 = Fq[u]/(u^3 - 2^40): value fixed by the maths (ark-ff Fp3) ------------------------ */
 static inline void fq3_mul(const u64 *a, const u64 *b, u64 *c) {
