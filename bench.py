@@ -1,17 +1,23 @@
 #!/usr/bin/env python
-"""bench.py -- the Ajtai step-witness commit of Latticeum's zkVM on B200 (BASELINE.json configs[1]).
+"""bench.py -- the Ajtai commitment path of Latticeum's zkVM on B200 (BASELINE.json).
 
-A "step" is one pass of the hot path over one synthetic step witness at the zkVM's parameters
-(kappa = 32, w_len = 19 763, n = 98 815, B = 2^15, L = 5): Witness::from_w_ccs (iCRT -> base-2^15 gadget
-decomposition -> CRT) followed by Witness::commit (A * f), i.e. the reference's `commit()` call site
-zkvm/src/main.rs:348-367.  At N GPUs the witness is N times wider and column-sharded (one zkVM-sized column
-block per GPU, weak scaling) with one NCCL all-gather of the 6 KB partial commitments + a mod-q fold.
+N = 1 (configs[1]): a "step" is one pass of the hot path over one synthetic step witness at the zkVM's parameters
+(kappa = 32, w_len = 19 763, n = 98 815, B = 2^15, L = 5): Witness::from_w_ccs (iCRT -> base-2^15 gadget decomposition ->
+CRT) followed by Witness::commit (A * f), i.e. the reference's `commit()` call site zkvm/src/main.rs:348-367.  Consecutive
+IVC steps of the reference are strictly dependent (zkvm/src/main.rs:140-182), so `value` times dependent device-resident
+steps and `e2e` times ONE BLOCKING host-buffer C-ABI call per step; the overlapped / ticketed throughput modes are
+reported beside them as extras.  The line also carries the whole fold step (`fold_step`: step commit + 28 plane commits +
+compute_f_0, zk_latticefold.rs:37-102) and the configs[4] commit on one GPU (`n_2_20_single_gpu`).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]                 our CUDA engine
-  python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  the CPU path (C restatement of the rayon path)
+N > 1 (configs[4]): ONE witness of n = 2^20 ring elements in CRT form, kappa = 32 (A = 6.44 GB), column-sharded over the N
+GPUs (strong scaling): a step is commit_ntt of every rank's column block + one exchange of the 6 KB partial commitments
+summed mod q.  Parity: every rank commits its block with the oracle on its host cores, the partials are summed mod q and
+compared with the engine's result.  The zkVM-width weak-scaling figures of round 1 stay as `weak_zkvm_width`.
 
-Prints ONE JSON line (rank 0).  `value` = witness ring elements committed per second with inputs resident in HBM;
-`e2e` = the same through the host-buffer C ABI call with H2D/D2H copies inside the timed region.
+  python bench.py [--gpus N] [--steps K] [--warmup W]                    our CUDA engine
+  python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]   the CPU path (C restatement of the rayon path)
+
+Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
@@ -32,11 +38,11 @@ sys.path.insert(0, ROOT)
 
 KAPPA, W_LEN, L_LIMBS, LOG2_B, K_PLANES = 32, 19763, 5, 15, 15
 N_COLS = W_LEN * L_LIMBS  # 98 815
+N_SHARDED = 1 << 20       # configs[4]
 Q = 2**64 - 2**32 + 1
 ELEM_B = 192
 METRIC = "ajtai_commit_ring_elems_per_s"
 UNIT = "ring elems/s"
-
 
 _JSON_OUT = None
 
@@ -45,6 +51,11 @@ def emit(line):
     out = _JSON_OUT or sys.stdout
     out.write(json.dumps(line) + "\n")
     out.flush()
+
+
+def log(msg):
+    sys.stderr.write(f"[bench r{os.environ.get('RANK', '0')}] {msg}\n")
+    sys.stderr.flush()
 
 
 # ---- synthetic inputs: independently random matrix, steady-state witness mix -----------------------------
@@ -58,8 +69,8 @@ def uniform_fq(shape, seed):
     return out
 
 
-def matrix_row(rank, i):
-    return uniform_fq((N_COLS, 24), 1_000_003 * (rank + 1) + i)
+def matrix_row(rank, i, n=N_COLS):
+    return uniform_fq((n, 24), 1_000_003 * (rank + 1) + i)
 
 
 def steady_state_w(rank):
@@ -70,6 +81,11 @@ def steady_state_w(rank):
     w[:nsc] = 0
     w[:nsc, 0::3] = vals[:, None]
     return w
+
+
+def signed_to_fq(v):
+    v = np.ascontiguousarray(v, dtype=np.int64)
+    return np.where(v < 0, v.view(np.uint64) + np.uint64(Q), v.view(np.uint64))  # uint64 add wraps to v + q
 
 
 # ---- clocks sampler (B200_PROFILING.md recipe) ----------------------------------------------------------------------
@@ -83,7 +99,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -103,21 +119,22 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self, t0, t1):
-        sm, mx, reasons = [], 0.0, set()
+        sm, mx, reasons, power = [], 0.0, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for (_, l) in self.lines]
+        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.1] or [l for (_, l) in self.lines[-1:]]
         for l in rows:
             p = [x.strip() for x in l.split(",")]
             try:
                 sm.append(float(p[0]))
                 mx = max(mx, float(p[1]))
+                power.append(float(p[2]))
                 for nme, v in zip(names, p[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(nme)
             except Exception:
                 continue
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
 def measured_peaks():
@@ -137,6 +154,27 @@ def ncu_traffic():
         except Exception:
             return None
     return None
+
+
+def imad_peak():
+    """IMAD.WIDE.U32 issue rate measured in THIS run by tools/imad_peak (register-only micro-benchmark); T/s."""
+    exe = os.path.join(ROOT, "tools", "imad_peak")
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
+        d = json.loads(out.strip().splitlines()[-1])
+        return {"imad_wide_T_per_s": d.get("imad_wide_Tops"), "imad_wide_carry_T_per_s": d.get("imad_wide_carry_Tops"),
+                "clock_mhz": d.get("clock_mhz"), "how": "tools/imad_peak (register-only IMAD.WIDE.U32 chains, best of 5), run inside this bench"}
+    except Exception as e:  # the figure is an extra; never fail the line for it
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 # ---- CPU arm: the C restatement of the reference's rayon path (oracle/), timed on the host cores ------------------------
@@ -159,260 +197,300 @@ def run_reference(args):
         return  # rank 0 alone runs the CPU arm
     from oracle import c_oracle as CO  # the CPU arm IS the oracle port (kind = "port": no Rust toolchain here)
 
-    if os.environ.get("OMP_NUM_THREADS") == "1" and "LOCAL_RANK" in os.environ:
+    if "LOCAL_RANK" in os.environ:
         # torchrun exports OMP_NUM_THREADS=1 to its workers; rank 0 alone runs this arm, so it takes all host cores
-        CO.set_num_threads(len(os.sched_getaffinity(0)))
+        CO.set_num_threads(host_threads())
     cores = CO.num_threads()
-    # calibrate on a small sample, then bound every step so that the whole run ends within ~2 minutes
-    cal_w = 2000
-    A, w = cpu_step_inputs(cal_w)
-    t = time.perf_counter()
-    cpu_step(CO, A, w)
-    per_w = (time.perf_counter() - t) / cal_w
-    budget_s = 110.0
     total_steps = args.steps + args.warmup
-    sample_w = int(min(W_LEN, max(500, budget_s / (total_steps * per_w))))
-    if sample_w != cal_w:
-        A, w = cpu_step_inputs(sample_w)
-    for _ in range(args.warmup):
+    budget_s = 110.0
+    if args.gpus <= 1:
+        # configs[1]: Witness::from_w_ccs + commit at the zkVM's width; calibrate, then bound every step
+        cal_w = 2000
+        A, w = cpu_step_inputs(cal_w)
+        t = time.perf_counter()
         cpu_step(CO, A, w)
+        per_w = (time.perf_counter() - t) / cal_w
+        sample_w = int(min(W_LEN, max(500, budget_s / (total_steps * per_w))))
+        if sample_w != cal_w:
+            A, w = cpu_step_inputs(sample_w)
+        step = lambda: cpu_step(CO, A, w)  # noqa: E731
+        units = sample_w * L_LIMBS
+        sample = (f"first {sample_w} of {W_LEN} w_ccs elements ({units} of {N_COLS} columns), kappa={KAPPA}; "
+                  "throughput is linear in columns")
+        config = {"workload": "zkvm_step_witness_commit", "kappa": KAPPA, "w_len": W_LEN, "n": N_COLS, "d": 24,
+                  "B": 1 << LOG2_B, "L": L_LIMBS, "cpu_impl": "C restatement of the reference's rayon path (oracle/), OpenMP"}
+        scaling = "weak"
+    else:
+        # configs[4]: commit_ntt of a CRT-form witness of n = 2^20 (the matrix-vector product alone), bounded sample
+        cal = 1 << 14
+        A = np.stack([matrix_row(0, i, cal) for i in range(KAPPA)])
+        f = uniform_fq((cal, 24), 9)
+        t = time.perf_counter()
+        CO.commit(A, f)
+        per_col = (time.perf_counter() - t) / cal
+        cols = int(min(N_SHARDED, max(1 << 13, budget_s / (total_steps * per_col))))
+        if cols != cal:
+            A = np.stack([matrix_row(0, i, cols) for i in range(KAPPA)])
+            f = uniform_fq((cols, 24), 9)
+        step = lambda: CO.commit(A, f)  # noqa: E731
+        units = cols
+        sample = f"first {cols} of {N_SHARDED} columns, kappa={KAPPA}; throughput is linear in columns"
+        config = {"workload": "sharded_commit_ntt_n_2_20", "kappa": KAPPA, "n_total": N_SHARDED, "d": 24,
+                  "cpu_impl": "C restatement of the reference's rayon path (oracle/), OpenMP"}
+        scaling = "strong"
+    for _ in range(args.warmup):
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_step(CO, A, w)
+        step()
     dt = time.perf_counter() - t0
-    ms = dt / args.steps * 1e3
-    value = sample_w * L_LIMBS * args.steps / dt
-    sample = (f"first {sample_w} of {W_LEN} w_ccs elements ({sample_w * L_LIMBS} of {N_COLS} columns), kappa={KAPPA}; "
-              "throughput is linear in columns")
+    value = units * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "zkvm_step_witness_commit", "kappa": KAPPA, "w_len": W_LEN, "n": N_COLS, "d": 24,
-                   "B": 1 << LOG2_B, "L": L_LIMBS, "cpu_impl": "C restatement of the reference's rayon path (oracle/), OpenMP"},
-        "commitments_per_s": value / N_COLS,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": scaling,
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+        "commitments_per_s": value / (N_COLS if args.gpus <= 1 else N_SHARDED),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
 
 
-# ---- our arm -------------------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+# ---- shared pieces of our arm -----------------------------------------------------------------------------------------
+class Ctx:
+    """torch / distributed plumbing of one rank."""
 
-    import latticeum_b200 as LB
-    from latticeum_b200 import _capi as capi
-    from latticeum_b200.device import DeviceScheme
-    from latticeum_b200.sharded import ShardedAjtaiScheme
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
 
-    # -- build this rank's column block of the matrix and its block of the step witness ----------------------------------
-    scheme = LB.AjtaiCommitmentScheme(KAPPA, N_COLS, device=local_rank)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, steps):
+        """K calls of fn between barriers, CUDA events on the launching stream, max over ranks; ms per step."""
+        torch = self.torch
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        self.barrier()
+        t1 = time.perf_counter()
+        return self.max_over_ranks(ev0.elapsed_time(ev1)) / steps, (t0, t1)
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def build_scheme(LB, rank_seed, n, device, mont):
+    from latticeum_b200 import scheme as S
+
+    scheme = LB.AjtaiCommitmentScheme(KAPPA, n, mont=mont, device=device)
     for i in range(KAPPA):
-        scheme.upload_rows(i, matrix_row(rank, i)[None])
-    eng = DeviceScheme(scheme)
-    sharded = ShardedAjtaiScheme(eng, world, rank, exchange=os.environ.get("LAT_EXCHANGE", "auto"))
-    w_host = steady_state_w(rank)
-    w_dev = eng.to_device(w_host)
-    partial = eng.new_commitment()
-    # Consecutive steps may overlap on the device (the next step's witness kernel starts under the draining
-    # matrix-vector kernel): legal here because every step's w_ccs is resident before the timed region starts.
-    step_overlap = os.environ.get("LAT_STEP_OVERLAP", "1") == "1"
-    eng.set_step_overlap(step_overlap)
+        row = matrix_row(rank_seed, i, n)
+        scheme.upload_rows(i, (S.to_mont(row) if mont else row)[None])
+    return scheme
 
-    def step():
-        return sharded.witness_commit(w_dev, partial)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        cm_dev = step()
-    barrier()
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.25)
-    profile_in_loop = os.environ.get("LAT_BENCH_PROFILE_IN_LOOP") == "1"
-    serial_ms_per_step = None
-    if profile_in_loop:
-        eng.set_profiling(True)
-        eng.mac_profile()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_wall0 = time.perf_counter()
-    ev0.record()
-    for _ in range(args.steps):
-        cm_dev = step()
-    ev1.record()
-    barrier()
-    t_wall1 = time.perf_counter()
-    if not profile_in_loop:
-        # Event brackets around mac_kernel would serialise it against the witness kernel (the engine overlaps the two
-        # with a programmatic dependent launch), so the kernel's own duration is taken in a second pass of the same
-        # K steps on the same inputs, immediately after the timed region.
-        eng.set_profiling(True)
-        eng.mac_profile()
-        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev2.record()
-        for _ in range(args.steps):
-            cm_dev = step()
-        ev3.record()
-        barrier()
-        serial_ms_per_step = ev2.elapsed_time(ev3) / args.steps
+def mac_roofline(eng, step, steps, ctx, alg_bytes, kernel_name, ms_per_step):
+    """Second pass of the same K steps with CUDA-event brackets around every mac_kernel launch (brackets would serialise
+    the kernel against the producer kernel it overlaps with in the timed region, hence not inside it)."""
+    torch = ctx.torch
+    eng.set_profiling(True)
+    eng.mac_profile()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.barrier()
+    ev2.record()
+    for _ in range(steps):
+        step()
+    ev3.record()
+    ctx.barrier()
+    serial_ms = ev2.elapsed_time(ev3) / steps
     mac_sum_ms, mac_launches = eng.mac_profile()
     eng.set_profiling(False)
-    elapsed_ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    ms_per_step = elapsed_ms / args.steps
-    value = world * N_COLS * args.steps / (elapsed_ms * 1e-3)
-
-    # -- e2e: the host-buffer C ABI call (pinned host memory), H2D of w_ccs and D2H of the commitment every step --------
-    e2e = None
-    if world == 1:
-        L = capi.lib()
-        hw, hcm = C.c_void_p(), C.c_void_p()
-        assert L.lat_host_alloc(C.byref(hw), W_LEN * ELEM_B) == 0 and L.lat_host_alloc(C.byref(hcm), KAPPA * ELEM_B) == 0
-        C.memmove(hw, w_host.ctypes.data, W_LEN * ELEM_B)
-        for _ in range(3):
-            st = L.lat_ajtai_witness_from_w_ccs(scheme._h, hw, W_LEN, None, None, hcm)
-            assert st == 0, capi.last_error()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            L.lat_ajtai_witness_from_w_ccs(scheme._h, hw, W_LEN, None, None, hcm)
-        t1 = time.perf_counter()
-        cm_sync = np.ctypeslib.as_array(C.cast(hcm, C.POINTER(C.c_uint64)), shape=(KAPPA, 24)).copy()
-        sync_call = {"value": N_COLS * args.steps / (t1 - t0), "ms_per_step": (t1 - t0) / args.steps * 1e3,
-                     "api": "lat_ajtai_witness_from_w_ccs, one blocking call per step (pinned w_ccs read in place over PCIe)"}
-        # the pipelined form of the same call: a stream of steps, every step's w_ccs uploaded from its own pinned buffer
-        # and its commitment downloaded, LAT_PIPELINE_DEPTH steps in flight
-        depth = capi.LAT_PIPELINE_DEPTH
-        hws, hcms = [], []
-        for i in range(depth):
-            a, b = C.c_void_p(), C.c_void_p()
-            assert L.lat_host_alloc(C.byref(a), W_LEN * ELEM_B) == 0 and L.lat_host_alloc(C.byref(b), KAPPA * ELEM_B) == 0
-            C.memmove(a, w_host.ctypes.data, W_LEN * ELEM_B)
-            hws.append(a)
-            hcms.append(b)
-
-        def run_pipelined(nsteps):
-            tk = C.c_uint64(0)
-            for k in range(nsteps):
-                if k >= depth:
-                    assert L.lat_ajtai_wait(scheme._h, k0 + k - depth) == 0, capi.last_error()
-                assert L.lat_ajtai_submit_w_ccs(scheme._h, hws[k % depth], W_LEN, hcms[k % depth], C.byref(tk)) == 0, capi.last_error()
-                if k == 0:
-                    k0 = tk.value
-            for k in range(max(nsteps - depth, 0), nsteps):
-                assert L.lat_ajtai_wait(scheme._h, k0 + k) == 0, capi.last_error()
-
-        run_pipelined(2 * depth)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        run_pipelined(args.steps)
-        t1 = time.perf_counter()
-        cm_e2e = np.ctypeslib.as_array(C.cast(hcms[(args.steps - 1) % depth], C.POINTER(C.c_uint64)), shape=(KAPPA, 24)).copy()
-        assert np.array_equal(cm_e2e, cm_sync), "pipelined and blocking host calls disagree"
-        e2e = {"value": N_COLS * args.steps / (t1 - t0), "unit": UNIT, "h2d_bytes_per_step": W_LEN * ELEM_B,
-               "d2h_bytes_per_step": KAPPA * ELEM_B + 4, "ms_per_step": (t1 - t0) / args.steps * 1e3,
-               "api": "lat_ajtai_submit_w_ccs(w_ccs_host_pinned, cm_host) / lat_ajtai_wait: every step uploads its w_ccs "
-                      f"(copy engine) and downloads its commitment, {depth} steps in flight; witness stays device-resident",
-               "blocking_call": sync_call}
-        for p_ in hws + hcms:
-            L.lat_host_free(p_)
-        # the full drop-in (Witness with f and f_coeff materialised on the host, as the reference's struct holds them)
-        hf, hfc = C.c_void_p(), C.c_void_p()
-        L.lat_host_alloc(C.byref(hf), N_COLS * ELEM_B)
-        L.lat_host_alloc(C.byref(hfc), N_COLS * ELEM_B)
-        reps = max(3, min(args.steps, 20))
-        L.lat_ajtai_witness_from_w_ccs(scheme._h, hw, W_LEN, hfc, hf, hcm)
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            L.lat_ajtai_witness_from_w_ccs(scheme._h, hw, W_LEN, hfc, hf, hcm)
-        t1 = time.perf_counter()
-        e2e["full_witness_to_host"] = {"value": N_COLS * reps / (t1 - t0), "ms_per_step": (t1 - t0) / reps * 1e3,
-                                       "d2h_bytes_per_step": 2 * N_COLS * ELEM_B + KAPPA * ELEM_B}
-        for p in (hw, hcm, hf, hfc):
-            L.lat_host_free(p)
-        eng.bind_stream()
-    else:
-        # N > 1: per rank, pinned host w_ccs block -> device, sharded commit + exchange, commitment back to the host,
-        # every step; steps are pipelined (upload / kernels / download of neighbouring steps overlap)
-        from latticeum_b200.sharded import ShardedCommitPipeline
-
-        pipe = ShardedCommitPipeline(sharded, W_LEN)
-        w_pins = [torch.from_numpy(w_host.view(np.int64)).pin_memory() for _ in range(pipe.depth)]
-
-        def run_pipelined(nsteps):
-            k0 = pipe.next_ticket
-            for k in range(nsteps):
-                if k >= pipe.depth:
-                    pipe.wait(k0 + k - pipe.depth)
-                pipe.submit(w_pins[k % pipe.depth])
-            last = None
-            for k in range(max(nsteps - pipe.depth, 0), nsteps):
-                last = pipe.wait(k0 + k)
-            return last
-
-        run_pipelined(2 * pipe.depth)
-        barrier()
-        t0 = time.perf_counter()
-        cm_pin = run_pipelined(args.steps)
-        barrier()
-        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        assert torch.equal(cm_pin.to(dev), cm_dev), "pipelined host path and device path disagree"
-        e2e = {"value": world * N_COLS * args.steps / float(dt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": W_LEN * ELEM_B, "d2h_bytes_per_step": KAPPA * ELEM_B,
-               "ms_per_step": float(dt.item()) / args.steps * 1e3,
-               "api": f"per rank: ShardedCommitPipeline.submit(pinned w_ccs block) / wait -> pinned cm, {pipe.depth} steps in flight "
-                      "(bytes are per rank)"}
-    sampler.stop()
-    clocks = sampler.summary(t_wall0, t_wall1)
-
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-
-    # -- roofline of the dominant kernel (mac_kernel): algorithmic bytes = 192 B of A per ring MAC x kappa*n ------------
     peak, peak_src = measured_peaks()
-    alg_bytes = KAPPA * N_COLS * ELEM_B
     mac_ms = mac_sum_ms / max(mac_launches, 1)
     achieved = alg_bytes / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": ncu_traffic(), "kernel": "lat::mac_kernel<1>", "algorithmic_bytes_per_launch": alg_bytes,
-                "kernel_ms": mac_ms,
-                # share of the SERIALISED step (the bracketed second pass, kernels back to back as under ncu); in the timed
-                # region the witness kernel runs under this kernel's tail, so kernel_ms / ms_per_step is not a share
-                "kernel_share_of_step": mac_ms / (serial_ms_per_step or ms_per_step) if ms_per_step else None,
-                "serialised_ms_per_step": serial_ms_per_step,
-                "launches_timed": int(mac_launches), "peak_source": peak_src,
-                "timed_in": "the timed region itself" if profile_in_loop else
-                            "a second pass of the same K steps right after the timed region (event brackets would serialise the "
-                            "kernel against the witness kernel it overlaps with in the timed region)"}
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+            "traffic": ncu_traffic(), "kernel": kernel_name, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": mac_ms,
+            # share of the SERIALISED step (the bracketed pass, kernels back to back as under ncu)
+            "kernel_share_of_step": mac_ms / serial_ms if serial_ms else None, "serialised_ms_per_step": serial_ms,
+            "step_level_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak if ms_per_step else None,
+            "launches_timed": int(mac_launches), "peak_source": peak_src,
+            "timed_in": "a second pass of the same K steps right after the timed region, CUDA events around each launch"}
 
-    # -- CPU baseline beside it (N = 1 only): the oracle port on the host cores, bounded sample ----------------------------
+
+# ---- N = 1: the zkVM step-witness commit (configs[1]) -------------------------------------------------------------------
+def run_single(args, ctx):
+    import latticeum_b200 as LB
+    from latticeum_b200 import _capi as capi
+    from latticeum_b200 import scheme as S
+    from latticeum_b200.device import DeviceScheme
+
+    torch = ctx.torch
+    mont = args.repr == "montgomery"
+    enc = (lambda x: S.to_mont(x)) if mont else (lambda x: x)
+    scheme = build_scheme(LB, 0, N_COLS, ctx.local_rank, mont)
+    eng = DeviceScheme(scheme)
+    w_canon = steady_state_w(0)
+    w_host = enc(w_canon)
+    w_dev = eng.to_device(w_host)
+    cm_dev = eng.new_commitment()
+    L = capi.lib()
+
+    def step():
+        return eng.witness_commit(w_dev, cm_dev)
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step()
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local_rank)
+    sampler.start()
+    time.sleep(0.2)
+
+    # -- value: K dependent device-resident steps (no cross-step overlap: the reference's IVC steps are dependent) --------
+    eng.set_step_overlap(False)
+    ms_per_step, (tw0, tw1) = ctx.timed(step, args.steps)
+    value = N_COLS / (ms_per_step * 1e-3)
+    # -- the same with consecutive steps overlapped on the device (independent witnesses only) ---------------------------
+    eng.set_step_overlap(True)
+    for _ in range(3):
+        step()
+    ms_overlap, _ = ctx.timed(step, args.steps)
+    eng.set_step_overlap(False)
+    # -- sustained: >= 2000 back-to-back steps so that the clocks / power record has real samples ------------------------
+    sus_steps = max(2000, args.steps)
+    ms_sustained, (ts0, ts1) = ctx.timed(step, sus_steps)
+    clocks = sampler.summary(tw0, tw1)
+    clocks_sustained = sampler.summary(ts0 + 0.05, ts1)
+    roofline = mac_roofline(eng, step, args.steps, ctx, KAPPA * N_COLS * ELEM_B, "lat::mac_kernel<1,8>", ms_per_step)
+
+    # -- e2e: ONE BLOCKING host-buffer C ABI call per step (pinned w_ccs in, commitment out) -----------------------------
+    hw, hcm = C.c_void_p(), C.c_void_p()
+    assert L.lat_host_alloc(C.byref(hw), W_LEN * ELEM_B) == 0 and L.lat_host_alloc(C.byref(hcm), KAPPA * ELEM_B) == 0
+    C.memmove(hw, w_host.ctypes.data, W_LEN * ELEM_B)
+    for _ in range(3):
+        assert L.lat_ajtai_witness_from_w_ccs(scheme._h, hw, W_LEN, None, None, hcm) == 0, capi.last_error()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        L.lat_ajtai_witness_from_w_ccs(scheme._h, hw, W_LEN, None, None, hcm)
+    t1 = time.perf_counter()
+    cm_e2e = np.ctypeslib.as_array(C.cast(hcm, C.POINTER(C.c_uint64)), shape=(KAPPA, 24)).copy()
+    e2e = {"value": N_COLS * args.steps / (t1 - t0), "unit": UNIT, "h2d_bytes_per_step": W_LEN * ELEM_B,
+           "d2h_bytes_per_step": KAPPA * ELEM_B + 4, "ms_per_step": (t1 - t0) / args.steps * 1e3,
+           "api": "lat_ajtai_witness_from_w_ccs(w_ccs pinned host, cm host): one BLOCKING call per step, each step issued "
+                  "after the previous one returned (the IVC dependency of zkvm/src/main.rs:140-182)"}
+    # the same call returning the witness the host's MLE code needs (Witness.f_coeff as int16 digits), see DESIGN.md
+    if hasattr(L, "lat_ajtai_witness_from_w_ccs_compact"):
+        hd = C.c_void_p()
+        assert L.lat_host_alloc(C.byref(hd), N_COLS * 24 * 2) == 0
+        for _ in range(3):
+            assert L.lat_ajtai_witness_from_w_ccs_compact(scheme._h, hw, W_LEN, hd, None, hcm) == 0, capi.last_error()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            L.lat_ajtai_witness_from_w_ccs_compact(scheme._h, hw, W_LEN, hd, None, hcm)
+        t1 = time.perf_counter()
+        e2e["witness_digits_to_host"] = {"value": N_COLS * args.steps / (t1 - t0), "ms_per_step": (t1 - t0) / args.steps * 1e3,
+                                         "d2h_bytes_per_step": N_COLS * 48 + KAPPA * ELEM_B,
+                                         "api": "lat_ajtai_witness_from_w_ccs_compact: cm + f_coeff as int16 digits (4.7 MB)"}
+        L.lat_host_free(hd)
+    # full Witness as the reference's struct holds it (f and f_coeff as u64 on the host: 38 MB D2H, PCIe-bound)
+    hf, hfc = C.c_void_p(), C.c_void_p()
+    L.lat_host_alloc(C.byref(hf), N_COLS * ELEM_B)
+    L.lat_host_alloc(C.byref(hfc), N_COLS * ELEM_B)
+    reps = max(3, min(args.steps, 20))
+    L.lat_ajtai_witness_from_w_ccs(scheme._h, hw, W_LEN, hfc, hf, hcm)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        L.lat_ajtai_witness_from_w_ccs(scheme._h, hw, W_LEN, hfc, hf, hcm)
+    t1 = time.perf_counter()
+    e2e["full_witness_to_host"] = {"value": N_COLS * reps / (t1 - t0), "ms_per_step": (t1 - t0) / reps * 1e3,
+                                   "d2h_bytes_per_step": 2 * N_COLS * ELEM_B + KAPPA * ELEM_B}
+    for p in (hf, hfc):
+        L.lat_host_free(p)
+    # independent tickets (NOT available to consecutive IVC steps): submit / wait, LAT_PIPELINE_DEPTH in flight
+    depth = capi.LAT_PIPELINE_DEPTH
+    hws, hcms = [], []
+    for _ in range(depth):
+        a, b = C.c_void_p(), C.c_void_p()
+        assert L.lat_host_alloc(C.byref(a), W_LEN * ELEM_B) == 0 and L.lat_host_alloc(C.byref(b), KAPPA * ELEM_B) == 0
+        C.memmove(a, w_host.ctypes.data, W_LEN * ELEM_B)
+        hws.append(a)
+        hcms.append(b)
+
+    def run_tickets(nsteps):
+        tk = C.c_uint64(0)
+        k0 = 0
+        for k in range(nsteps):
+            if k >= depth:
+                assert L.lat_ajtai_wait(scheme._h, k0 + k - depth) == 0, capi.last_error()
+            assert L.lat_ajtai_submit_w_ccs(scheme._h, hws[k % depth], W_LEN, hcms[k % depth], C.byref(tk)) == 0, capi.last_error()
+            if k == 0:
+                k0 = tk.value
+        for k in range(max(nsteps - depth, 0), nsteps):
+            assert L.lat_ajtai_wait(scheme._h, k0 + k) == 0, capi.last_error()
+
+    run_tickets(2 * depth)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run_tickets(args.steps)
+    t1 = time.perf_counter()
+    cm_tk = np.ctypeslib.as_array(C.cast(hcms[(args.steps - 1) % depth], C.POINTER(C.c_uint64)), shape=(KAPPA, 24)).copy()
+    e2e["independent_tickets"] = {"value": N_COLS * args.steps / (t1 - t0), "ms_per_step": (t1 - t0) / args.steps * 1e3,
+                                  "api": f"lat_ajtai_submit_w_ccs / lat_ajtai_wait, {depth} independent steps in flight "
+                                         "(a throughput mode; consecutive IVC steps cannot use it)"}
+    for p_ in hws + hcms + [hw, hcm]:
+        L.lat_host_free(p_)
+    eng.bind_stream()
+    sampler.stop()
+
+    # -- the other representation (canonical limbs), device-resident, for comparison --------------------------------------
+    other = None
+    if not args.quick:
+        scheme_o = build_scheme(LB, 0, N_COLS, ctx.local_rank, not mont)
+        eng_o = DeviceScheme(scheme_o)
+        wo_dev = eng_o.to_device(w_canon if mont else S.to_mont(w_canon))
+        cmo = eng_o.new_commitment()
+        for _ in range(3):
+            eng_o.witness_commit(wo_dev, cmo)
+        ms_o, _ = ctx.timed(lambda: eng_o.witness_commit(wo_dev, cmo), args.steps)
+        other = {"repr": "canonical" if mont else "montgomery", "ms_per_step": ms_o, "value": N_COLS / (ms_o * 1e-3)}
+        scheme_o.close()
+
+    # -- the whole fold step and the configs[4] commit on this one GPU ----------------------------------------------------
+    fold_step = None if args.quick else fold_step_leg(args, ctx, LB, scheme, eng, mont, w_canon)
+    big = None if args.quick else single_gpu_2_20_leg(args, ctx, LB)
+
+    # -- CPU baseline beside it: the oracle port on the host cores, bounded sample; parity of the timed results ------------
     cpu_baseline, parity = None, None
-    if world == 1 and not args.no_cpu:
+    if not args.no_cpu:
         from oracle import c_oracle as CO  # checker / CPU arm only
 
         A = np.empty((KAPPA, N_COLS, 24), np.uint64)
@@ -421,34 +499,282 @@ def run_ours(args):
         reps, t_cpu, cm_cpu = 0, 0.0, None
         while reps < 3 or (t_cpu < 10.0 and reps < 40):
             t0 = time.perf_counter()
-            cm_cpu = cpu_step(CO, A, w_host)
+            cm_cpu = cpu_step(CO, A, w_canon)
             t_cpu += time.perf_counter() - t0
             reps += 1
         cpu_baseline = {"value": N_COLS * reps / t_cpu, "unit": UNIT, "cores": CO.num_threads(), "kind": "port",
                         "sample": f"{reps} full steps (kappa={KAPPA}, n={N_COLS}), {t_cpu / reps * 1e3:.1f} ms each",
                         "ms_per_step": t_cpu / reps * 1e3}
-        got = DeviceScheme.to_numpy(cm_dev)
-        parity = bool(np.array_equal(got, cm_cpu) and np.array_equal(cm_e2e, cm_cpu))
+        dec = (lambda x: CO.from_mont(x)) if mont else (lambda x: x)
+        parity = bool(np.array_equal(dec(DeviceScheme.to_numpy(cm_dev)), cm_cpu) and np.array_equal(dec(cm_e2e), cm_cpu)
+                      and np.array_equal(dec(cm_tk), cm_cpu))
+        if fold_step is not None and fold_step.get("_check") is not None:
+            ok, cpu_ms = fold_step.pop("_check")(CO, A)
+            fold_step["parity_vs_cpu"], fold_step["cpu_ms"] = ok, cpu_ms
+            parity = parity and ok
+    if fold_step is not None:
+        fold_step.pop("_check", None)
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
-        "config": {"workload": "zkvm_step_witness_commit", "kappa": KAPPA, "w_len": W_LEN, "n_per_gpu": N_COLS,
-                   "n_total": world * N_COLS, "d": 24, "B": 1 << LOG2_B, "L": L_LIMBS,
+        "config": {"workload": "zkvm_step_witness_commit", "kappa": KAPPA, "w_len": W_LEN, "n": N_COLS, "d": 24,
+                   "B": 1 << LOG2_B, "L": L_LIMBS, "repr": args.repr,
                    "pipeline": "iCRT -> gadget_decompose(2^15,5) -> CRT -> A*f (Witness::from_w_ccs + commit)",
-                   "sharding": f"columns x{world}" + (f", 6 KB partial commitments exchanged and folded mod q; exchange = {sharded.exchange}"
-                                                        if world > 1 else ""),
                    "l2": "inputs larger than L2 (607 MB matrix streamed every step)",
-                   "step_overlap": step_overlap},
-        "commitments_per_s": args.steps / (elapsed_ms * 1e-3),
-        "e2e": e2e, "gpu_launches": args.steps * (2 + (1 if world > 1 else 0)),
+                   "dependency": "value and e2e time dependent steps (no cross-step overlap, one blocking call per step)"},
+        "commitments_per_s": 1e3 / ms_per_step,
+        "e2e": e2e, "gpu_launches": args.steps * 2,
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_vs_cpu": parity,
+        "independent_steps_overlapped": {"ms_per_step": ms_overlap, "value": N_COLS / (ms_overlap * 1e-3),
+                                         "note": "lat_ajtai_set_step_overlap: next witness kernel under the draining mac kernel"},
+        "sustained": {"steps": sus_steps, "ms_per_step": ms_sustained, "value": N_COLS / (ms_sustained * 1e-3),
+                      "clocks": clocks_sustained},
+        "other_repr": other, "fold_step": fold_step, "n_2_20_single_gpu": big, "imad_peak": None if args.quick else imad_peak(),
     }
     emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    scheme.close()
+
+
+def fold_step_leg(args, ctx, LB, scheme, eng, mont, w_canon):
+    """Filled in by the fold-step entry points (lat_ajtai_fold_step_*); absent until the library exports them."""
+    from latticeum_b200 import _capi as capi
+
+    if not hasattr(capi.lib(), "lat_ajtai_fold_step_begin"):
+        return None
+    from latticeum_b200 import foldstep
+
+    return foldstep.bench_leg(args, ctx, scheme, eng, mont, w_canon, sys.modules[__name__])
+
+
+def single_gpu_2_20_leg(args, ctx, LB):
+    """configs[4]'s commit (kappa = 32, n = 2^20, CRT-form witness) on ONE GPU: the base of the strong-scaling curve."""
+    from latticeum_b200.device import DeviceScheme
+
+    try:
+        scheme = LB.AjtaiCommitmentScheme(KAPPA, N_SHARDED, device=ctx.local_rank)
+        rng = np.random.Generator(np.random.PCG64(4242))
+        for i in range(KAPPA):  # masked to < 2^63 < q: uniform enough for a bandwidth figure, and quick to generate
+            scheme.upload_rows(i, (rng.integers(0, 2**63, size=(1, N_SHARDED, 24), dtype=np.uint64)))
+        eng = DeviceScheme(scheme)
+        f = eng.to_device(rng.integers(0, 2**63, size=(N_SHARDED, 24), dtype=np.uint64))
+        cm = eng.new_commitment()
+        step = lambda: eng.commit_ntt(f, cm)  # noqa: E731
+        for _ in range(3):
+            step()
+        steps = max(5, min(args.steps, 20))
+        ms, _ = ctx.timed(step, steps)
+        roof = mac_roofline(eng, step, steps, ctx, KAPPA * N_SHARDED * ELEM_B, "lat::mac_kernel<1,8>", ms)
+        scheme.close()
+        return {"workload": "commit_ntt, kappa=32, n=2^20, one GPU", "ms_per_step": ms, "value": N_SHARDED / (ms * 1e-3),
+                "roofline_frac": roof["frac"], "kernel_ms": roof["kernel_ms"], "step_level_frac": roof["step_level_frac"]}
+    except Exception as e:  # an extra: never fail the line for it
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
+# ---- N > 1: one n = 2^20 witness, column-sharded (configs[4], strong scaling) --------------------------------------------
+def run_sharded(args, ctx):
+    import latticeum_b200 as LB
+    from latticeum_b200.device import DeviceScheme
+    from latticeum_b200.sharded import ShardedAjtaiScheme, shard_bounds
+
+    torch, dist, rank, world = ctx.torch, ctx.dist, ctx.rank, ctx.world
+    lo, hi = shard_bounds(N_SHARDED, world, rank)
+    n_local = hi - lo
+    t_setup = time.perf_counter()
+    # this rank's column block of the matrix (seeded per (world, rank, row)) and of the witness
+    A_local = np.empty((KAPPA, n_local, 24), np.uint64)
+    scheme = LB.AjtaiCommitmentScheme(KAPPA, n_local, device=ctx.local_rank)
+    for i in range(KAPPA):
+        A_local[i] = matrix_row(1000 * world + rank, i, n_local)
+        scheme.upload_rows(i, A_local[i][None])
+    f_local = uniform_fq((n_local, 24), 5_000_000 + 1000 * world + rank)
+    eng = DeviceScheme(scheme)
+    sharded = ShardedAjtaiScheme(eng, world, rank, exchange=os.environ.get("LAT_EXCHANGE", "auto"))
+    f_dev = eng.to_device(f_local)
+    partial = eng.new_commitment()
+    log(f"setup {time.perf_counter() - t_setup:.1f} s, exchange = {sharded.exchange}, columns [{lo}, {hi})")
+    out = {}
+
+    def step():
+        out["cm"] = sharded.commit_ntt(f_dev, partial)
+        return out["cm"]
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step()
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local_rank)
+    sampler.start()
+    time.sleep(0.2)
+    ms_per_step, (tw0, tw1) = ctx.timed(step, args.steps)
+    cm_timed = DeviceScheme.to_numpy(out["cm"]).copy()
+    value = N_SHARDED / (ms_per_step * 1e-3)
+    sus_steps = max(500, args.steps)
+    ms_sustained, (ts0, ts1) = ctx.timed(step, sus_steps)
+    clocks = sampler.summary(tw0, tw1)
+    clocks_sustained = sampler.summary(ts0 + 0.05, ts1)
+    alg_bytes = KAPPA * n_local * ELEM_B
+    roofline = mac_roofline(eng, step, args.steps, ctx, alg_bytes, "lat::mac_kernel<1,8> (per rank, its column block)", ms_per_step)
+    roofline["per_rank_hbm_floor_ms"] = alg_bytes / (roofline["peak"] * 1e9) * 1e3
+    roofline["kernel_ms_max_over_ranks"] = ctx.max_over_ranks(roofline["kernel_ms"])
+    roofline["bounded_by"] = ("per-launch fixed cost (fill, drain, publication: ~14 us) on a "
+                              f"{roofline['per_rank_hbm_floor_ms'] * 1e3:.0f} us shard stream, then witness re-layout + exchange")
+
+    # -- e2e: per rank, pinned host block of f -> device, commit + exchange, commitment back to the host; blocking steps --
+    f_pin = torch.from_numpy(f_local.view(np.int64)).pin_memory()
+    cm_pin = torch.empty((KAPPA, 24), dtype=torch.int64).pin_memory()
+
+    def e2e_step():
+        f_dev.copy_(f_pin, non_blocking=True)
+        cm = sharded.commit_ntt(f_dev, partial)
+        cm_pin.copy_(cm, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    ctx.barrier()
+    dt = ctx.max_over_ranks(time.perf_counter() - t0)
+    cm_e2e = cm_pin.numpy().view(np.uint64).copy()
+    e2e = {"value": N_SHARDED * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": n_local * ELEM_B,
+           "d2h_bytes_per_step": KAPPA * ELEM_B, "ms_per_step": dt / args.steps * 1e3,
+           "api": "per rank and per step: pinned host block of f -> device (cudaMemcpyAsync), ShardedAjtaiScheme.commit_ntt "
+                  "(extend + A*f + exchange), full commitment -> pinned host, synchronize (bytes are per rank; PCIe-bound)"}
+    sampler.stop()
+
+    # -- parity: every rank commits ITS block with the oracle on its share of the host cores; partial sums mod q ----------
+    parity, cpu_baseline = None, None
+    if not args.no_cpu:
+        from oracle import c_oracle as CO  # checker only
+
+        CO.set_num_threads(max(1, host_threads() // world))
+        t0 = time.perf_counter()
+        part_cpu = CO.commit(A_local, f_local)
+        t_cpu = time.perf_counter() - t0
+        gathered = torch.empty((world, KAPPA, 24), dtype=torch.int64, device=ctx.dev)
+        dist.all_gather_into_tensor(gathered.view(-1), torch.from_numpy(part_cpu.view(np.int64)).to(ctx.dev).view(-1))
+        parts = gathered.cpu().numpy().view(np.uint64).astype(object)
+        exp = (parts.sum(axis=0) % Q).astype(np.uint64)
+        ok = bool(np.array_equal(cm_timed, exp) and np.array_equal(cm_e2e, exp))
+        parity = bool(ctx.max_over_ranks(0.0 if ok else 1.0) == 0.0)  # every rank holds the full commitment: all must agree
+        t_cpu = ctx.max_over_ranks(t_cpu)
+        cpu_baseline = {"value": N_SHARDED / t_cpu, "unit": UNIT, "cores": max(1, host_threads() // world) * world, "kind": "port",
+                        "sample": f"one full commit (kappa={KAPPA}, n=2^20): every rank's column block on its share of the host "
+                                  f"cores, concurrently; {t_cpu * 1e3:.0f} ms", "ms_per_step": t_cpu * 1e3}
+    del A_local
+
+    weak = None
+    if os.environ.get("LAT_BENCH_WEAK", "1") == "1" and not args.quick:
+        try:
+            weak = weak_zkvm_leg(args, ctx, LB, sharded.exchange)
+        except Exception as e:  # the extra leg must not take the line down with it
+            weak = {"error": f"{type(e).__name__}: {e}"}
+    if rank != 0:
+        scheme.close()
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic",
+        "config": {"workload": "sharded_commit_ntt_n_2_20", "kappa": KAPPA, "n_total": N_SHARDED, "n_per_gpu": n_local, "d": 24,
+                   "pipeline": "per rank: extend(f block) -> A block * f block; then one exchange of the 6 KB partials, summed mod q",
+                   "sharding": f"columns x{world}; exchange = {sharded.exchange}",
+                   "l2": f"inputs larger than L2 ({alg_bytes / 1e6:.0f} MB matrix block streamed every step)",
+                   "note": "N = 1 of this bench is the zkVM-width step commit (configs[1]); the one-GPU figure of THIS workload is "
+                           "the N = 1 line's n_2_20_single_gpu"},
+        "commitments_per_s": 1e3 / ms_per_step,
+        "e2e": e2e, "gpu_launches": args.steps * (3 if sharded.exchange == "p2p" else 3),
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_vs_cpu": parity,
+        "sustained": {"steps": sus_steps, "ms_per_step": ms_sustained, "value": N_SHARDED / (ms_sustained * 1e-3),
+                      "clocks": clocks_sustained},
+        "weak_zkvm_width": weak,
+    }
+    emit(line)
+    scheme.close()
+
+
+def weak_zkvm_leg(args, ctx, LB, exchange):
+    """Round 1's weak-scaling workload, kept as an extra: one zkVM-sized column block per GPU, Witness::from_w_ccs + commit
+    on every block + exchange; device-resident with consecutive steps overlapped, and the ticketed host-buffer pipeline.
+    Parity against the oracle as in the main leg (per-rank oracle partials summed mod q)."""
+    from latticeum_b200.device import DeviceScheme
+    from latticeum_b200.sharded import ShardedAjtaiScheme, ShardedCommitPipeline
+
+    torch, dist, rank, world = ctx.torch, ctx.dist, ctx.rank, ctx.world
+    A_local = np.stack([matrix_row(rank, i) for i in range(KAPPA)])
+    scheme = LB.AjtaiCommitmentScheme(KAPPA, N_COLS, device=ctx.local_rank)
+    for i in range(KAPPA):
+        scheme.upload_rows(i, A_local[i][None])
+    eng = DeviceScheme(scheme)
+    sharded = ShardedAjtaiScheme(eng, world, rank, exchange="p2p" if exchange == "p2p" else "nccl")
+    w_host = steady_state_w(rank)
+    w_dev = eng.to_device(w_host)
+    partial = eng.new_commitment()
+    eng.set_step_overlap(True)
+    out = {}
+
+    def step():
+        out["cm"] = sharded.witness_commit(w_dev, partial)
+
+    for _ in range(5):
+        step()
+    ms, _ = ctx.timed(step, args.steps)
+    cm_dev = DeviceScheme.to_numpy(out["cm"]).copy()
+    pipe = ShardedCommitPipeline(sharded, W_LEN)
+    w_pins = [torch.from_numpy(w_host.view(np.int64)).pin_memory() for _ in range(pipe.depth)]
+
+    def run_pipelined(nsteps):
+        k0 = pipe.next_ticket
+        last = None
+        for k in range(nsteps):
+            if k >= pipe.depth:
+                pipe.wait(k0 + k - pipe.depth)
+            pipe.submit(w_pins[k % pipe.depth])
+        for k in range(max(nsteps - pipe.depth, 0), nsteps):
+            last = pipe.wait(k0 + k)
+        return last
+
+    run_pipelined(2 * pipe.depth)
+    ctx.barrier()
+    t0 = time.perf_counter()
+    cm_pin = run_pipelined(args.steps)
+    ctx.barrier()
+    dt = ctx.max_over_ranks(time.perf_counter() - t0)
+    cm_pipe = cm_pin.numpy().view(np.uint64).copy()
+    eng.set_step_overlap(False)
+    res = {"workload": "zkvm_step_witness_commit, one zkVM-sized column block per GPU (weak scaling)", "n_total": world * N_COLS,
+           "ms_per_step": ms, "value": world * N_COLS / (ms * 1e-3), "step_overlap": True,
+           "e2e_tickets": {"ms_per_step": dt / args.steps * 1e3, "value": world * N_COLS * args.steps / dt,
+                           "api": f"ShardedCommitPipeline.submit/wait, {pipe.depth} independent steps in flight per rank"},
+           "exchange": sharded.exchange}
+    if not args.no_cpu:
+        from oracle import c_oracle as CO  # checker only
+
+        CO.set_num_threads(max(1, host_threads() // world))
+        part_cpu = cpu_step(CO, A_local, w_host)
+        gathered = torch.empty((world, KAPPA, 24), dtype=torch.int64, device=ctx.dev)
+        dist.all_gather_into_tensor(gathered.view(-1), torch.from_numpy(part_cpu.view(np.int64)).to(ctx.dev).view(-1))
+        exp = (gathered.cpu().numpy().view(np.uint64).astype(object).sum(axis=0) % Q).astype(np.uint64)
+        ok = bool(np.array_equal(cm_dev, exp) and np.array_equal(cm_pipe, exp))
+        res["parity_vs_cpu"] = bool(ctx.max_over_ranks(0.0 if ok else 1.0) == 0.0)
+    scheme.close()
+    return res
+
+
+def run_ours(args):
+    ctx = Ctx()
+    try:
+        if ctx.world == 1:
+            run_single(args, ctx)
+        else:
+            run_sharded(args, ctx)
+    finally:
+        ctx.close()
 
 
 def main():
@@ -463,7 +789,10 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--repr", default="montgomery", choices=["montgomery", "canonical"],
+                    help="limb representation at the boundary (a Rust/ark-ff host passes Montgomery limbs)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / oracle parity leg")
+    ap.add_argument("--quick", action="store_true", help="skip the extra legs (other repr, fold step, n = 2^20, weak scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

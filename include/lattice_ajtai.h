@@ -130,14 +130,18 @@ int lat_ajtai_witness_from_w_ccs(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w
 int lat_ajtai_witness_from_w_ccs_dev(lat_ajtai *h, const uint64_t *w_ccs_dev, uint64_t w_len,
                                      uint64_t *f_coeff_dev, uint64_t *f_dev, uint64_t *cm_dev);
 
-/* Pipelined form of the same call for a stream of steps (the zkVM commits one witness per VM step,
- * ZKVM/main.rs:121-219,348-367, and knows step i+1's w_ccs before it needs step i's commitment):
- * lat_ajtai_submit_w_ccs queues upload -> iCRT/decompose/CRT -> A * f -> report of cm and returns at once with a
- * ticket; lat_ajtai_wait blocks until that ticket's cm has been written (and reports its LAT_E_DIGIT_OVERFLOW, if
- * any).  At most LAT_PIPELINE_DEPTH tickets may be outstanding; w_ccs and cm must stay valid until the ticket has
- * been waited for.  The upload runs on a copy engine and the kernels of consecutive steps overlap on the device, so
- * with page-locked w_ccs (lat_host_alloc / cudaHostRegister) the call sustains the device-resident rate; pageable
- * memory works but serialises the upload.  The handle's "current witness" is the one submitted last.            */
+/* Non-blocking form of the same call: lat_ajtai_submit_w_ccs queues upload -> iCRT/decompose/CRT -> A * f -> report
+ * of cm and returns at once with a ticket; lat_ajtai_wait blocks until that ticket's cm has been written (and reports
+ * its LAT_E_DIGIT_OVERFLOW, if any).  What it is for: work that is INDEPENDENT of the commitment -- the host's own
+ * MLE/sumcheck work of the same step, or independent provers sharing one matrix.  It does NOT pipeline the steps of
+ * one zkVM run against each other: step i+1's z is built from ivc_output.{acc, w_acc, folding_proof}
+ * (ZKVM/main.rs:140-156), which come out of fold(cm_i, w_i) (ZKVM/main.rs:174-182), so consecutive IVC steps are
+ * strictly dependent and a drop-in caller sees the latency of one ticket (bench.py reports that figure as e2e).
+ * At most LAT_PIPELINE_DEPTH tickets may be outstanding; w_ccs and cm must stay valid until the ticket has been
+ * waited for.  The upload runs on a copy engine; with page-locked w_ccs (lat_host_alloc / cudaHostRegister) it
+ * overlaps the kernels of other tickets, pageable memory works but serialises the upload.  The handle's "current
+ * witness" is the one submitted last.  All per-slot state is allocated at lat_ajtai_create; nothing is allocated,
+ * memset or synchronised on the submit path.                                                                   */
 #define LAT_PIPELINE_DEPTH 4
 int lat_ajtai_submit_w_ccs(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_len, uint64_t *cm, uint64_t *ticket);
 int lat_ajtai_wait(lat_ajtai *h, uint64_t ticket);
@@ -156,6 +160,10 @@ int lat_ajtai_decompose_commit(lat_ajtai *h, const uint64_t *f_coeff, uint64_t n
                                uint64_t *planes_coeff, uint64_t *planes_f, uint64_t *cms);
 int lat_ajtai_decompose_commit_dev(lat_ajtai *h, const uint64_t *f_coeff_dev, uint64_t n, const uint64_t *cm_dev,
                                    uint64_t *planes_coeff_dev, uint64_t *planes_f_dev, uint64_t *cms_dev);
+/* In the _dev form cm_dev may be NULL: cms[0] is then left untouched.  Column-sharded callers do this -- their
+ * cms[1..K-1] are partial sums over one column block, and y_0 needs the exchanged totals -- and finish with
+ * lat_commitment_y0_dev: cms[0] = cm - sum_{k>=1} 2^k cms[k]  (LF/nifs/decomposition.rs:189-197), cms: K x kappa x 24. */
+int lat_commitment_y0_dev(const uint64_t *cm_dev, uint64_t *cms_dev, uint32_t K, uint32_t kappa, void *cuda_stream);
 /* Same, on the witness left resident by the last lat_ajtai_witness_from_w_ccs* call (no re-upload).        */
 int lat_ajtai_decompose_commit_resident(lat_ajtai *h, const uint64_t *cm, uint64_t *planes_coeff,
                                         uint64_t *planes_f, uint64_t *cms);
@@ -265,6 +273,17 @@ int lat_ajtai_set_step_overlap(lat_ajtai *h, int enabled);
  * since profiling was enabled (or since the last call), then resets both.                                     */
 int lat_ajtai_set_profiling(lat_ajtai *h, int enabled);
 int lat_ajtai_mac_profile(lat_ajtai *h, double *sum_ms, uint64_t *launches);
+
+/* ---- bounded device-side waits ----------------------------------------------------------------------------------------
+ * Two kernels wait inside the GPU for something that another engine or GPU delivers: the witness kernel of a
+ * submitted step polls its upload ticket, the exchange kernel polls its peers' flags.  Both waits are bounded by
+ * %globaltimer (default 5000 ms; LAT_SPIN_TIMEOUT_MS in the environment or lat_set_spin_timeout_ms; 0 = unbounded):
+ * on expiry the kernel records what it was waiting for in a per-device status word and carries on, and the next
+ * lat_ajtai_wait / lat_ajtai_synchronize / host-buffer call on that device -- or lat_device_wait_status for callers
+ * of the handle-less exchange -- returns LAT_E_CUDA with a message naming the wait (lat_last_error) and clears the
+ * word.  *code (may be NULL) receives the raw word: low byte 1 = upload ticket, 2 = peer flag; 0 = none.          */
+int lat_set_spin_timeout_ms(uint64_t ms);
+int lat_device_wait_status(int device, uint64_t *code);
 
 /* ---- pinned host memory for callers that want the fast copy path (optional) -------------------------------- */
 int lat_host_alloc(void **ptr, size_t bytes);

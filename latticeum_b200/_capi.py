@@ -65,6 +65,7 @@ SIGNATURES = {
     "lat_ring_crt_dev": (C.c_int, [_u64p, C.c_uint64, _u64p, C.c_void_p]),
     "lat_ring_icrt_dev": (C.c_int, [_u64p, C.c_uint64, _u64p, C.c_void_p]),
     "lat_ring_gadget_decompose": (C.c_int, [_u64p, C.c_uint64, C.c_uint32, C.c_uint32, _u64p, C.c_int, C.c_int]),
+    "lat_commitment_y0_dev": (C.c_int, [_u64p, _u64p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "lat_commitment_sum_dev": (C.c_int, [_u64p, C.c_uint32, C.c_uint64, _u64p, C.c_void_p]),
     "lat_commitment_sum": (C.c_int, [_u64p, C.c_uint32, C.c_uint64, _u64p, C.c_int]),
     "lat_commitment_exchange_dev": (C.c_int, [_u64p, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
@@ -77,6 +78,8 @@ SIGNATURES = {
     "lat_ajtai_set_step_overlap": (C.c_int, [_H, C.c_int]),
     "lat_ajtai_set_profiling": (C.c_int, [_H, C.c_int]),
     "lat_ajtai_mac_profile": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "lat_set_spin_timeout_ms": (C.c_int, [C.c_uint64]),
+    "lat_device_wait_status": (C.c_int, [C.c_int, C.POINTER(C.c_uint64)]),
     "lat_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "lat_host_free": (None, [C.c_void_p]),
 }

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -38,6 +39,68 @@ int fail(int status, const std::string &msg) {
     } while (0)
 
 constexpr size_t ELEM_BYTES = LAT_RING_DEGREE * sizeof(uint64_t);  // 192
+
+// ---- bounded device-side waits (lat::SpinGuard) ----------------------------------------------------------------------
+// One page-locked status word per device, mapped into the device: a kernel whose wait for an upload ticket or for a
+// peer's flag times out stores its code there and carries on; the host side turns a non-zero word into LAT_E_CUDA.
+constexpr int MAX_DEVICES = 64;
+std::mutex g_status_mu;
+unsigned long long *g_status_host[MAX_DEVICES] = {}, *g_status_dev[MAX_DEVICES] = {};
+std::atomic<unsigned long long> g_spin_timeout_ns{~0ull};  // ~0: not yet read from the environment
+
+unsigned long long spin_timeout_ns() {
+    unsigned long long v = g_spin_timeout_ns.load(std::memory_order_relaxed);
+    if (v == ~0ull) {
+        const char *e = getenv("LAT_SPIN_TIMEOUT_MS");
+        v = (e ? strtoull(e, nullptr, 10) : 5000ull) * 1000000ull;
+        g_spin_timeout_ns.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+// the device must be current
+int spin_guard(int device, lat::SpinGuard &g) {
+    if (device < 0 || device >= MAX_DEVICES) return fail(LAT_E_INVALID_ARGUMENT, "device ordinal out of range");
+    std::lock_guard<std::mutex> lock(g_status_mu);
+    if (!g_status_host[device]) {
+        unsigned long long *hp = nullptr, *dp = nullptr;
+        CK(cudaHostAlloc((void **)&hp, sizeof(unsigned long long), cudaHostAllocMapped));
+        *hp = 0;
+        cudaError_t e = cudaHostGetDevicePointer((void **)&dp, hp, 0);
+        if (e != cudaSuccess) {
+            cudaFreeHost(hp);
+            return fail_cuda(e, "cudaHostGetDevicePointer", __LINE__);
+        }
+        g_status_host[device] = hp;
+        g_status_dev[device] = dp;
+    }
+    g.status = g_status_dev[device];
+    g.timeout_ns = spin_timeout_ns();
+    return LAT_OK;
+}
+
+// LAT_OK, or LAT_E_CUDA with a message naming the wait that gave up (and the word is cleared)
+int spin_status(int device, uint64_t *code_out = nullptr) {
+    unsigned long long code = 0;
+    if (device >= 0 && device < MAX_DEVICES) {
+        std::lock_guard<std::mutex> lock(g_status_mu);
+        volatile unsigned long long *hp = g_status_host[device];
+        if (hp && (code = *hp)) *hp = 0;
+    }
+    if (code_out) *code_out = code;
+    if (!code) return LAT_OK;
+    char buf[256];
+    const unsigned long long what = code & 0xff, detail = code >> 8;
+    if (what == lat::SPIN_UPLOAD_TICKET)
+        snprintf(buf, sizeof(buf), "device %d: a witness kernel gave up waiting for the upload ticket %llu (upload never landed)",
+                 device, detail);
+    else if (what == lat::SPIN_PEER_FLAG)
+        snprintf(buf, sizeof(buf), "device %d: the commitment exchange gave up waiting for peer rank %llu at epoch %llu",
+                 device, detail & 0xff, detail >> 8);
+    else
+        snprintf(buf, sizeof(buf), "device %d: a device-side wait timed out (code %llu)", device, code);
+    return fail(LAT_E_CUDA, buf);
+}
 
 struct DevBuf {
     void *p = nullptr;
@@ -129,6 +192,7 @@ struct lat_ajtai {
     lat::PeerPtrs peers{};
     uint64_t peer_epoch = 1;
     uint64_t next_ticket = 0;
+    lat::SpinGuard guard{};  // bound on every device-side wait this handle launches (status word of its device)
     // profiling: pool of event pairs around mac_kernel launches, drained lazily
     static constexpr int EV_POOL = 256;
     bool profiling = false;
@@ -205,8 +269,31 @@ struct lat_ajtai {
         CK(cudaMemcpyAsync(h_flag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
         CK(cudaMemsetAsync(flag.p, 0, sizeof(int), stream));
         CK(cudaStreamSynchronize(stream));
+        int st = spin_status(device);  // a bounded device-side wait gave up: the results are not to be trusted
+        if (st) return st;
         if (*h_flag)
             return fail(LAT_E_DIGIT_OVERFLOW, "a coefficient needs more digits than the decomposition padding allows");
+        return LAT_OK;
+    }
+    // pipelined-step state (lat_ajtai_submit_w_ccs): everything a slot needs, allocated and initialised once at
+    // creation on the handle's own stream and synchronised there -- nothing is allocated or memset on the submit path
+    // (a first-use cudaMemset on the legacy stream once raced the ticket copy on copy_stream and hung the step).
+    int slots_init() {
+        const size_t cm_bytes = (size_t)kappa * ELEM_BYTES, in_bytes = ((n + L - 1) / L) * ELEM_BYTES;
+        int st;
+        for (Slot &sl : slots) {
+            if ((st = sl.in.ensure(in_bytes)) || (st = sl.cm.ensure(cm_bytes)) || (st = sl.out.ensure(cm_bytes)) ||
+                (st = sl.flag.ensure(sizeof(int))) || (st = sl.ready.ensure(sizeof(unsigned long long))))
+                return st;
+            CK(cudaMemsetAsync(sl.flag.p, 0, sizeof(int), stream));
+            CK(cudaMemsetAsync(sl.ready.p, 0xff, sizeof(unsigned long long), stream));  // no ticket has this value
+            CK(cudaHostAlloc((void **)&sl.h_cm, cm_bytes, cudaHostAllocMapped));
+            CK(cudaHostAlloc((void **)&sl.h_flag, sizeof(int), cudaHostAllocMapped));
+            CK(cudaHostAlloc((void **)&sl.h_ticket, sizeof(unsigned long long), cudaHostAllocDefault));
+            CK(cudaHostAlloc((void **)&sl.h_done, sizeof(unsigned long long), cudaHostAllocMapped));
+            *sl.h_flag = 0;
+            *sl.h_done = ~0ull;
+        }
         return LAT_OK;
     }
 };
@@ -272,6 +359,15 @@ int lat_ajtai_create(lat_ajtai **out, uint32_t kappa, uint64_t n, uint32_t log2_
         if ((st = h->fx.ensure(n * lat::FX_WORDS * sizeof(u64)))) break;
         if ((st = h->cms.ensure((size_t)K * kappa * ELEM_BYTES))) break;
         if ((st = h->cm_in.ensure((size_t)kappa * ELEM_BYTES))) break;
+        // first-use allocations would stall (and implicitly synchronise) the kernel chains later: make them here
+        if ((st = h->fx_alt.ensure(n * lat::FX_WORDS * sizeof(u64)))) break;
+        {
+            const uint32_t max_planes = 2 * K > 32 ? 2 * K : 32;
+            if ((st = h->ws.ensure(lat::plan_mac(h->lay, max_planes, h->sm_count).ws_elems * sizeof(u64)))) break;
+            if ((e = cudaMemsetAsync(h->ws.p, 0, h->ws.bytes, h->stream)) != cudaSuccess) break;
+        }
+        if ((st = spin_guard(device, h->guard))) break;
+        if ((st = h->slots_init())) break;
         if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) break;
     } while (0);
     if (st == LAT_OK && e != cudaSuccess) st = fail_cuda(e, "lat_ajtai_create", __LINE__);
@@ -427,13 +523,10 @@ static int witness_core(lat_ajtai *h, const u64 *w_dev, u64 w_len, bool in_coeff
     // makes the buffer of two steps back safe to reuse).  Event brackets (profiling) serialise the launches anyway.
     u64 *fxp = h->fx.as<u64>();
     const bool chained = h->step_overlap && cm_dev && h->mac_was_last && !h->profiling;
-    if (chained && h->last_mac_src == h->fx.p) {
-        int st = h->fx_alt.ensure(h->n * lat::FX_WORDS * sizeof(u64));
-        if (st) return st;
-        fxp = h->fx_alt.as<u64>();
-    }
+    if (chained && h->last_mac_src == h->fx.p) fxp = h->fx_alt.as<u64>();
+    h->guard.timeout_ns = spin_timeout_ns();
     lat::launch_witness(w_dev, w_len, (int)h->log2_B, (int)h->L, h->mont, in_coeff, h->f16.as<int16_t>(), f_coeff_dev,
-                        f_dev, cm_dev ? fxp : nullptr, h->flag.as<int>(), h->stream, chained, ready_flag, ready_value);
+                        f_dev, cm_dev ? fxp : nullptr, h->flag.as<int>(), h->stream, chained, ready_flag, ready_value, h->guard);
     CK(cudaGetLastError());
     h->has_resident = true;
     if (cm_dev) return h->mac_fx(fxp, h->n, 1, cm_dev);
@@ -534,30 +627,13 @@ int lat_ajtai_decompose_and_commit_coeff(lat_ajtai *h, const uint64_t *w_coeff, 
     return witness_host(h, w_coeff, w_len, true, nullptr, nullptr, cm);
 }
 
-// ---- pipelined steps ------------------------------------------------------------------------------------------------
-// A prover that commits one witness per VM step (ZKVM/main.rs:348-367) knows step i+1's w_ccs before it needs step i's
-// commitment.  submit() queues upload (copy engine) -> witness kernel -> matrix-vector kernel -> result download
-// (second copy engine) on three streams chained by events and returns; wait() blocks on one ticket.  In steady state
-// the PCIe transfers of neighbouring steps hide under the kernels.
-static int slot_prepare(lat_ajtai *h, lat_ajtai::Slot &sl, size_t in_bytes) {
-    int st;
-    const size_t cm_bytes = (size_t)h->kappa * ELEM_BYTES;
-    if ((st = sl.in.ensure(in_bytes)) || (st = sl.cm.ensure(cm_bytes))) return st;
-    if (!sl.flag.p) {
-        if ((st = sl.flag.ensure(sizeof(int))) || (st = sl.ready.ensure(sizeof(unsigned long long)))) return st;
-        CK(cudaMemset(sl.flag.p, 0, sizeof(int)));
-        CK(cudaMemset(sl.ready.p, 0xff, sizeof(unsigned long long)));  // no ticket has this value
-    }
-    if (!sl.h_cm) CK(cudaHostAlloc((void **)&sl.h_cm, cm_bytes, cudaHostAllocMapped));
-    if (!sl.h_flag) CK(cudaHostAlloc((void **)&sl.h_flag, sizeof(int), cudaHostAllocMapped));
-    if (!sl.h_ticket) CK(cudaHostAlloc((void **)&sl.h_ticket, sizeof(unsigned long long), cudaHostAllocDefault));
-    if (!sl.h_done) {
-        CK(cudaHostAlloc((void **)&sl.h_done, sizeof(unsigned long long), cudaHostAllocMapped));
-        *sl.h_done = ~0ull;
-    }
-    return LAT_OK;
-}
-
+// ---- non-blocking steps -------------------------------------------------------------------------------------------------
+// submit() queues upload (copy engine) -> witness kernel -> matrix-vector kernel (-> exchange kernel when sharded) and
+// returns; the last kernel writes the commitment and then the ticket into mapped host memory, wait() polls that word.
+// The compute stream carries nothing but kernels, so several tickets overlap on the device.  This is for work that is
+// independent of the commitment (the host's own work of the same step, independent provers): the IVC steps of one
+// zkVM run are strictly dependent -- step i+1's z is built from fold(cm_i, w_i) (ZKVM/main.rs:140-156,174-182) -- so a
+// drop-in caller gets one ticket's latency per step, not the overlapped throughput.
 static int device_view(void *host, void **dev) {
     CK(cudaHostGetDevicePointer(dev, host, 0));
     return LAT_OK;
@@ -571,9 +647,9 @@ int lat_ajtai_submit_w_ccs(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_len, 
     lat_ajtai::Slot &sl = h->slots[h->next_ticket % LAT_PIPELINE_DEPTH];
     if (sl.busy)
         return fail(LAT_E_INVALID_ARGUMENT, "pipeline full: lat_ajtai_wait(ticket " + std::to_string(sl.ticket) + ") first");
-    const size_t in_bytes = w_len * ELEM_BYTES;
-    if ((st = slot_prepare(h, sl, in_bytes))) return st;
+    const size_t in_bytes = w_len * ELEM_BYTES;  // fits: the slot was sized for ceil(n / L) elements at creation
     const unsigned long long tk = h->next_ticket;
+    h->guard.timeout_ns = spin_timeout_ns();
     // Upload on the copy stream, followed by a copy of the ticket: the witness kernel polls that word instead of the
     // compute stream waiting for an event, so the compute stream is a pure chain of kernels -- witness, matrix-vector,
     // witness, ... -- that overlap through programmatic dependent launches (see witness_kernel / mac_kernel).
@@ -583,12 +659,9 @@ int lat_ajtai_submit_w_ccs(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_len, 
     // this step's kernel may start under the previous step's draining matrix-vector kernel: other witness buffer
     u64 *fxp = h->fx.as<u64>();
     const bool chained = h->mac_was_last && !h->profiling;
-    if (chained && h->last_mac_src == h->fx.p) {
-        if ((st = h->fx_alt.ensure(h->n * lat::FX_WORDS * sizeof(u64)))) return st;
-        fxp = h->fx_alt.as<u64>();
-    }
+    if (chained && h->last_mac_src == h->fx.p) fxp = h->fx_alt.as<u64>();
     lat::launch_witness(sl.in.as<u64>(), w_len, (int)h->log2_B, (int)h->L, h->mont, false, h->f16.as<int16_t>(), nullptr, nullptr,
-                        fxp, sl.flag.as<int>(), h->stream, chained, sl.ready.as<unsigned long long>(), tk);
+                        fxp, sl.flag.as<int>(), h->stream, chained, sl.ready.as<unsigned long long>(), tk, h->guard);
     CK(cudaGetLastError());
     h->has_resident = true;
     // the matrix-vector kernel reports straight into mapped host memory: commitment, overflow flag, then the ticket
@@ -607,10 +680,9 @@ int lat_ajtai_submit_w_ccs(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_len, 
         // same kernel chain) sums the partial commitments of all ranks and reports the full one
         u64 *cm_map = rep.cm_host;
         rep.cm_host = nullptr;
-        if ((st = sl.out.ensure((size_t)h->kappa * ELEM_BYTES))) return st;
         if ((st = h->mac_fx(fxp, h->n, 1, sl.cm.as<u64>(), rep))) return st;
         lat::launch_exchange(sl.cm.as<u64>(), (u64)h->kappa * LAT_RING_DEGREE, h->peer_rank, h->peer_world, h->peers,
-                             h->peer_epoch++, sl.out.as<u64>(), h->stream, cm_map, done_dev, tk);
+                             h->peer_epoch++, sl.out.as<u64>(), h->stream, cm_map, done_dev, tk, h->guard);
         CK(cudaGetLastError());
     }
     sl.busy = true;
@@ -657,6 +729,7 @@ int lat_ajtai_wait(lat_ajtai *h, uint64_t ticket) {
         }
     }
     std::atomic_thread_fence(std::memory_order_acquire);
+    if (int st = spin_status(h->device)) return st;  // a bounded device-side wait gave up: no result to hand out
     memcpy(sl.user_cm, sl.h_cm, (size_t)h->kappa * ELEM_BYTES);
     if (*sl.h_flag)
         return fail(LAT_E_DIGIT_OVERFLOW, "a coefficient needs more digits than the decomposition padding allows");
@@ -683,9 +756,11 @@ static int planes_core(lat_ajtai *h, const u64 *cm_dev, u64 *planes_coeff_dev, u
             st = h->mac_fx(pfx + h->n * lat::FX_WORDS, h->n, h->K - 1, cms_dev + (size_t)h->kappa * LAT_RING_DEGREE);
             if (st) return st;
         }
-        lat::launch_y0(cm_dev, cms_dev, h->K, h->kappa, h->stream);
-        CK(cudaGetLastError());
-        h->last_op_was_mac = false;
+        if (cm_dev) {  // column-sharded callers derive y_0 after the exchange (lat_commitment_y0_dev)
+            lat::launch_y0(cm_dev, cms_dev, h->K, h->kappa, h->stream);
+            CK(cudaGetLastError());
+            h->last_op_was_mac = false;
+        }
     }
     return LAT_OK;
 }
@@ -693,7 +768,6 @@ static int planes_core(lat_ajtai *h, const u64 *cm_dev, u64 *planes_coeff_dev, u
 int lat_ajtai_decompose_commit_dev(lat_ajtai *h, const uint64_t *f_coeff_dev, uint64_t n, const uint64_t *cm_dev,
                                    uint64_t *planes_coeff_dev, uint64_t *planes_f_dev, uint64_t *cms_dev) {
     if (!h || !f_coeff_dev) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
-    if (cms_dev && !cm_dev) return fail(LAT_E_INVALID_ARGUMENT, "cm is required to derive cms[0]");
     if (n != h->n) return h->wrong_len(n);
     int st = h->bind();
     if (st) return st;
@@ -956,6 +1030,14 @@ int lat_ajtai_mac_profile(lat_ajtai *h, double *sum_ms, uint64_t *launches) {
     return LAT_OK;
 }
 
+int lat_commitment_y0_dev(const uint64_t *cm_dev, uint64_t *cms_dev, uint32_t K, uint32_t kappa, void *cuda_stream) {
+    if (!cm_dev || !cms_dev) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (K < 1 || kappa < 1) return fail(LAT_E_INVALID_ARGUMENT, "need K >= 1, kappa >= 1");
+    lat::launch_y0((const u64 *)cm_dev, (u64 *)cms_dev, K, kappa, (cudaStream_t)cuda_stream);
+    CK(cudaGetLastError());
+    return LAT_OK;
+}
+
 int lat_commitment_sum_dev(const uint64_t *parts_dev, uint32_t count, uint64_t words, uint64_t *out_dev,
                            void *cuda_stream) {
     if (words && (!parts_dev || !out_dev)) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
@@ -979,8 +1061,12 @@ int lat_commitment_exchange_report_dev(const uint64_t *partial_dev, uint64_t wor
     unsigned long long *done_map = nullptr;
     if (cm_host) CK(cudaHostGetDevicePointer((void **)&cm_map, cm_host, 0));
     if (done_host) CK(cudaHostGetDevicePointer((void **)&done_map, done_host, 0));
+    lat::SpinGuard guard;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (int st = spin_guard(dev, guard)) return st;
     lat::launch_exchange((const u64 *)partial_dev, words, rank, world, peers, epoch, (u64 *)out_dev, (cudaStream_t)cuda_stream,
-                         cm_map, done_map, done_value);
+                         cm_map, done_map, done_value, guard);
     CK(cudaGetLastError());
     return LAT_OK;
 }
@@ -1011,6 +1097,15 @@ int lat_commitment_sum(const uint64_t *parts, uint32_t count, uint64_t words, ui
     din.release(); dout.release();
     if (e != cudaSuccess) return fail_cuda(e, "lat_commitment_sum", __LINE__);
     return LAT_OK;
+}
+
+int lat_set_spin_timeout_ms(uint64_t ms) {
+    g_spin_timeout_ns.store(ms >= (~0ull - 1) / 1000000ull ? 0ull : ms * 1000000ull, std::memory_order_relaxed);
+    return LAT_OK;
+}
+int lat_device_wait_status(int device, uint64_t *code) {
+    if (device < 0 || device >= MAX_DEVICES) return fail(LAT_E_INVALID_ARGUMENT, "device ordinal out of range");
+    return spin_status(device, code);
 }
 
 int lat_host_alloc(void **ptr, size_t bytes) {

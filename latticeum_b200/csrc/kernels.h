@@ -8,6 +8,17 @@ namespace lat {
 
 typedef unsigned long long u64;
 
+// Every in-kernel wait for something another engine or another GPU delivers (the upload ticket of a pipelined step,
+// the peers' flags of an exchange) is bounded by %globaltimer: after `timeout_ns` the waiter stores
+// code | detail << 8 into *status (a page-locked word mapped into the device, read by the host in lat_ajtai_wait /
+// lat_ajtai_synchronize / lat_device_wait_status) and carries on, so that a protocol slip ends in LAT_E_CUDA with a
+// message instead of a hung GPU.  timeout_ns = 0 waits for ever; status may be null.
+struct SpinGuard {
+    unsigned long long *status = nullptr;
+    unsigned long long timeout_ns = 0;
+};
+constexpr unsigned long long SPIN_UPLOAD_TICKET = 1, SPIN_PEER_FLAG = 2;
+
 // ---- ring_kernels.cu ------------------------------------------------------------------------------------
 // Batched CRT / iCRT of `count` ring elements of 24 u64 (in-place allowed).
 void launch_crt(const u64 *in, u64 *out, u64 count, cudaStream_t stream);
@@ -22,7 +33,8 @@ void launch_icrt(const u64 *in, u64 *out, u64 count, cudaStream_t stream);
 //   flag     : device int, OR-ed with 1 when a coefficient does not fit in L digits
 void launch_witness(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool in_coeff, int16_t *f16, u64 *f_coeff,
                     u64 *f_plain, u64 *fx, int *flag, cudaStream_t stream, bool overlap_previous = false,
-                    const unsigned long long *ready_flag = nullptr, unsigned long long ready_value = 0);
+                    const unsigned long long *ready_flag = nullptr, unsigned long long ready_value = 0,
+                    const SpinGuard &guard = SpinGuard());
 
 // int16 coefficients -> K base-2 digit planes: plane k of element j = sign * bit_k(|c|).
 //   planes_f     : K x n x 24 CRT form, or nullptr
@@ -111,7 +123,8 @@ struct PeerPtrs {
 };
 void launch_exchange(const u64 *partial, u64 words, int rank, int world, const PeerPtrs &peers, u64 epoch, u64 *out,
                      cudaStream_t stream, u64 *report_cm = nullptr,
-                     unsigned long long *report_done = nullptr, unsigned long long done_value = 0);
+                     unsigned long long *report_done = nullptr, unsigned long long done_value = 0,
+                     const SpinGuard &guard = SpinGuard());
 
 // Standalone negacyclic NTT over Z_q[X]/(X^d + 1), d = 2^logd (ntt_pow2.cu; not on the drop-in path).  Returns 0 or a
 // cudaError_t as int.

@@ -31,6 +31,7 @@
 
 #include "kernels.h"
 #include "ring24.cuh"
+#include "spin.cuh"
 
 namespace lat {
 using gl::u32;
@@ -623,7 +624,7 @@ void launch_recompose(const u64 *f, u64 count, int log2b, int L, u64 *out, cudaS
 __global__ void __launch_bounds__(256)
 exchange_kernel(const u64 *__restrict__ partial, u64 words, int rank, int world, PeerPtrs peers, u64 epoch,
                 u64 *__restrict__ out, u64 *__restrict__ report_cm, unsigned long long *report_done,
-                unsigned long long done_value) {
+                unsigned long long done_value, SpinGuard guard) {
     // Programmatic dependent launch on both sides: this block may become resident while the matrix-vector kernel that
     // produces `partial` is still running (it waits for it here), and the NEXT step's witness kernel may start behind
     // it at once -- so the whole exchange, NVLink latency included, hides under that kernel (lat_ajtai_set_step_overlap).
@@ -639,11 +640,9 @@ exchange_kernel(const u64 *__restrict__ partial, u64 words, int rank, int world,
     if ((int)threadIdx.x < world) {
         u64 *f = peers.flags[threadIdx.x] + slot * world + rank;
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+        // bounded (SpinGuard): a peer that never delivers ends in LAT_E_CUDA on the host, not in a hung GPU
         const u64 *mine = peers.flags[rank] + slot * world + threadIdx.x;
-        u64 v;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
-        } while (v != epoch);
+        spin_until_equals(mine, epoch, guard, SPIN_PEER_FLAG, (u64)threadIdx.x | (epoch << 8));
     }
     __syncthreads();
     __threadfence_system();
@@ -666,7 +665,8 @@ exchange_kernel(const u64 *__restrict__ partial, u64 words, int rank, int world,
     }
 }
 void launch_exchange(const u64 *partial, u64 words, int rank, int world, const PeerPtrs &peers, u64 epoch, u64 *out,
-                     cudaStream_t stream, u64 *report_cm, unsigned long long *report_done, unsigned long long done_value) {
+                     cudaStream_t stream, u64 *report_cm, unsigned long long *report_done, unsigned long long done_value,
+                     const SpinGuard &guard) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(1);
     cfg.blockDim = dim3(256);
@@ -676,7 +676,7 @@ void launch_exchange(const u64 *partial, u64 words, int rank, int world, const P
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, exchange_kernel, partial, words, rank, world, peers, epoch, out, report_cm, report_done, done_value);
+    cudaLaunchKernelEx(&cfg, exchange_kernel, partial, words, rank, world, peers, epoch, out, report_cm, report_done, done_value, guard);
 }
 
 // Sum of `count` partial commitments mod q (column-sharded multi-GPU exchange).

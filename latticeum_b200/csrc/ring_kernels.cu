@@ -18,6 +18,7 @@
 #include "kernels.h"
 #include "ring24.cuh"
 #include "ring8.cuh"
+#include "spin.cuh"
 
 namespace lat {
 using gl::u32;
@@ -250,17 +251,13 @@ template <bool MONT>
 __global__ void __launch_bounds__(THREADS, 4)
 witness_kernel(const u64 *__restrict__ w, u64 w_len, int log2b, int L, bool in_coeff, int16_t *__restrict__ f16,
                u64 *__restrict__ f_coeff, u64 *__restrict__ f_plain, u64 *__restrict__ fx, int *__restrict__ flag, int chained,
-               const unsigned long long *__restrict__ ready_flag, unsigned long long ready_value) {
+               const unsigned long long *__restrict__ ready_flag, unsigned long long ready_value, SpinGuard guard) {
     asm volatile("griddepcontrol.launch_dependents;");
     if (ready_flag) {
         // pipelined host-buffer steps: the input is uploaded by a copy engine on another stream, followed by a copy of
-        // the step's ticket into *ready_flag; waiting for it here keeps event waits out of the kernel chain
-        if (threadIdx.x == 0) {
-            unsigned long long v;
-            do {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(ready_flag) : "memory");
-            } while (v != ready_value);
-        }
+        // the step's ticket into *ready_flag; waiting for it here keeps event waits out of the kernel chain.  The
+        // wait is bounded (SpinGuard): on expiry the host gets LAT_E_CUDA from lat_ajtai_wait, not a hung GPU.
+        if (threadIdx.x == 0) spin_until_equals(ready_flag, ready_value, guard, SPIN_UPLOAD_TICKET, ready_value);
         __syncthreads();
     }
     witness_body<MONT>(w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag);
@@ -269,7 +266,7 @@ witness_kernel(const u64 *__restrict__ w, u64 w_len, int log2b, int L, bool in_c
 
 void launch_witness(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool in_coeff, int16_t *f16, u64 *f_coeff,
                     u64 *f_plain, u64 *fx, int *flag, cudaStream_t stream, bool overlap_previous,
-                    const unsigned long long *ready_flag, unsigned long long ready_value) {
+                    const unsigned long long *ready_flag, unsigned long long ready_value, const SpinGuard &guard) {
     if (!w_len) return;
     unsigned grid = (unsigned)((w_len + OPB - 1) / OPB);
     size_t smem = (f_plain || fx) ? (size_t)OPB * L * (FX_UNITS + 1) * 16 : 0;  // 32 KB at L = 5
@@ -288,8 +285,8 @@ void launch_witness(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool i
     cfg.attrs = attr;
     cfg.numAttrs = overlap_previous ? 1 : 0;
     const int chained = overlap_previous ? 1 : 0;
-    if (mont) cudaLaunchKernelEx(&cfg, witness_kernel<true>, w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag, chained, ready_flag, ready_value);
-    else cudaLaunchKernelEx(&cfg, witness_kernel<false>, w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag, chained, ready_flag, ready_value);
+    if (mont) cudaLaunchKernelEx(&cfg, witness_kernel<true>, w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag, chained, ready_flag, ready_value, guard);
+    else cudaLaunchKernelEx(&cfg, witness_kernel<false>, w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag, chained, ready_flag, ready_value, guard);
 }
 
 // ---- int16 coefficients -> K sign*bit planes, each CRT'd ---------------------------------------------------

@@ -23,7 +23,7 @@ class DeviceScheme:
             raise RuntimeError("latticeum_b200 needs a CUDA device; there is no CPU fallback")
         self.scheme = scheme
         self.device = torch.device("cuda", scheme.device)
-        self.kappa, self.n, self.L = scheme._kappa, scheme._n, scheme.params.L
+        self.kappa, self.n, self.L, self.K = scheme._kappa, scheme._n, scheme.params.L, scheme.params.K
         self._bound_stream = None
         self.bind_stream()
 
@@ -83,14 +83,39 @@ class DeviceScheme:
             _raise(st, f.shape[0], self.n)
         return cm
 
-    def decompose_commit(self, f_coeff: torch.Tensor, cm: torch.Tensor, cms: torch.Tensor,
-                         planes_f: torch.Tensor = None) -> torch.Tensor:
+    def decompose_commit(self, f_coeff: torch.Tensor, cm, cms: torch.Tensor, planes_f: torch.Tensor = None,
+                         side: int = None) -> torch.Tensor:
+        """decompose_witness + commit_witnesses (latticefold/src/nifs/decomposition.rs:162-201) on device tensors.
+        cms: (K, kappa, 24); cms[1:] = A * plane_k, cms[0] = y_0 by homomorphism from `cm` -- or left untouched when
+        cm is None (column-sharded callers finish with `y0` after exchanging cms[1:]).  `side` (0 / 1) selects which
+        resident plane buffer the call fills for `fold_witness`."""
         self.bind_stream()
+        if side is not None:
+            _raise(capi.lib().lat_ajtai_select_side(self.scheme._h, side))
         st = capi.lib().lat_ajtai_decompose_commit_dev(
-            self.scheme._h, self._check(f_coeff, "f_coeff"), f_coeff.shape[0], self._check(cm, "cm"), None,
-            self._check(planes_f, "planes_f") if planes_f is not None else None, self._check(cms, "cms"))
+            self.scheme._h, self._check(f_coeff, "f_coeff"), f_coeff.shape[0], self._check(cm, "cm") if cm is not None else None,
+            None, self._check(planes_f, "planes_f") if planes_f is not None else None, self._check(cms, "cms"))
         _raise(st, f_coeff.shape[0], self.n)
         return cms
+
+    def y0(self, cm: torch.Tensor, cms: torch.Tensor) -> torch.Tensor:
+        """cms[0] = cm - sum_{k>=1} 2^k cms[k]  (decomposition.rs:189-197), in place on device."""
+        s = torch.cuda.current_stream(self.device).cuda_stream or 1
+        _raise(capi.lib().lat_commitment_y0_dev(self._check(cm, "cm"), self._check(cms, "cms"), cms.shape[0], self.kappa,
+                                                C.c_void_p(s)))
+        return cms
+
+    def fold_witness(self, rho: torch.Tensor, f0: torch.Tensor = None, f0_coeff: torch.Tensor = None):
+        """compute_f_0 over the 2K planes left resident by the two decompose_commit calls + Witness::from_f's iCRT
+        (latticefold/src/nifs/folding.rs:258-268, arith.rs:299-313).  Returns (f0, f0_coeff) device tensors."""
+        self.bind_stream()
+        if f0 is None:
+            f0 = torch.empty((self.n, D), dtype=torch.int64, device=self.device)
+        if f0_coeff is None:
+            f0_coeff = torch.empty((self.n, D), dtype=torch.int64, device=self.device)
+        _raise(capi.lib().lat_ajtai_fold_witness_dev(self.scheme._h, self._check(rho, "rho"), self._check(f0, "f0"),
+                                                     self._check(f0_coeff, "f0_coeff")))
+        return f0, f0_coeff
 
     def fold_partials(self, parts: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
         """Sum of partial commitments mod q (parts: (world, ...), out: (...))."""

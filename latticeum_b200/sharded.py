@@ -29,28 +29,61 @@ def shard_bounds(total: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def _all_agree(ok: bool, device: torch.device, group) -> bool:
+    """True iff `ok` on EVERY rank (all-reduce MIN).  Every rank must call this the same number of times."""
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(t.item()) == 1)
+
+
 class PeerExchange:
     """NVLink peer-memory state for the fused exchange + fold kernel (lat_commitment_exchange_dev): a receive buffer
     of 2 x world x max_words u64 and 2 x world flags per rank, allocated as torch symmetric memory so that every
-    rank holds addresses of every peer's buffers.  One kernel per rank per exchange, no NCCL call on the data path."""
+    rank holds addresses of every peer's buffers.  One kernel per rank per exchange, no NCCL call on the data path.
 
-    def __init__(self, device: torch.device, world: int, rank: int, max_words: int, group=None):
-        import torch.distributed._symmetric_memory as symm_mem
+    Construction is collective.  Use `PeerExchange.create`, which makes the decision "peer memory works" COLLECTIVELY:
+    a rank on which a step fails still takes part in every all-reduce, so either all ranks get an exchange or all get
+    None -- never a mix of ranks spinning in the peer kernel and ranks calling NCCL."""
 
-        group = group if group is not None else dist.group.WORLD
+    def __init__(self, device: torch.device, world: int, rank: int, max_words: int, recv, flags, handles):
         self.world, self.rank, self.max_words = world, rank, max_words
-        self.recv = symm_mem.empty(2 * world * max_words, dtype=torch.int64, device=device)
-        self.flags = symm_mem.empty(2 * world, dtype=torch.int64, device=device)
-        self.recv.zero_()
-        self.flags.zero_()
-        h_recv = symm_mem.rendezvous(self.recv, group)
-        h_flags = symm_mem.rendezvous(self.flags, group)
-        self.recv_ptrs = [int(p) for p in h_recv.buffer_ptrs]
-        self.flag_ptrs = [int(p) for p in h_flags.buffer_ptrs]
-        self._handles = (h_recv, h_flags)
+        self.recv, self.flags = recv, flags
+        self.recv_ptrs = [int(p) for p in handles[0].buffer_ptrs]
+        self.flag_ptrs = [int(p) for p in handles[1].buffer_ptrs]
+        self._handles = handles
         self.epoch = 0
-        torch.cuda.synchronize(device)
-        dist.barrier(group=group)  # every rank's flags are zero before anyone raises one
+
+    @classmethod
+    def create(cls, device: torch.device, world: int, rank: int, max_words: int, group=None):
+        """(exchange or None, reason).  Phase 1 (local, no collective inside): import, peer access, allocation.
+        Agreement.  Phase 2 (collective rendezvous; it fails or succeeds on all ranks alike, but is checked anyway).
+        Agreement, which doubles as the barrier that orders "every rank's flags are zero" before the first exchange."""
+        group = group if group is not None else dist.group.WORLD
+        recv = flags = symm_mem = None
+        why = ""
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            for peer in range(torch.cuda.device_count()):
+                if peer != device.index and not torch.cuda.can_device_access_peer(device.index, peer):
+                    raise RuntimeError(f"no peer access {device.index} -> {peer}")
+            recv = symm_mem.empty(2 * world * max_words, dtype=torch.int64, device=device)
+            flags = symm_mem.empty(2 * world, dtype=torch.int64, device=device)
+            recv.zero_()
+            flags.zero_()
+        except Exception as e:  # pragma: no cover - depends on the box
+            why = f"{type(e).__name__}: {e}"
+        if not _all_agree(not why, device, group):
+            return None, why or "a peer rank cannot set up peer memory"
+        handles = None
+        try:
+            handles = (symm_mem.rendezvous(recv, group), symm_mem.rendezvous(flags, group))
+            torch.cuda.synchronize(device)
+        except Exception as e:  # pragma: no cover
+            why = f"{type(e).__name__}: {e}"
+        if not _all_agree(not why, device, group):
+            return None, why or "rendezvous failed on a peer rank"
+        return cls(device, world, rank, max_words, recv, flags, handles), ""
 
 
 class ShardedAjtaiScheme:
@@ -75,14 +108,15 @@ class ShardedAjtaiScheme:
         self.peer: Optional[PeerExchange] = None
         self.exchange = "none" if world == 1 else "nccl"
         if world > 1 and exchange in ("p2p", "auto") and hasattr(engine, "exchange_partials"):
-            try:
-                self.peer = PeerExchange(engine.device, world, rank, max_batch * engine.kappa * 24, group)
+            # the same decision on every rank (see PeerExchange.create): a per-rank fallback would leave some ranks
+            # spinning in the peer kernel while others sit in an NCCL all-gather
+            self.peer, why = PeerExchange.create(engine.device, world, rank, max_batch * engine.kappa * 24, group)
+            if self.peer is not None:
                 self.exchange = "p2p"
-            except Exception as e:  # pragma: no cover - depends on the box
-                if exchange == "p2p":
-                    raise
-                self.peer = None
-                self.exchange = f"nccl (p2p unavailable: {type(e).__name__})"
+            elif exchange == "p2p":
+                raise RuntimeError(f"peer-memory exchange unavailable: {why}")
+            else:
+                self.exchange = f"nccl (p2p unavailable: {why.split(':')[0]})"
 
     def _exchange(self, partial: torch.Tensor) -> torch.Tensor:
         if self.world == 1:
@@ -109,6 +143,30 @@ class ShardedAjtaiScheme:
             partial = self.engine.new_commitment(f_local.shape[0] if f_local.dim() == 3 else 1)
         self.engine.commit_ntt(f_local, partial)
         return self._exchange(partial)
+
+
+    # -- the fold step, column-sharded ("the partition applies to the decompose-and-commit entry points too") --
+    def decompose_commit(self, f_coeff_local: torch.Tensor, cm_full: torch.Tensor, side: int = 0,
+                         cms: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """decompose_witness + commit_witnesses (latticefold/src/nifs/decomposition.rs:162-201) on this rank's block of
+        f_coeff: the K planes of the block stay resident on this rank (for `fold_witness`), the K-1 partial commitments
+        of planes 1..K-1 are exchanged in ONE go ((K-1) x kappa x 24 words) and y_0 = cm - sum 2^k y_k is derived from
+        the exchanged totals and the FULL commitment `cm_full`.  Returns (K, kappa, 24) on every rank."""
+        eng = self.engine
+        K = eng.K
+        if cms is None:
+            cms = eng.new_commitment(K)
+        eng.decompose_commit(f_coeff_local, None if self.world > 1 else cm_full, cms, side=side)
+        if self.world == 1:
+            return cms
+        if K > 1:
+            cms[1:].copy_(self._exchange(cms[1:]))
+        return eng.y0(cm_full, cms)
+
+    def fold_witness(self, rho: torch.Tensor):
+        """compute_f_0 + iCRT on this rank's columns: per element, so no exchange (folding.rs:258-268, arith.rs:299-313).
+        Returns this rank's blocks (f0_local, f0_coeff_local)."""
+        return self.engine.fold_witness(rho)
 
 
 class ShardedCommitPipeline:

@@ -557,8 +557,7 @@ def test_gadget_recompose_vs_oracle():
 
 def test_commitment_sum_and_single_rank_exchange():
     # lat_commitment_sum (SURVEY 8e fold of column-shard partials) and the fused exchange kernel with world = 1
-    # (multi-rank runs need real peers: tools/mgpu_check.py under torchrun; a spinning multi-rank emulation on one
-    # GPU is not safe)
+    # (multi-rank runs need real peers: tests/test_multigpu.py under torchrun)
     import ctypes as C
 
     import torch
@@ -621,6 +620,86 @@ def test_gated_witness_call_waits_for_the_ticket():
     torch.cuda.synchronize()
     _, f = CO.witness_from_w_ccs(w, DP.B, DP.L)
     assert np.array_equal(cm.cpu().numpy().view(np.uint64), CO.commit(A, f))
+    scheme.close()
+
+
+def test_device_side_waits_are_bounded():
+    # Every in-kernel wait has a %globaltimer deadline (lat::SpinGuard): a peer that never delivers, or an upload ticket
+    # that never lands, ends in LAT_E_CUDA with a message -- not in a hung GPU.
+    import ctypes as C
+
+    import torch
+    from latticeum_b200.device import DeviceScheme
+
+    L = capi.lib()
+    code = C.c_uint64(0)
+    assert L.lat_device_wait_status(0, C.byref(code)) == 0 and code.value == 0
+    assert L.lat_set_spin_timeout_ms(50) == 0
+    try:
+        # (1) a 2-rank exchange in which rank 1 never shows up
+        words = 32 * 24
+        partial = torch.from_numpy(CO.fill_uniform((words,), 124).view(np.int64)).cuda()
+        recv = torch.zeros(2 * 2 * words, dtype=torch.int64, device="cuda")
+        flags = torch.zeros(2 * 2, dtype=torch.int64, device="cuda")
+        res = torch.empty(words, dtype=torch.int64, device="cuda")
+        rp = (C.c_uint64 * 2)(recv.data_ptr(), recv.data_ptr())  # "peer" mailboxes alias the local one: nobody raises flag 1
+        fp = (C.c_uint64 * 2)(flags.data_ptr(), flags.data_ptr())
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream or 1)
+        assert L.lat_commitment_exchange_dev(partial.data_ptr(), words, 0, 2, rp, fp, 1, res.data_ptr(), stream) == 0
+        torch.cuda.synchronize()  # returns: the wait gave up after ~50 ms
+        assert L.lat_device_wait_status(0, C.byref(code)) == capi.LAT_E_CUDA
+        assert code.value & 0xFF == 2 and (code.value >> 8) & 0xFF == 1, hex(code.value)  # peer flag, rank 1
+        assert "peer rank 1" in capi.last_error()
+        assert L.lat_device_wait_status(0, C.byref(code)) == 0 and code.value == 0  # cleared
+        # (2) a gated witness call whose ticket never arrives: the handle's synchronize reports it
+        kappa, wl = 4, 64
+        A = CO.fill_uniform((kappa, wl * DP.L, 24), 140)
+        scheme = make_scheme(A)
+        eng = DeviceScheme(scheme)
+        w_dev = torch.zeros((wl, 24), dtype=torch.int64, device="cuda")
+        ready = torch.full((1,), -1, dtype=torch.int64, device="cuda")
+        eng.witness_commit_gated(w_dev, eng.new_commitment(), ready, 7)
+        with pytest.raises(S.EngineError, match="upload ticket 7"):
+            eng.synchronize()
+        eng.synchronize()  # cleared, and the handle is still usable
+        w = CO.fill_uniform((wl, 24), 141)
+        cm = eng.witness_commit(eng.to_device(w), eng.new_commitment())
+        eng.synchronize()
+        assert np.array_equal(DeviceScheme.to_numpy(cm), CO.commit(A, CO.witness_from_w_ccs(w, DP.B, DP.L)[1]))
+        scheme.close()
+    finally:
+        L.lat_set_spin_timeout_ms(5000)
+
+
+def test_submit_on_the_legacy_stream_behind_a_busy_stream():
+    # Regression for the round-1 N=4 hang: the first submits of a handle bound to the LEGACY stream, issued while
+    # that stream is still busy.  Slot state used to be memset on first use on the legacy stream (queued behind the
+    # busy work) while the ticket copy ran ahead on the copy stream; the late memset then wiped the ticket and the
+    # gated kernel spun for ever.  All slot state is now initialised at creation.
+    import ctypes as C
+
+    import torch
+
+    kappa, wl = 8, 300
+    A = CO.fill_uniform((kappa, wl * DP.L, 24), 150)
+    w = CO.fill_uniform((wl, 24), 151)
+    scheme = make_scheme(A)
+    L = capi.lib()
+    assert L.lat_ajtai_set_stream(scheme._h, C.c_void_p(1)) == 0  # cudaStreamLegacy
+    w_pin = S.pinned_empty((wl, 24))
+    w_pin[:] = w
+    cms = [np.zeros((kappa, 24), np.uint64) for _ in range(capi.LAT_PIPELINE_DEPTH)]
+    torch.cuda.synchronize()
+    torch.cuda._sleep(40_000_000)  # ~20 ms of work on the legacy stream (torch's default stream)
+    tks = []
+    for cm in cms:
+        tk = C.c_uint64()
+        assert L.lat_ajtai_submit_w_ccs(scheme._h, w_pin.ctypes.data, wl, cm.ctypes.data, C.byref(tk)) == 0, capi.last_error()
+        tks.append(tk.value)
+    exp = CO.commit(A, CO.witness_from_w_ccs(w, DP.B, DP.L)[1])
+    for tk, cm in zip(tks, cms):
+        assert L.lat_ajtai_wait(scheme._h, tk) == 0, capi.last_error()
+        assert np.array_equal(cm, exp)
     scheme.close()
 
 

@@ -61,6 +61,33 @@ class OracleEngine:
             cm.copy_(to_t(CO.commit(self.A, f)))
         return cm
 
+    K = 15
+
+    def decompose_commit(self, f_coeff_local, cm, cms, side=None):
+        # the local K-1 matrix commits of this column block; y_0 only when the caller hands over a commitment
+        fc = to_np(f_coeff_local)
+        cm_np = to_np(cm) if cm is not None else np.zeros((self.kappa, 24), np.uint64)
+        _, pf, out = CO.decompose_commit(self.A, fc, cm_np, 2, self.K, want_planes=True)
+        self.planes = getattr(self, "planes", {})
+        self.planes[side or 0] = pf
+        if cm is None:
+            cms[1:].copy_(to_t(out[1:]))
+        else:
+            cms.copy_(to_t(out))
+        return cms
+
+    def y0(self, cm, cms):
+        acc = np.zeros((self.kappa, 24), dtype=object)
+        c = to_np(cms).astype(object)
+        for k in range(self.K - 1, 0, -1):  # decomposition.rs:189-197: fold_rev((acc + y_k) * b), b = 2
+            acc = (acc + c[k]) * 2 % Q
+        cms[0].copy_(to_t(((to_np(cm).astype(object) - acc) % Q).astype(np.uint64)))
+        return cms
+
+    def fold_witness(self, rho):
+        f0 = CO.compute_f0(to_np(rho), [self.planes[s][k] for s in (0, 1) for k in range(self.K)])
+        return to_t(f0), to_t(CO.icrt(f0))
+
     def fold_partials(self, parts, out):
         p = to_np(parts).astype(object)
         out.copy_(to_t((p.sum(axis=0) % Q).astype(np.uint64)))
@@ -92,7 +119,19 @@ def _worker(rank, world, port, results):
         outs.append(to_np(pipe.wait(t1)).copy())
         outs.append(to_np(pipe.wait(t2)).copy())
         assert np.array_equal(outs[0], to_np(cm)) and np.array_equal(outs[1], to_np(cm)) and np.array_equal(outs[2], to_np(cm))
-        results[rank] = (to_np(cm).copy(), to_np(cms).copy())
+        # the fold step, column-sharded: K-1 partial commitments per side exchanged at once, y_0 from the totals
+        n = W_TOTAL * L
+        rng = np.random.Generator(np.random.PCG64(5))
+        fold = {}
+        for side in (0, 1):
+            small = rng.integers(-(1 << 14), (1 << 14) + 1, size=(n, 24), dtype=np.int64)
+            fc = np.where(small < 0, small.view(np.uint64) + np.uint64(Q), small.view(np.uint64))  # wraps to small + q
+            cm_full = CO.commit(A, CO.crt(fc))
+            ys = sh.decompose_commit(to_t(np.ascontiguousarray(fc[lo * L : hi * L])), to_t(cm_full), side=side)
+            fold[side] = to_np(ys).copy()
+        rho = CO.fill_uniform((30, 24), 6)
+        f0_local, f0c_local = sh.fold_witness(to_t(rho))
+        results[rank] = (to_np(cm).copy(), to_np(cms).copy(), fold, to_np(f0_local).copy(), to_np(f0c_local).copy())
     finally:
         dist.destroy_process_group()
 
@@ -110,10 +149,23 @@ def test_sharded_commit_equals_unsharded(world):
     _, f = CO.witness_from_w_ccs(w, B, L)
     exp = CO.commit(A, f)
     exp2 = CO.commit(A, CO.fill_uniform((W_TOTAL * L, 24), 3))
+    n = W_TOTAL * L
+    rng = np.random.Generator(np.random.PCG64(5))
+    exp_fold, planes = {}, []
+    for side in (0, 1):
+        small = rng.integers(-(1 << 14), (1 << 14) + 1, size=(n, 24), dtype=np.int64)
+        fc = np.where(small < 0, small.view(np.uint64) + np.uint64(Q), small.view(np.uint64))  # wraps to small + q
+        _, pf, ys = CO.decompose_commit(A, fc, CO.commit(A, CO.crt(fc)), 2, 15, want_planes=True)
+        exp_fold[side] = ys
+        planes += [pf[k] for k in range(15)]
+    f0 = CO.compute_f0(CO.fill_uniform((30, 24), 6), planes)
     for r in range(world):
-        cm, cms = results[r]
+        cm, cms, fold, f0_local, f0c_local = results[r]
         assert np.array_equal(cm, exp), f"rank {r}"
         assert np.array_equal(cms[0], exp) and np.array_equal(cms[1], exp2), f"rank {r}"
+        assert np.array_equal(fold[0], exp_fold[0]) and np.array_equal(fold[1], exp_fold[1]), f"rank {r}: sharded decompose_commit"
+        lo, hi = shard_bounds(W_TOTAL, world, r)
+        assert np.array_equal(f0_local, f0[lo * L : hi * L]) and np.array_equal(f0c_local, CO.icrt(f0[lo * L : hi * L]))
 
 
 def test_single_rank_needs_no_process_group():
