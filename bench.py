@@ -538,14 +538,99 @@ def run_single(args, ctx):
 
 
 def fold_step_leg(args, ctx, LB, scheme, eng, mont, w_canon):
-    """Filled in by the fold-step entry points (lat_ajtai_fold_step_*); absent until the library exports them."""
+    """The whole GPU side of one IVC step's fold (zk_latticefold.rs:37-102) through the host-buffer C ABI, with its real
+    dependencies: begin (step commit + both decompositions' 2 x 14 matrix commits) -> [host work] -> finish (compute_f_0,
+    from_f, cm_0); the folded witness of step i is the accumulator that step i+1 decomposes.  Pinned host buffers."""
     from latticeum_b200 import _capi as capi
+    from latticeum_b200 import scheme as S
 
-    if not hasattr(capi.lib(), "lat_ajtai_fold_step_begin"):
-        return None
-    from latticeum_b200 import foldstep
+    L = capi.lib()
+    K, n = K_PLANES, N_COLS
+    enc = (lambda x: S.to_mont(x)) if mont else (lambda x: x)
+    rng = np.random.default_rng(2024)
+    acc_fc = signed_to_fq(np.clip(np.rint(rng.normal(0.0, 350.0, size=(n, 24))), -(2**15 - 1), 2**15 - 1).astype(np.int64))
+    rho_canon = None  # CRT of short challenges (coefficients in [-32, 32), cyclotomic-rings/src/rings/goldilocks.rs:32-35)
+    rho_coeff = signed_to_fq(rng.integers(-32, 32, size=(2 * K, 24)))
+    rho_canon = np.empty_like(rho_coeff)
+    assert L.lat_ring_crt(rho_coeff.ctypes.data, 2 * K, rho_canon.ctypes.data, ctx.local_rank) == 0, capi.last_error()
 
-    return foldstep.bench_leg(args, ctx, scheme, eng, mont, w_canon, sys.modules[__name__])
+    def pinned(shape, dtype):
+        a = S.pinned_empty((int(np.prod(shape)) * np.dtype(dtype).itemsize + 7) // 8)
+        return a.view(np.uint8)[: int(np.prod(shape)) * np.dtype(dtype).itemsize].view(dtype).reshape(shape)
+
+    w_pin = pinned((W_LEN, 24), np.uint64)
+    w_pin[:] = enc(w_canon)
+    rho_pin = pinned((2 * K, 24), np.uint64)
+    rho_pin[:] = enc(rho_canon)
+    d16, f0d = pinned((n, 24), np.int16), pinned((n, 24), np.int16)
+    cm, cm0, cms = pinned((KAPPA, 24), np.uint64), pinned((KAPPA, 24), np.uint64), pinned((2, K, KAPPA, 24), np.uint64)
+    acc_cm = np.empty((KAPPA, 24), np.uint64)
+    acc_in = enc(acc_fc)
+    assert L.lat_ajtai_commit_coeff(scheme._h, acc_in.ctypes.data, n, acc_cm.ctypes.data) == 0, capi.last_error()
+
+    def reset():
+        assert L.lat_ajtai_set_accumulator(scheme._h, acc_in.ctypes.data, n, acc_cm.ctypes.data) == 0, capi.last_error()
+
+    def one_step(digits=True):
+        st = L.lat_ajtai_fold_step_begin(scheme._h, w_pin.ctypes.data, W_LEN, None, d16.ctypes.data if digits else None,
+                                         cm.ctypes.data, cms.ctypes.data)
+        assert st == 0, capi.last_error()
+        st = L.lat_ajtai_fold_step_finish(scheme._h, rho_pin.ctypes.data, f0d.ctypes.data if digits else None, None,
+                                          cm0.ctypes.data, None)
+        assert st == 0, capi.last_error()
+
+    # first step from the known initial state: kept for the oracle check
+    reset()
+    one_step()
+    first = {"cm": cm.copy(), "cms": cms.copy(), "d16": d16.copy(), "f0d": f0d.copy(), "cm0": cm0.copy()}
+    for _ in range(2):
+        one_step()
+    steps = max(5, min(args.steps, 50))
+    ctx.torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    e2e_ms = (time.perf_counter() - t0) / steps * 1e3
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step(digits=False)
+    dev_ms = (time.perf_counter() - t0) / steps * 1e3
+    eng.bind_stream()
+    # multiply count of one fold step (Karatsuba: 24 IMAD.WIDE.U32 per Fq3 product; SURVEY 8d counts 36 schoolbook)
+    wide = (1 + 2 * (K - 1)) * KAPPA * n * 8 * 24 + 2 * K * n * 8 * 24
+    res = {"workload": "one IVC step: from_w_ccs + commit, decompose_witness + commit_witnesses on both sides (2 x 14 matrix "
+                       "commits), compute_f_0 + from_f + cm_0; accumulator resident, steps dependent",
+           "api": "lat_ajtai_fold_step_begin / lat_ajtai_fold_step_finish, two blocking calls per step, pinned host buffers",
+           "e2e_ms": e2e_ms, "h2d_bytes_per_step": W_LEN * ELEM_B + 2 * K * ELEM_B,
+           "d2h_bytes_per_step": 2 * n * 48 + (2 + 2 * K) * KAPPA * ELEM_B,
+           "ms": dev_ms, "ms_note": "same calls without the two 4.7 MB int16 digit downloads (commitments still come back)",
+           "matrix_commits_per_step": 1 + 2 * (K - 1), "commitments_per_s": (1 + 2 * (K - 1)) / (e2e_ms * 1e-3),
+           "imad_wide_per_step": wide}
+    pk = imad_peak()
+    if pk and pk.get("imad_wide_T_per_s"):
+        res["imad_peak_T_per_s"] = pk["imad_wide_T_per_s"]
+        res["imad_frac"] = wide / (dev_ms * 1e-3) / (pk["imad_wide_T_per_s"] * 1e12)
+        res["imad_frac_note"] = "Karatsuba multiply count of the whole step / (ms x IMAD.WIDE.U32 peak measured in this run)"
+
+    def check(CO, A):
+        dec = (lambda x: CO.from_mont(x)) if mont else (lambda x: x)
+        t0 = time.perf_counter()
+        f_coeff, f = CO.witness_from_w_ccs(w_canon, 1 << LOG2_B, L_LIMBS)
+        e_cm = CO.commit(A, f)
+        _, pf0, ys0 = CO.decompose_commit(A, acc_fc, dec(acc_cm), 2, K)
+        _, pf1, ys1 = CO.decompose_commit(A, f_coeff, e_cm, 2, K)
+        f0 = CO.compute_f0(rho_canon, [pf0[k] for k in range(K)] + [pf1[k] for k in range(K)])
+        f0c = CO.icrt(f0)
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        sd = lambda x: np.where(x > np.uint64(Q // 2), (x + np.uint64(2**32 - 1)).view(np.int64), x.view(np.int64))  # noqa: E731  x - q wraps
+        ok = (np.array_equal(dec(first["cm"]), e_cm) and np.array_equal(dec(first["cms"][0]), ys0)
+              and np.array_equal(dec(first["cms"][1]), ys1) and np.array_equal(first["d16"].astype(np.int64), sd(f_coeff))
+              and np.array_equal(first["f0d"].astype(np.int64), sd(f0c))
+              and np.array_equal(dec(first["cm0"]), CO.commit(A, f0)))  # cm_0 = sum rho_i cm_i = A * f_0 (homomorphism)
+        return bool(ok), cpu_ms
+
+    res["_check"] = check
+    return res
 
 
 def single_gpu_2_20_leg(args, ctx, LB):

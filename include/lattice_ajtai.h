@@ -130,6 +130,13 @@ int lat_ajtai_witness_from_w_ccs(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w
 int lat_ajtai_witness_from_w_ccs_dev(lat_ajtai *h, const uint64_t *w_ccs_dev, uint64_t w_len,
                                      uint64_t *f_coeff_dev, uint64_t *f_dev, uint64_t *cm_dev);
 
+/* The same call returning Witness::f_coeff as the int16 digits the device holds (n x 24 int16, 4.7 MB instead of
+ * 19 MB at the zkVM's size): base-B limbs satisfy |digit| <= B/2 <= 2^14, so int16 is lossless, and the host widens
+ * them into Fq (negative digits are q - |d|) where its MLE code wants field elements -- f_hat (LF/arith.rs:273-297) is
+ * a re-layout of exactly these digits.  f_coeff16 and f may be NULL.                                            */
+int lat_ajtai_witness_from_w_ccs_compact(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_len, int16_t *f_coeff16,
+                                         uint64_t *f, uint64_t *cm);
+
 /* Non-blocking form of the same call: lat_ajtai_submit_w_ccs queues upload -> iCRT/decompose/CRT -> A * f -> report
  * of cm and returns at once with a ticket; lat_ajtai_wait blocks until that ticket's cm has been written (and reports
  * its LAT_E_DIGIT_OVERFLOW, if any).  What it is for: work that is INDEPENDENT of the commitment -- the host's own
@@ -179,6 +186,38 @@ int lat_ajtai_decompose_commit_resident(lat_ajtai *h, const uint64_t *cm, uint64
 int lat_ajtai_select_side(lat_ajtai *h, int side);
 int lat_ajtai_fold_witness(lat_ajtai *h, const uint64_t *rho, uint64_t *f0, uint64_t *f0_coeff);
 int lat_ajtai_fold_witness_dev(lat_ajtai *h, const uint64_t *rho_dev, uint64_t *f0_dev, uint64_t *f0_coeff_dev);
+
+/* ---- the fold step of one IVC step as two blocking calls            ZKVM/zk_latticefold.rs:37-102, ZKVM/main.rs:174-182
+ * The engine keeps the running accumulator witness w_acc resident (its coefficients as int16 digits) together with its
+ * commitment, so that per step only w_ccs goes up and commitments + int16 digits come down:
+ *
+ *   lat_ajtai_set_accumulator : upload the initial accumulator witness (ZKVM/main.rs:306-344: the zero witness),
+ *       f_coeff: n x 24 coefficient form with |c| < 2^K else LAT_E_DIGIT_OVERFLOW; cm_acc (kappa x 24) may be NULL if
+ *       it is passed to the first begin instead.
+ *   lat_ajtai_fold_step_begin : Witness::from_w_ccs + Witness::commit of the step witness (ZKVM/main.rs:348-367), then
+ *       decompose_witness + commit_witnesses (LF/nifs/decomposition.rs:162-201) of the accumulator (side 0, against
+ *       cm_acc; NULL = the folded commitment left resident by the previous finish) and of the step witness (side 1,
+ *       against the commitment just computed) -- all chained on the device, one synchronisation.  Outputs: cm
+ *       (kappa x 24), cms (2 x K x kappa x 24: side 0 then side 1, each [y_0 .. y_{K-1}]) and, optionally, the step
+ *       witness's f_coeff as int16 digits (n x 24).  The 2K planes stay resident.
+ *   -- the host runs its linearization / decomposition / folding sumchecks and derives the challenges rho --
+ *   lat_ajtai_fold_step_finish: f_0 = sum_i rho_i * f_i over the 2K planes (LF/nifs/folding.rs:258-268), Witness::from_f's
+ *       iCRT (LF/arith.rs:299-313) and cm_0 = sum_i rho_i * cm_i (LF/nifs/folding/utils.rs:466-472).  rho: 2K x 24 CRT
+ *       form.  Outputs (each may be NULL): f0_coeff16 (n x 24 int16), f0 (n x 24 CRT form), cm0 (kappa x 24).  f_0 becomes
+ *       the resident accumulator of the next step; if one of its coefficients reaches 2^K (the protocol's norm bound,
+ *       checked nowhere in the reference, which would panic in the next decomposition) -> LAT_E_DIGIT_OVERFLOW.   */
+int lat_ajtai_set_accumulator(lat_ajtai *h, const uint64_t *f_coeff, uint64_t n, const uint64_t *cm_acc);
+int lat_ajtai_fold_step_begin(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_len, const uint64_t *cm_acc,
+                              int16_t *f_coeff16, uint64_t *cm, uint64_t *cms);
+int lat_ajtai_fold_step_finish(lat_ajtai *h, const uint64_t *rho, int16_t *f0_coeff16, uint64_t *f0, uint64_t *cm0,
+                               uint64_t *w_ccs0);
+/* (w_ccs0, may be NULL: gadget_recompose(f_0), n / L elements in CRT form -- the w_ccs of Witness::from_f, LF/arith.rs:305.)
+ *
+ * Witness::get_fhat (LF/arith.rs:273-297) of a resident witness on the device, for MLE code that runs there:
+ * fhat_dev: tau = 3 tables x n x 24; table j, element i, slot s = (coefficient 8 j + s of f_coeff[i], 0, 0).
+ * which: 0 = the current witness (last from_w_ccs / begin), 1 = the accumulator.  Hosts re-lay out the int16 digits
+ * themselves (12x less PCIe than fetching the tables).                                                          */
+int lat_ajtai_get_fhat_dev(lat_ajtai *h, int which, uint64_t *fhat_dev);
 
 /* GadgetRecompose for &[R] in CRT form: out[i] = sum_l B^l * f[i*L + l]   (Witness::from_f / from_f_coeff rebuild
  * w_ccs this way, LF/arith.rs:305,330; RING/balanced_decomposition/mod.rs:105-117,177-190).

@@ -13,6 +13,7 @@ from .scheme import (  # noqa: F401
     DecompositionParams,
     DigitOverflow,
     EngineError,
+    FoldStep,
     GoldiLocksDP,
     KAPPA,
     LFDecompositionProver,
@@ -25,7 +26,9 @@ from .scheme import (  # noqa: F401
     WrongWitnessLength,
     from_mont,
     gadget_recompose,
+    digits_to_fq,
     get_fhat,
+    get_fhat_from_digits,
     ntt_from_scalar,
     ntt_negacyclic,
     pinned_empty,
@@ -35,5 +38,5 @@ from .scheme import (  # noqa: F401
 __all__ = [
     "AjtaiCommitmentScheme", "Commitment", "ntt_negacyclic", "CommitPipeline", "pinned_empty", "CommitmentError", "DecompositionParams", "DigitOverflow", "EngineError",
     "GoldiLocksDP", "KAPPA", "LFDecompositionProver", "LFFoldingProver", "gadget_recompose", "N", "W_SIZE", "Witness", "WrongAjtaiMatrixDimensions",
-    "WrongCommitmentLength", "WrongWitnessLength", "from_mont", "get_fhat", "ntt_from_scalar", "to_mont",
+    "WrongCommitmentLength", "WrongWitnessLength", "from_mont", "get_fhat", "get_fhat_from_digits", "digits_to_fq", "FoldStep", "ntt_from_scalar", "to_mont",
 ]

@@ -50,6 +50,11 @@ SIGNATURES = {
     "lat_ajtai_decompose_and_commit_ntt": (C.c_int, [_H, _u64p, C.c_uint64, _u64p]),
     "lat_ajtai_witness_from_w_ccs": (C.c_int, [_H, _u64p, C.c_uint64, _u64p, _u64p, _u64p]),
     "lat_ajtai_witness_from_w_ccs_dev": (C.c_int, [_H, _u64p, C.c_uint64, _u64p, _u64p, _u64p]),
+    "lat_ajtai_witness_from_w_ccs_compact": (C.c_int, [_H, _u64p, C.c_uint64, C.c_void_p, _u64p, _u64p]),
+    "lat_ajtai_set_accumulator": (C.c_int, [_H, _u64p, C.c_uint64, _u64p]),
+    "lat_ajtai_fold_step_begin": (C.c_int, [_H, _u64p, C.c_uint64, _u64p, C.c_void_p, _u64p, _u64p]),
+    "lat_ajtai_fold_step_finish": (C.c_int, [_H, _u64p, C.c_void_p, _u64p, _u64p, _u64p]),
+    "lat_ajtai_get_fhat_dev": (C.c_int, [_H, C.c_int, _u64p]),
     "lat_ajtai_submit_w_ccs": (C.c_int, [_H, _u64p, C.c_uint64, _u64p, C.POINTER(C.c_uint64)]),
     "lat_ajtai_wait": (C.c_int, [_H, C.c_uint64]),
     "lat_ajtai_set_peers": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint64]),

@@ -162,6 +162,10 @@ struct lat_ajtai {
     DevBuf planes_fx[2]; // K x n x 48 CRT-form planes, extended layout (MAC input), one buffer per fold side
     bool side_ready[2] = {false, false};
     int cur_side = 0;
+    // fold step (lat_ajtai_fold_step_*): the running accumulator's coefficients as int16 digits, the 2 x K commitments of
+    // the current step's two decompositions, the step commitment and the (folded) accumulator commitment
+    DevBuf f16_acc, cms_side[2], cm_step, cm_acc;
+    bool acc_ready = false, cm_acc_ready = false, fold_pending = false;
     DevBuf rho;          // 2K x 24
     DevBuf f0;           // n x 24, folded witness (host-call staging)
     DevBuf planes_coeff; // K x n x 24 coefficient-form planes (host output only)
@@ -385,7 +389,8 @@ void lat_ajtai_destroy(lat_ajtai *h) {
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     if (h->stream && h->stream != h->own_stream) cudaStreamSynchronize(h->stream);  // steps in flight write into our buffers
     DevBuf *bufs[] = {&h->A, &h->stage, &h->in, &h->f16, &h->f, &h->fx, &h->fcoeff64, &h->planes, &h->planes_fx[0], &h->planes_fx[1],
-                      &h->rho, &h->f0, &h->planes_coeff, &h->cms, &h->cm_in, &h->ws, &h->flag, &h->fx_alt};
+                      &h->rho, &h->f0, &h->planes_coeff, &h->cms, &h->cm_in, &h->ws, &h->flag, &h->fx_alt,
+                      &h->f16_acc, &h->cms_side[0], &h->cms_side[1], &h->cm_step, &h->cm_acc};
     for (DevBuf *b : bufs) b->release();
     if (h->h_flag) cudaFreeHost(h->h_flag);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
@@ -553,23 +558,16 @@ int lat_ajtai_witness_from_w_ccs_gated_dev(lat_ajtai *h, const uint64_t *w_ccs_d
                         (const unsigned long long *)ready_flag_dev, ready_value);
 }
 
-static int witness_host(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool in_coeff, uint64_t *f_coeff, uint64_t *f,
-                        uint64_t *cm) {
-    if (!h || !w) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
-    if (w_len * h->L != h->n) return h->wrong_len(w_len * h->L);
-    int st = h->bind();
-    if (st) return st;
-    if (cm && (st = h->matrix_ready())) return st;
-    size_t in_bytes = w_len * ELEM_BYTES, n_bytes = h->n * ELEM_BYTES;
+// Host-buffer w (w_ccs, or coefficients when in_coeff) -> resident digits (+ optional u64 outputs on the device) and,
+// with want_cm, the commitment in cm_dev.  Enqueues only; the caller copies results out and calls finish().
+static int witness_enqueue(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool in_coeff, u64 *d_fc, u64 *d_f, u64 *cm_dev) {
+    int st;
+    const size_t in_bytes = w_len * ELEM_BYTES;
     if ((st = h->in.ensure(in_bytes))) return st;
-    if (f_coeff && (st = h->fcoeff64.ensure(n_bytes))) return st;
-    if (f && (st = h->f.ensure(n_bytes))) return st;
     // Pipeline the upload with the witness kernel: w_ccs goes up in chunks on a copy stream and each chunk's
     // iCRT/decompose/CRT starts as soon as its bytes have landed (per-element work, so chunks are independent); only
-    // the matrix-vector kernel needs the whole witness.  With pinned host memory this hides the witness kernel behind
-    // the PCIe transfer.
-    u64 *d_fc = f_coeff ? h->fcoeff64.as<u64>() : nullptr, *d_f = f ? h->f.as<u64>() : nullptr;
-    u64 *d_fx = cm ? h->fx.as<u64>() : nullptr;
+    // the matrix-vector kernel needs the whole witness.
+    u64 *d_fx = cm_dev ? h->fx.as<u64>() : nullptr;
     // Pinned (page-locked) host memory is mapped into the device address space: the witness kernel then reads w_ccs
     // straight over PCIe -- no staging copy, no extra launch, the 8-lane loads are contiguous 768-byte runs per warp.
     const u64 *w_mapped = nullptr;
@@ -603,12 +601,29 @@ static int witness_host(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool in
         CK(cudaGetLastError());
     }
     h->has_resident = true;
-    if (cm && (st = h->mac_fx(h->fx.as<u64>(), h->n, 1, h->cms.as<u64>()))) return st;
+    if (cm_dev && (st = h->mac_fx(h->fx.as<u64>(), h->n, 1, cm_dev))) return st;
     if (nchunks > 1) {  // the next call's copies must not overtake this call's kernels reading h->in
         CK(cudaEventRecord(h->work_done, h->stream));
         CK(cudaStreamWaitEvent(h->copy_stream, h->work_done, 0));
     }
+    return LAT_OK;
+}
+
+static int witness_host(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool in_coeff, uint64_t *f_coeff, uint64_t *f,
+                        uint64_t *cm, int16_t *f_coeff16 = nullptr) {
+    if (!h || !w) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (w_len * h->L != h->n) return h->wrong_len(w_len * h->L);
+    int st = h->bind();
+    if (st) return st;
+    if (cm && (st = h->matrix_ready())) return st;
+    const size_t n_bytes = h->n * ELEM_BYTES;
+    if (f_coeff && (st = h->fcoeff64.ensure(n_bytes))) return st;
+    if (f && (st = h->f.ensure(n_bytes))) return st;
+    u64 *d_fc = f_coeff ? h->fcoeff64.as<u64>() : nullptr, *d_f = f ? h->f.as<u64>() : nullptr;
+    if ((st = witness_enqueue(h, w, w_len, in_coeff, d_fc, d_f, cm ? h->cms.as<u64>() : nullptr))) return st;
     if (cm) CK(cudaMemcpyAsync(cm, h->cms.p, (size_t)h->kappa * ELEM_BYTES, cudaMemcpyDeviceToHost, h->stream));
+    if (f_coeff16)
+        CK(cudaMemcpyAsync(f_coeff16, h->f16.p, h->n * LAT_RING_DEGREE * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
     if (f_coeff) CK(cudaMemcpyAsync(f_coeff, h->fcoeff64.p, n_bytes, cudaMemcpyDeviceToHost, h->stream));
     if (f) CK(cudaMemcpyAsync(f, h->f.p, n_bytes, cudaMemcpyDeviceToHost, h->stream));
     return h->finish();
@@ -617,6 +632,10 @@ static int witness_host(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool in
 int lat_ajtai_witness_from_w_ccs(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_len, uint64_t *f_coeff, uint64_t *f,
                                  uint64_t *cm) {
     return witness_host(h, w_ccs, w_len, false, f_coeff, f, cm);
+}
+int lat_ajtai_witness_from_w_ccs_compact(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_len, int16_t *f_coeff16,
+                                         uint64_t *f, uint64_t *cm) {
+    return witness_host(h, w_ccs, w_len, false, nullptr, f, cm, f_coeff16);
 }
 int lat_ajtai_decompose_and_commit_ntt(lat_ajtai *h, const uint64_t *w, uint64_t w_len, uint64_t *cm) {
     if (!cm) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
@@ -738,8 +757,10 @@ int lat_ajtai_wait(lat_ajtai *h, uint64_t ticket) {
 
 // ---- decompose_witness + commit_witnesses ---------------------------------------------------------------------------
 // f16 already holds the coefficients; produce planes (to caller buffers or internal), K-1 commits and y_0.
-static int planes_core(lat_ajtai *h, const u64 *cm_dev, u64 *planes_coeff_dev, u64 *planes_f_dev, u64 *cms_dev) {
+static int planes_core(lat_ajtai *h, const u64 *cm_dev, u64 *planes_coeff_dev, u64 *planes_f_dev, u64 *cms_dev,
+                       const int16_t *src16 = nullptr) {
     int st;
+    if (!src16) src16 = h->f16.as<int16_t>();
     u64 *pfx = nullptr;
     {   // the extended-layout planes of this side stay resident for lat_ajtai_fold_witness
         DevBuf &buf = h->planes_fx[h->cur_side];
@@ -748,7 +769,7 @@ static int planes_core(lat_ajtai *h, const u64 *cm_dev, u64 *planes_coeff_dev, u
         h->side_ready[h->cur_side] = true;
     }
     if (pfx || planes_f_dev || planes_coeff_dev) {
-        lat::launch_planes(h->f16.as<int16_t>(), h->n, (int)h->K, h->mont, planes_f_dev, pfx, planes_coeff_dev, h->stream);
+        lat::launch_planes(src16, h->n, (int)h->K, h->mont, planes_f_dev, pfx, planes_coeff_dev, h->stream);
         CK(cudaGetLastError());
     }
     if (cms_dev) {
@@ -870,6 +891,126 @@ int lat_ajtai_fold_witness(lat_ajtai *h, const uint64_t *rho, uint64_t *f0, uint
     if (f0) CK(cudaMemcpyAsync(f0, h->f0.p, n_bytes, cudaMemcpyDeviceToHost, h->stream));
     if (f0_coeff) CK(cudaMemcpyAsync(f0_coeff, h->in.p, n_bytes, cudaMemcpyDeviceToHost, h->stream));
     return h->finish();
+}
+
+// ---- the fold step as two blocking calls (zk_latticefold.rs:37-102) -------------------------------------------------------
+// begin : Witness::from_w_ccs + commit of the step witness, then decompose_witness + commit_witnesses of BOTH
+//         decompositions -- side 0 = the running accumulator (resident from the previous finish or from
+//         lat_ajtai_set_accumulator), side 1 = the step witness -- chained on the device, one synchronisation.
+// finish: compute_f_0 over the 2K resident planes with the host's challenges, Witness::from_f's iCRT, the folded
+//         commitment cm_0 = sum rho_i cm_i, and the re-packing of f_0's coefficients as the next accumulator.
+// Between the two the host runs its sumchecks (the challenges depend on all 2K commitments).
+static int set_accumulator_dev(lat_ajtai *h, const u64 *f_coeff_dev) {
+    int st = h->f16_acc.ensure(h->n * LAT_RING_DEGREE * sizeof(int16_t));
+    if (st) return st;
+    lat::launch_pack_coeff(f_coeff_dev, h->n, h->mont, (int)h->K, h->f16_acc.as<int16_t>(), h->flag.as<int>(), h->stream);
+    CK(cudaGetLastError());
+    h->acc_ready = true;
+    return LAT_OK;
+}
+
+int lat_ajtai_set_accumulator(lat_ajtai *h, const uint64_t *f_coeff, uint64_t n, const uint64_t *cm_acc) {
+    if (!h || !f_coeff) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (n != h->n) return h->wrong_len(n);
+    int st = h->bind();
+    if (st) return st;
+    const size_t n_bytes = n * ELEM_BYTES, cm_bytes = (size_t)h->kappa * ELEM_BYTES;
+    if ((st = h->in.ensure(n_bytes)) || (st = h->cm_acc.ensure(cm_bytes))) return st;
+    CK(cudaMemcpyAsync(h->in.p, f_coeff, n_bytes, cudaMemcpyHostToDevice, h->stream));
+    if ((st = set_accumulator_dev(h, h->in.as<u64>()))) return st;
+    h->cm_acc_ready = false;
+    if (cm_acc) {
+        CK(cudaMemcpyAsync(h->cm_acc.p, cm_acc, cm_bytes, cudaMemcpyHostToDevice, h->stream));
+        h->cm_acc_ready = true;
+    }
+    st = h->finish();
+    if (st) h->acc_ready = false;
+    return st;
+}
+
+int lat_ajtai_fold_step_begin(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_len, const uint64_t *cm_acc,
+                              int16_t *f_coeff16, uint64_t *cm, uint64_t *cms) {
+    if (!h || !w_ccs || !cm || !cms) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (w_len * h->L != h->n) return h->wrong_len(w_len * h->L);
+    if (!h->acc_ready) return fail(LAT_E_INVALID_ARGUMENT, "no accumulator witness: call lat_ajtai_set_accumulator first");
+    if (!cm_acc && !h->cm_acc_ready) return fail(LAT_E_INVALID_ARGUMENT, "no accumulator commitment resident: pass cm_acc");
+    if (h->log2_B > h->K) return fail(LAT_E_INVALID_ARGUMENT, "step limbs may exceed 2^K (log2_B > K)");
+    int st = h->bind();
+    if (st || (st = h->matrix_ready())) return st;
+    const size_t cm_bytes = (size_t)h->kappa * ELEM_BYTES, side_bytes = (size_t)h->K * cm_bytes;
+    if ((st = h->cm_step.ensure(cm_bytes)) || (st = h->cm_acc.ensure(cm_bytes)) || (st = h->cms_side[0].ensure(side_bytes)) ||
+        (st = h->cms_side[1].ensure(side_bytes)))
+        return st;
+    if (cm_acc) CK(cudaMemcpyAsync(h->cm_acc.p, cm_acc, cm_bytes, cudaMemcpyHostToDevice, h->stream));
+    // the step witness and its commitment (ZKVM/main.rs:348-367)
+    if ((st = witness_enqueue(h, w_ccs, w_len, false, nullptr, nullptr, h->cm_step.as<u64>()))) return st;
+    CK(cudaMemcpyAsync(cm, h->cm_step.p, cm_bytes, cudaMemcpyDeviceToHost, h->stream));  // the host may start on it early
+    if (f_coeff16)
+        CK(cudaMemcpyAsync(f_coeff16, h->f16.p, h->n * LAT_RING_DEGREE * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
+    // side 1: the step witness (lin_cm_i, w_i); side 0: the accumulator (acc, w_acc)      zk_latticefold.rs:60-71
+    const int side_before = h->cur_side;
+    h->cur_side = 1;
+    st = planes_core(h, h->cm_step.as<u64>(), nullptr, nullptr, h->cms_side[1].as<u64>(), h->f16.as<int16_t>());
+    if (!st) {
+        h->cur_side = 0;
+        st = planes_core(h, h->cm_acc.as<u64>(), nullptr, nullptr, h->cms_side[0].as<u64>(), h->f16_acc.as<int16_t>());
+    }
+    h->cur_side = side_before;
+    if (st) return st;
+    CK(cudaMemcpyAsync(cms, h->cms_side[0].p, side_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(cms + (size_t)h->K * h->kappa * LAT_RING_DEGREE, h->cms_side[1].p, side_bytes, cudaMemcpyDeviceToHost,
+                       h->stream));
+    h->fold_pending = true;
+    return h->finish();
+}
+
+int lat_ajtai_fold_step_finish(lat_ajtai *h, const uint64_t *rho, int16_t *f0_coeff16, uint64_t *f0, uint64_t *cm0,
+                               uint64_t *w_ccs0) {
+    if (!h || !rho) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (!h->fold_pending) return fail(LAT_E_INVALID_ARGUMENT, "lat_ajtai_fold_step_begin has not run");
+    int st = h->bind();
+    if (st) return st;
+    const size_t n_bytes = h->n * ELEM_BYTES, rho_bytes = (size_t)2 * h->K * ELEM_BYTES, cm_bytes = (size_t)h->kappa * ELEM_BYTES;
+    if ((st = h->rho.ensure(rho_bytes)) || (st = h->f0.ensure(n_bytes)) || (st = h->in.ensure(n_bytes))) return st;
+    CK(cudaMemcpyAsync(h->rho.p, rho, rho_bytes, cudaMemcpyHostToDevice, h->stream));
+    // f_0 = sum rho_i f_i (folding.rs:258-268), f_0 coefficients (arith.rs:299-313)
+    if ((st = lat_ajtai_fold_witness_dev(h, h->rho.as<uint64_t>(), h->f0.as<uint64_t>(), h->in.as<uint64_t>()))) return st;
+    // cm_0 = sum rho_i cm_i (folding/utils.rs:466-472): the next step's accumulator commitment, kept resident
+    lat::launch_lincomb(h->rho.as<u64>(), h->cms_side[0].as<u64>(), h->cms_side[1].as<u64>(), (int)h->K, h->kappa, h->mont,
+                        h->cm_acc.as<u64>(), h->stream);
+    CK(cudaGetLastError());
+    h->cm_acc_ready = true;
+    // the folded witness becomes the accumulator: its coefficients must stay below 2^K (the protocol's norm bound)
+    if ((st = set_accumulator_dev(h, h->in.as<u64>()))) return st;
+    if (f0_coeff16)
+        CK(cudaMemcpyAsync(f0_coeff16, h->f16_acc.p, h->n * LAT_RING_DEGREE * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
+    if (f0) CK(cudaMemcpyAsync(f0, h->f0.p, n_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (cm0) CK(cudaMemcpyAsync(cm0, h->cm_acc.p, cm_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (w_ccs0) {  // Witness::from_f rebuilds w_ccs = gadget_recompose(f_0) (arith.rs:305): n / L elements, CRT form
+        const u64 count = h->n / h->L;
+        // h->in held f_0's coefficients; they are packed into f16_acc by now (stream order), so it is free again
+        lat::launch_recompose(h->f0.as<u64>(), count, (int)h->log2_B, (int)h->L, h->in.as<u64>(), h->stream);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(w_ccs0, h->in.p, count * ELEM_BYTES, cudaMemcpyDeviceToHost, h->stream));
+    }
+    h->fold_pending = false;
+    st = h->finish();
+    if (st) h->acc_ready = false;  // e.g. LAT_E_DIGIT_OVERFLOW: the folded witness broke the norm bound
+    return st;
+}
+
+// Witness::get_fhat (LF/arith.rs:273-297) of a resident witness, on the device: tau = 3 tables of n ring elements, table j,
+// element i, slot s = (coefficient 8j + s of f_coeff[i], 0, 0).  For MLE code that runs on the GPU; a host gets the same
+// tables by re-laying out the int16 digits itself (scheme.get_fhat_from_digits / ajtai.hpp), which is 12x less PCIe.
+int lat_ajtai_get_fhat_dev(lat_ajtai *h, int which, uint64_t *fhat_dev) {
+    if (!h || !fhat_dev) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
+    if (which != 0 && which != 1) return fail(LAT_E_INVALID_ARGUMENT, "which: 0 = current witness, 1 = accumulator");
+    if (which == 0 ? !h->has_resident : !h->acc_ready) return fail(LAT_E_INVALID_ARGUMENT, "no such resident witness");
+    int st = h->bind();
+    if (st) return st;
+    lat::launch_fhat((which == 0 ? h->f16 : h->f16_acc).as<int16_t>(), h->n, h->mont, (u64 *)fhat_dev, h->stream);
+    CK(cudaGetLastError());
+    return LAT_OK;
 }
 
 int lat_ring_gadget_recompose(const uint64_t *f, uint64_t count, uint32_t log2_b, uint32_t L, uint64_t *out, int repr,

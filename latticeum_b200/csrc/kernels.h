@@ -43,6 +43,10 @@ void launch_witness(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool i
 void launch_planes(const int16_t *f16, u64 n, int K, bool mont, u64 *planes_f, u64 *planes_fx, u64 *planes_coeff,
                    cudaStream_t stream);
 
+// int16 digits (n x 24) -> Witness::get_fhat tables: fhat[j][i][3 s] = digit 8 j + s of element i as a field element in
+// the caller's representation, the other two components of every slot zero; fhat: 3 x n x 24.
+void launch_fhat(const int16_t *f16, u64 n, bool mont, u64 *fhat, cudaStream_t stream);
+
 // u64 coefficient-form elements (caller's representation) -> int16, flag |= 1 unless |c| < 2^bits for all c.
 void launch_pack_coeff(const u64 *f_coeff, u64 count, bool mont, int bits, int16_t *f16, int *flag,
                        cudaStream_t stream);
@@ -108,6 +112,11 @@ void launch_y0(const u64 *cm, u64 *cms, uint32_t K, uint32_t kappa, cudaStream_t
 // buffers of planes_per_side x n x 48 each.  rho: nplanes x 24 in the caller's representation.  f0: n x 24.
 void launch_fold(const u64 *const *sides_fx, int nsides, int planes_per_side, u64 n, const u64 *rho, bool mont, u64 *f0,
                  cudaStream_t stream);
+
+// out[i] = sum_{p < 2K} rho[p] (*) cms[p][i]  over the K commitments of side 0 followed by the K of side 1 (each
+// K x kappa x 24); the folded commitment cm_0 (LF/nifs/folding/utils.rs:466-472).  rho in the caller's representation.
+void launch_lincomb(const u64 *rho, const u64 *cms0, const u64 *cms1, int K, uint32_t kappa, bool mont, u64 *out,
+                    cudaStream_t stream);
 
 // out[i] = sum_l (2^log2b)^l * f[i*L + l], CRT form (scalar multiples, so any representation)
 void launch_recompose(const u64 *f, u64 count, int log2b, int L, u64 *out, cudaStream_t stream);

@@ -349,6 +349,24 @@ void launch_planes(const int16_t *f16, u64 n, int K, bool mont, u64 *planes_f, u
     else planes_kernel<false><<<grid, PLANE_THREADS, 0, stream>>>(f16, n, K, planes_f, planes_fx, planes_coeff);
 }
 
+// ---- Witness::get_fhat (latticefold/src/arith.rs:273-297) from the resident digits ---------------------------------------------
+template <bool MONT>
+__global__ void __launch_bounds__(256) fhat_kernel(const int16_t *__restrict__ f16, u64 n, u64 *__restrict__ fhat) {
+    const u64 idx = (u64)blockIdx.x * 256 + threadIdx.x;  // (table j, element i, slot s), s fastest
+    if (idx >= 3 * n * ring::NSLOT) return;
+    const u64 s = idx & 7, ji = idx >> 3, j = ji / n, i = ji - j * n;
+    u64 *o = fhat + ji * ring::D + 3 * s;
+    o[0] = gl::from_small<MONT>((int)f16[i * ring::D + 8 * j + s]);
+    o[1] = 0;
+    o[2] = 0;
+}
+void launch_fhat(const int16_t *f16, u64 n, bool mont, u64 *fhat, cudaStream_t stream) {
+    if (!n) return;
+    const unsigned grid = (unsigned)((3 * n * ring::NSLOT + 255) / 256);
+    if (mont) fhat_kernel<true><<<grid, 256, 0, stream>>>(f16, n, fhat);
+    else fhat_kernel<false><<<grid, 256, 0, stream>>>(f16, n, fhat);
+}
+
 // ---- u64 coefficients -> int16 with range check ---------------------------------------------------------------
 template <bool MONT>
 __global__ void __launch_bounds__(256)

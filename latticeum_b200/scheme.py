@@ -391,6 +391,21 @@ class Witness:
         return (wit, Commitment(cm, scheme.mont)) if commit else wit
 
     @classmethod
+    def from_w_ccs_compact(cls, scheme: AjtaiCommitmentScheme, w_ccs, want_f: bool = False, commit: bool = True):
+        """Witness::from_w_ccs (+ commit) fetching f_coeff as the device's int16 digits (lat_ajtai_witness_from_w_ccs_compact);
+        `f_coeff` is widened on the host (digits_to_fq).  `wit.digits` keeps the int16 rows for get_fhat_from_digits."""
+        w = _as_u64(w_ccs, "w_ccs").reshape(-1, D)
+        n = w.shape[0] * scheme.params.L
+        d16 = np.empty((n, D), np.int16)
+        f = np.empty((n, D), np.uint64) if want_f else None
+        cm = np.empty((scheme._kappa, D), np.uint64) if commit else None
+        st = capi.lib().lat_ajtai_witness_from_w_ccs_compact(scheme._h, _ptr(w), w.shape[0], _ptr(d16), _ptr(f), _ptr(cm))
+        _raise(st, n, scheme._n)
+        wit = cls(w, f, digits_to_fq(d16, scheme.mont), scheme.mont)
+        wit.digits = d16
+        return (wit, Commitment(cm, scheme.mont)) if commit else wit
+
+    @classmethod
     def from_f_coeff(cls, scheme: AjtaiCommitmentScheme, f_coeff):
         """Witness::from_f_coeff (arith.rs:324-338): f = CRT(f_coeff).  (w_ccs = gadget_recompose(f) is host-side MLE
         plumbing, SURVEY 8 f2, and is left None.)"""
@@ -410,6 +425,27 @@ class Witness:
     def commit(self, scheme: AjtaiCommitmentScheme) -> Commitment:
         """Witness::commit (arith.rs:357-362) = scheme.commit_ntt(&self.f)"""
         return scheme.commit_ntt(self.f)
+
+
+def digits_to_fq(d16, mont: bool = False) -> np.ndarray:
+    """Widen the engine's int16 digits (Witness.f_coeff as the device holds it) into Fq limbs in the caller's
+    representation: d >= 0 -> d, d < 0 -> q - |d|; Montgomery: times 2^64 = 2^32 - 1 (mod q), exact for |d| < 2^31."""
+    d = np.ascontiguousarray(d16, dtype=np.int16).astype(np.int64)
+    m = np.abs(d).astype(np.uint64)
+    if mont:
+        m = (m << np.uint64(32)) - m
+    return np.where((d < 0) & (m != 0), np.uint64(Q) - m, m)
+
+
+def get_fhat_from_digits(d16, mont: bool = False) -> np.ndarray:
+    """Witness::get_fhat (arith.rs:273-297) straight from the int16 digits: the host-side re-layout that replaces
+    fetching f_coeff as 192-byte elements (4.7 MB instead of 19 MB over PCIe at the zkVM's size)."""
+    d = np.ascontiguousarray(d16, dtype=np.int16).reshape(-1, D)
+    out = np.zeros((3, d.shape[0], D), np.uint64)
+    fq = digits_to_fq(d, mont)
+    for j in range(3):
+        out[j, :, 0::3] = fq[:, 8 * j : 8 * j + 8]
+    return out
 
 
 def get_fhat(f_coeff: np.ndarray, mont: bool = False) -> np.ndarray:
@@ -483,6 +519,51 @@ class LFFoldingProver:
         fc = np.empty((scheme._n, D), np.uint64) if want_f_coeff else None
         _raise(capi.lib().lat_ajtai_fold_witness(scheme._h, _ptr(rho), _ptr(f0), _ptr(fc)))
         return Witness(None, f0, fc, scheme.mont)
+
+
+class FoldStep:
+    """The GPU side of one IVC step's fold (zkvm/src/zk_latticefold.rs:37-102 as called from zkvm/src/main.rs:174-182),
+    as the two blocking engine calls lat_ajtai_fold_step_begin / _finish.  The running accumulator witness stays on the
+    device; per step only w_ccs goes up and commitments + int16 digits come down.
+
+        fs = FoldStep(scheme); fs.set_accumulator(w_acc.f_coeff, acc_cm)        # initialize_accumulator, main.rs:306-344
+        cm_i, ys_acc, ys_step, digits = fs.begin(w_ccs)      # commit + both decompositions' 2K commitments
+        ... host: linearization / decomposition / folding sumchecks -> rho_s ...
+        cm_0, f0_digits, f0, w_ccs0 = fs.finish(rho_s)       # compute_f_0, from_f, cm_0; f_0 is the next accumulator
+    """
+
+    def __init__(self, scheme: AjtaiCommitmentScheme):
+        self.scheme = scheme
+
+    def set_accumulator(self, f_coeff, cm_acc: Optional[Commitment] = None) -> None:
+        fc = _as_u64(f_coeff, "f_coeff").reshape(-1, D)
+        cm = _as_u64(cm_acc.as_ref(), "cm_acc") if cm_acc is not None else None
+        _raise(capi.lib().lat_ajtai_set_accumulator(self.scheme._h, _ptr(fc), fc.shape[0], _ptr(cm)), fc.shape[0], self.scheme._n)
+
+    def begin(self, w_ccs, cm_acc: Optional[Commitment] = None, want_digits: bool = True):
+        s = self.scheme
+        w = _as_u64(w_ccs, "w_ccs").reshape(-1, D)
+        K, kappa, n = s.params.K, s._kappa, w.shape[0] * s.params.L
+        d16 = np.empty((n, D), np.int16) if want_digits else None
+        cm = np.empty((kappa, D), np.uint64)
+        cms = np.empty((2, K, kappa, D), np.uint64)
+        acc = _as_u64(cm_acc.as_ref(), "cm_acc") if cm_acc is not None else None
+        st = capi.lib().lat_ajtai_fold_step_begin(s._h, _ptr(w), w.shape[0], _ptr(acc), _ptr(d16), _ptr(cm), _ptr(cms))
+        _raise(st, n, s._n)
+        ys = [[Commitment(c, s.mont) for c in side] for side in cms]
+        return Commitment(cm, s.mont), ys[0], ys[1], d16
+
+    def finish(self, rho_s, want_digits: bool = True, want_f0: bool = False, want_w_ccs: bool = False):
+        s = self.scheme
+        rho = _as_u64(rho_s, "rho_s").reshape(-1, D)
+        if rho.shape[0] != 2 * s.params.K:
+            raise ValueError("need 2K challenges")
+        d16 = np.empty((s._n, D), np.int16) if want_digits else None
+        f0 = np.empty((s._n, D), np.uint64) if want_f0 else None
+        w0 = np.empty((s._n // s.params.L, D), np.uint64) if want_w_ccs else None
+        cm0 = np.empty((s._kappa, D), np.uint64)
+        _raise(capi.lib().lat_ajtai_fold_step_finish(s._h, _ptr(rho), _ptr(d16), _ptr(f0), _ptr(cm0), _ptr(w0)))
+        return Commitment(cm0, s.mont), d16, f0, w0
 
 
 def gadget_recompose(f, params: DecompositionParams = GoldiLocksDP, device: int = 0) -> np.ndarray:

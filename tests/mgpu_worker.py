@@ -104,7 +104,7 @@ if hasattr(sh2, "decompose_commit"):
     sides = []
     for side in range(2):
         small = rng.integers(-(1 << 14), (1 << 14) + 1, size=(n2, 24), dtype=np.int64)
-        sides.append(np.where(small < 0, small.view(np.uint64) + np.uint64(Q), small.view(np.uint64))  # wraps to small + q)
+        sides.append(np.where(small < 0, small.view(np.uint64) + np.uint64(Q), small.view(np.uint64)))  # wraps to small + q
     rho = CO.fill_uniform((2 * K, 24), 33)
     ok = True
     planes_full = []

@@ -546,6 +546,87 @@ def test_fold_witness_compute_f0_vs_oracle(mont):
     s2.close()
 
 
+def oracle_fold_step(A, w, acc_fc, acc_cm, rho):
+    """One IVC step's GPU-side work on the oracle: step commit, both decompositions, compute_f_0, from_f, cm_0."""
+    f_coeff, f = CO.witness_from_w_ccs(w, DP.B, DP.L)
+    cm = CO.commit(A, f)
+    _, pf0, ys0 = CO.decompose_commit(A, acc_fc, acc_cm, 2, DP.K)
+    _, pf1, ys1 = CO.decompose_commit(A, f_coeff, cm, 2, DP.K)
+    f0 = CO.compute_f0(rho, [pf0[k] for k in range(DP.K)] + [pf1[k] for k in range(DP.K)])
+    cm0 = np.zeros((A.shape[0], 24), dtype=object)
+    for r, y in zip(rho, list(ys0) + list(ys1)):  # cm_0 = sum rho_i * cm_i   LF/nifs/folding/utils.rs:466-472
+        cm0 = (cm0 + S._fq3_mul_scalar_vec(y, r, False).astype(object)) % Q
+    return f_coeff, cm, ys0, ys1, f0, CO.icrt(f0), cm0.astype(np.uint64)
+
+
+@pytest.mark.parametrize("mont", [False, True], ids=["canonical", "montgomery"])
+def test_fold_step_begin_finish_vs_oracle(mont):
+    # zk_latticefold.rs:37-102 as two blocking calls; three dependent steps: f_0 of step i is the accumulator of step i+1
+    kappa, wl = 8, 301
+    n = wl * DP.L
+    A = CO.fill_uniform((kappa, n, 24), 160)
+    scheme = make_scheme(A, mont)
+    fs = LB.FoldStep(scheme)
+    rng = np.random.default_rng(161)
+    acc_fc = signed_to_fq(np.clip(np.rint(rng.normal(0.0, 350.0, size=(n, 24))), -(2**15 - 1), 2**15 - 1).astype(np.int64))
+    acc_cm = CO.commit(A, CO.crt(acc_fc))
+    with pytest.raises(LB.EngineError):
+        fs.begin(CO.fill_uniform((wl, 24), 1))  # no accumulator yet
+    fs.set_accumulator(maybe_mont(acc_fc, mont), LB.Commitment(maybe_mont(acc_cm, mont), mont))
+    for step in range(3):
+        w = CO.fill_uniform((wl, 24), 170 + step)
+        rho = CO.crt(signed_to_fq(rng.integers(-32, 32, size=(2 * DP.K, 24))))  # short challenges
+        e_fc, e_cm, e_ys0, e_ys1, e_f0, e_f0c, e_cm0 = oracle_fold_step(A, w, acc_fc, acc_cm, rho)
+        # every other step hands the accumulator commitment over explicitly, the others use the resident one
+        cm_arg = LB.Commitment(maybe_mont(acc_cm, mont), mont) if step % 2 == 0 else None
+        cm, ys0, ys1, d16 = fs.begin(maybe_mont(w, mont), cm_arg)
+        assert np.array_equal(unmont(cm.as_ref(), mont), e_cm)
+        assert np.array_equal(fq_to_signed(e_fc), d16.astype(np.int64))
+        assert np.array_equal(unmont(S.digits_to_fq(d16, mont), mont), e_fc)
+        for k in range(DP.K):
+            assert np.array_equal(unmont(ys0[k].as_ref(), mont), e_ys0[k]), (step, 0, k)
+            assert np.array_equal(unmont(ys1[k].as_ref(), mont), e_ys1[k]), (step, 1, k)
+        cm0, f0d, f0, w0 = fs.finish(maybe_mont(rho, mont), want_f0=True, want_w_ccs=True)
+        assert np.array_equal(unmont(f0, mont), e_f0)
+        assert np.array_equal(f0d.astype(np.int64), fq_to_signed(e_f0c))
+        assert np.array_equal(unmont(cm0.as_ref(), mont), e_cm0)
+        assert np.array_equal(unmont(w0, mont), CO.gadget_recompose_ntt(e_f0, DP.B, DP.L))
+        # homomorphism: the folded commitment IS the commitment of the folded witness
+        assert np.array_equal(e_cm0, CO.commit(A, e_f0))
+        acc_fc, acc_cm = e_f0c, e_cm0
+    # get_fhat on the device and from the digits on the host (LF/arith.rs:273-297)
+    import torch
+    fh = torch.empty((3, n, 24), dtype=torch.int64, device="cuda")
+    assert capi.lib().lat_ajtai_get_fhat_dev(scheme._h, 1, fh.data_ptr()) == 0, capi.last_error()
+    assert capi.lib().lat_ajtai_synchronize(scheme._h) == 0
+    exp_fhat = S.get_fhat(maybe_mont(acc_fc, mont))
+    assert np.array_equal(fh.cpu().numpy().view(np.uint64), exp_fhat)
+    assert np.array_equal(S.get_fhat_from_digits(f0d, mont), exp_fhat)
+    # a folded witness that breaks the norm bound 2^K is reported, not truncated; the accumulator is then invalid
+    cm, ys0, ys1, _ = fs.begin(maybe_mont(CO.fill_uniform((wl, 24), 180), mont))
+    with pytest.raises(LB.DigitOverflow):
+        fs.finish(maybe_mont(CO.fill_uniform((2 * DP.K, 24), 181), mont))  # uniform (not short) challenges
+    with pytest.raises(LB.EngineError):
+        fs.begin(maybe_mont(CO.fill_uniform((wl, 24), 182), mont))
+    scheme.close()
+
+
+def test_witness_from_w_ccs_compact_vs_oracle():
+    kappa, wl = 9, 777
+    A = CO.fill_uniform((kappa, wl * DP.L, 24), 190)
+    w = CO.fill_uniform((wl, 24), 191)
+    w[:5] = 0
+    f_coeff, f = CO.witness_from_w_ccs(w, DP.B, DP.L)
+    for mont in (False, True):
+        scheme = make_scheme(A, mont)
+        wit, cm = LB.Witness.from_w_ccs_compact(scheme, maybe_mont(w, mont), want_f=True)
+        assert np.array_equal(wit.digits.astype(np.int64), fq_to_signed(f_coeff))
+        assert np.array_equal(unmont(wit.f_coeff, mont), f_coeff) and np.array_equal(unmont(wit.f, mont), f)
+        assert np.array_equal(unmont(cm.as_ref(), mont), CO.commit(A, f))
+        assert np.array_equal(S.get_fhat_from_digits(wit.digits, mont), S.get_fhat(maybe_mont(f_coeff, mont)))
+        scheme.close()
+
+
 def test_gadget_recompose_vs_oracle():
     # RING/balanced_decomposition/mod.rs:177-190 in CRT form: recompose(from_w_ccs(w).f) == w  (LF/arith.rs:516-548)
     w = CO.fill_uniform((333, 24), 96)

@@ -30,7 +30,11 @@ def test_sharded_paths_vs_oracle(exchange):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py")]
     r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
-    sys.stdout.write(r.stdout[-4000:])
-    sys.stderr.write(r.stderr[-4000:])
+    sys.stdout.write(r.stdout[-6000:])
+    sys.stderr.write(r.stderr[-6000:])
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):  # keep the workers' output where a gpurun call brings it back
+        with open(os.path.join(out_dir, f"mgpu_worker_{exchange}.log"), "w") as f:
+            f.write(r.stdout + "\n---- stderr ----\n" + r.stderr)
     assert r.returncode == 0, "mgpu_worker failed"
     assert "MISMATCH" not in r.stdout
