@@ -130,6 +130,41 @@ struct DevBuf {
     T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+
+// ---- per-device scratch for the handle-less host-buffer calls (lat_ring_*, lat_ntt_negacyclic, lat_commitment_sum) ----
+// Grow-only device buffers and one non-blocking stream per device, reused across calls: no cudaMalloc / cudaFree and no
+// legacy-stream synchronisation on the call path once the buffers have reached their working size.
+struct Scratch {
+    std::mutex mu;
+    DevBuf buf[4];
+    cudaStream_t stream = nullptr;
+    int *h_flag = nullptr;
+};
+Scratch g_scratch[MAX_DEVICES];
+
+// locks the device's scratch for the scope, makes the device current, sizes the buffers
+struct ScratchLock {
+    Scratch *s = nullptr;
+    std::unique_lock<std::mutex> lock;
+    int open(int device, size_t b0, size_t b1 = 0, size_t b2 = 0, size_t b3 = 0) {
+        if (device < 0 || device >= MAX_DEVICES) return fail(LAT_E_INVALID_ARGUMENT, "device ordinal out of range");
+        CK(cudaSetDevice(device));
+        s = &g_scratch[device];
+        lock = std::unique_lock<std::mutex>(s->mu);
+        if (!s->stream) CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        if (!s->h_flag) CK(cudaHostAlloc((void **)&s->h_flag, sizeof(int), cudaHostAllocDefault));
+        const size_t want[4] = {b0, b1, b2, b3};
+        for (int i = 0; i < 4; ++i)
+            if (want[i]) {
+                int st = s->buf[i].ensure(want[i]);
+                if (st) return st;
+            }
+        return LAT_OK;
+    }
+    template <class T>
+    T *at(int i) const { return s->buf[i].as<T>(); }
+    cudaStream_t stream() const { return s->stream; }
+};
 }  // namespace
 
 struct lat_ajtai {
@@ -142,6 +177,8 @@ struct lat_ajtai {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_stream = nullptr;          // host-call uploads, pipelined against the kernels
     cudaEvent_t copy_done[4] = {nullptr, nullptr, nullptr, nullptr}, work_done = nullptr;
+    cudaEvent_t witness_done = nullptr;          // digits / witness outputs complete: their downloads overlap the matrix-vector kernels
+    bool copy_stream_busy = false;               // downloads in flight on copy_stream: finish() waits for them
 
     DevBuf A;            // re-laid-out matrix, canonical form
     std::vector<uint8_t> row_done;
@@ -273,6 +310,10 @@ struct lat_ajtai {
         CK(cudaMemcpyAsync(h_flag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
         CK(cudaMemsetAsync(flag.p, 0, sizeof(int), stream));
         CK(cudaStreamSynchronize(stream));
+        if (copy_stream_busy) {
+            copy_stream_busy = false;
+            CK(cudaStreamSynchronize(copy_stream));
+        }
         int st = spin_status(device);  // a bounded device-side wait gave up: the results are not to be trusted
         if (st) return st;
         if (*h_flag)
@@ -353,6 +394,7 @@ int lat_ajtai_create(lat_ajtai **out, uint32_t kappa, uint64_t n, uint32_t log2_
         for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->copy_done[i], cudaEventDisableTiming);
         if (e != cudaSuccess) break;
         if ((e = cudaEventCreateWithFlags(&h->work_done, cudaEventDisableTiming)) != cudaSuccess) break;
+        if ((e = cudaEventCreateWithFlags(&h->witness_done, cudaEventDisableTiming)) != cudaSuccess) break;
         if ((e = cudaHostAlloc((void **)&h->h_flag, sizeof(int), cudaHostAllocDefault)) != cudaSuccess) break;
         size_t a_bytes = h->lay.total_elems() * sizeof(u64);
         if ((st = h->A.ensure(a_bytes))) break;
@@ -410,6 +452,7 @@ void lat_ajtai_destroy(lat_ajtai *h) {
     for (cudaEvent_t ev : h->copy_done)
         if (ev) cudaEventDestroy(ev);
     if (h->work_done) cudaEventDestroy(h->work_done);
+    if (h->witness_done) cudaEventDestroy(h->witness_done);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -560,7 +603,8 @@ int lat_ajtai_witness_from_w_ccs_gated_dev(lat_ajtai *h, const uint64_t *w_ccs_d
 
 // Host-buffer w (w_ccs, or coefficients when in_coeff) -> resident digits (+ optional u64 outputs on the device) and,
 // with want_cm, the commitment in cm_dev.  Enqueues only; the caller copies results out and calls finish().
-static int witness_enqueue(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool in_coeff, u64 *d_fc, u64 *d_f, u64 *cm_dev) {
+static int witness_enqueue(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool in_coeff, u64 *d_fc, u64 *d_f, u64 *cm_dev,
+                           bool early_downloads = false) {
     int st;
     const size_t in_bytes = w_len * ELEM_BYTES;
     if ((st = h->in.ensure(in_bytes))) return st;
@@ -601,6 +645,14 @@ static int witness_enqueue(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool
         CK(cudaGetLastError());
     }
     h->has_resident = true;
+    if (early_downloads) {
+        // the caller downloads the witness outputs (digits, f_coeff, f) on copy_stream while the matrix-vector kernels
+        // run: they are complete here.  (The event between the two kernels costs the programmatic overlap of the
+        // matrix-vector kernel's prologue, a few microseconds against ~90 us of PCIe transfer hidden.)
+        CK(cudaEventRecord(h->witness_done, h->stream));
+        CK(cudaStreamWaitEvent(h->copy_stream, h->witness_done, 0));
+        h->copy_stream_busy = true;
+    }
     if (cm_dev && (st = h->mac_fx(h->fx.as<u64>(), h->n, 1, cm_dev))) return st;
     if (nchunks > 1) {  // the next call's copies must not overtake this call's kernels reading h->in
         CK(cudaEventRecord(h->work_done, h->stream));
@@ -620,12 +672,17 @@ static int witness_host(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool in
     if (f_coeff && (st = h->fcoeff64.ensure(n_bytes))) return st;
     if (f && (st = h->f.ensure(n_bytes))) return st;
     u64 *d_fc = f_coeff ? h->fcoeff64.as<u64>() : nullptr, *d_f = f ? h->f.as<u64>() : nullptr;
-    if ((st = witness_enqueue(h, w, w_len, in_coeff, d_fc, d_f, cm ? h->cms.as<u64>() : nullptr))) return st;
+    const bool early = cm && (f_coeff16 || f_coeff || f);
+    if ((st = witness_enqueue(h, w, w_len, in_coeff, d_fc, d_f, cm ? h->cms.as<u64>() : nullptr, early))) return st;
     if (cm) CK(cudaMemcpyAsync(cm, h->cms.p, (size_t)h->kappa * ELEM_BYTES, cudaMemcpyDeviceToHost, h->stream));
-    if (f_coeff16)
-        CK(cudaMemcpyAsync(f_coeff16, h->f16.p, h->n * LAT_RING_DEGREE * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
-    if (f_coeff) CK(cudaMemcpyAsync(f_coeff, h->fcoeff64.p, n_bytes, cudaMemcpyDeviceToHost, h->stream));
-    if (f) CK(cudaMemcpyAsync(f, h->f.p, n_bytes, cudaMemcpyDeviceToHost, h->stream));
+    cudaStream_t ds = early ? h->copy_stream : h->stream;  // with a commitment to compute, the downloads run beside it
+    if (f_coeff16) CK(cudaMemcpyAsync(f_coeff16, h->f16.p, h->n * LAT_RING_DEGREE * sizeof(int16_t), cudaMemcpyDeviceToHost, ds));
+    if (f_coeff) CK(cudaMemcpyAsync(f_coeff, h->fcoeff64.p, n_bytes, cudaMemcpyDeviceToHost, ds));
+    if (f) CK(cudaMemcpyAsync(f, h->f.p, n_bytes, cudaMemcpyDeviceToHost, ds));
+    if (early) {  // later calls write the buffers these downloads read: order them behind
+        CK(cudaEventRecord(h->work_done, h->copy_stream));
+        CK(cudaStreamWaitEvent(h->stream, h->work_done, 0));
+    }
     return h->finish();
 }
 
@@ -943,10 +1000,10 @@ int lat_ajtai_fold_step_begin(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_le
         return st;
     if (cm_acc) CK(cudaMemcpyAsync(h->cm_acc.p, cm_acc, cm_bytes, cudaMemcpyHostToDevice, h->stream));
     // the step witness and its commitment (ZKVM/main.rs:348-367)
-    if ((st = witness_enqueue(h, w_ccs, w_len, false, nullptr, nullptr, h->cm_step.as<u64>()))) return st;
-    CK(cudaMemcpyAsync(cm, h->cm_step.p, cm_bytes, cudaMemcpyDeviceToHost, h->stream));  // the host may start on it early
-    if (f_coeff16)
-        CK(cudaMemcpyAsync(f_coeff16, h->f16.p, h->n * LAT_RING_DEGREE * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
+    if ((st = witness_enqueue(h, w_ccs, w_len, false, nullptr, nullptr, h->cm_step.as<u64>(), f_coeff16 != nullptr))) return st;
+    CK(cudaMemcpyAsync(cm, h->cm_step.p, cm_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (f_coeff16)  // on copy_stream, beside the 29 matrix-vector products (the digits are not modified by them)
+        CK(cudaMemcpyAsync(f_coeff16, h->f16.p, h->n * LAT_RING_DEGREE * sizeof(int16_t), cudaMemcpyDeviceToHost, h->copy_stream));
     // side 1: the step witness (lin_cm_i, w_i); side 0: the accumulator (acc, w_acc)      zk_latticefold.rs:60-71
     const int side_before = h->cur_side;
     h->cur_side = 1;
@@ -1019,21 +1076,14 @@ int lat_ring_gadget_recompose(const uint64_t *f, uint64_t count, uint32_t log2_b
     if (count == 0) return LAT_OK;
     if (!f || !out) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
     if (log2_b < 1 || log2_b > 62 || L < 1) return fail(LAT_E_INVALID_ARGUMENT, "need 1<=log2_b<=62, L>=1");
-    CK(cudaSetDevice(device));
-    DevBuf din, dout;
-    int st;
-    if ((st = din.ensure(count * L * ELEM_BYTES)) || (st = dout.ensure(count * ELEM_BYTES))) {
-        din.release(); dout.release();
-        return st;
-    }
-    cudaError_t e = cudaMemcpy(din.p, f, count * L * ELEM_BYTES, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
-        lat::launch_recompose(din.as<u64>(), count, (int)log2_b, (int)L, dout.as<u64>(), nullptr);
-        e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaMemcpy(out, dout.p, count * ELEM_BYTES, cudaMemcpyDeviceToHost);
-    din.release(); dout.release();
-    if (e != cudaSuccess) return fail_cuda(e, "lat_ring_gadget_recompose", __LINE__);
+    ScratchLock sc;
+    int st = sc.open(device, count * L * ELEM_BYTES, count * ELEM_BYTES);
+    if (st) return st;
+    CK(cudaMemcpyAsync(sc.at<u64>(0), f, count * L * ELEM_BYTES, cudaMemcpyHostToDevice, sc.stream()));
+    lat::launch_recompose(sc.at<u64>(0), count, (int)log2_b, (int)L, sc.at<u64>(1), sc.stream());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, sc.at<u64>(1), count * ELEM_BYTES, cudaMemcpyDeviceToHost, sc.stream()));
+    CK(cudaStreamSynchronize(sc.stream()));
     return LAT_OK;
 }
 
@@ -1054,19 +1104,15 @@ int lat_ring_icrt_dev(const uint64_t *ntt_dev, uint64_t count, uint64_t *coeff_d
 static int ring_host(const uint64_t *in, uint64_t count, uint64_t *out, int device, bool inverse) {
     if (count == 0) return LAT_OK;
     if (!in || !out) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
-    CK(cudaSetDevice(device));
-    DevBuf buf;
-    int st = buf.ensure(count * ELEM_BYTES);
+    ScratchLock sc;
+    int st = sc.open(device, count * ELEM_BYTES);
     if (st) return st;
-    cudaError_t e = cudaMemcpy(buf.p, in, count * ELEM_BYTES, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
-        if (inverse) lat::launch_icrt(buf.as<u64>(), buf.as<u64>(), count, nullptr);
-        else lat::launch_crt(buf.as<u64>(), buf.as<u64>(), count, nullptr);
-        e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaMemcpy(out, buf.p, count * ELEM_BYTES, cudaMemcpyDeviceToHost);
-    buf.release();
-    if (e != cudaSuccess) return fail_cuda(e, "lat_ring_crt/icrt", __LINE__);
+    CK(cudaMemcpyAsync(sc.at<u64>(0), in, count * ELEM_BYTES, cudaMemcpyHostToDevice, sc.stream()));
+    if (inverse) lat::launch_icrt(sc.at<u64>(0), sc.at<u64>(0), count, sc.stream());  // in place
+    else lat::launch_crt(sc.at<u64>(0), sc.at<u64>(0), count, sc.stream());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, sc.at<u64>(0), count * ELEM_BYTES, cudaMemcpyDeviceToHost, sc.stream()));
+    CK(cudaStreamSynchronize(sc.stream()));
     return LAT_OK;
 }
 int lat_ring_crt(const uint64_t *coeff, uint64_t count, uint64_t *ntt, int device) {
@@ -1081,27 +1127,18 @@ int lat_ring_gadget_decompose(const uint64_t *in, uint64_t count, uint32_t log2_
     if (count == 0) return LAT_OK;
     if (!in || !out) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
     if (log2_b < 1 || log2_b > 15 || L < 1 || L > 32) return fail(LAT_E_INVALID_ARGUMENT, "need 1<=log2_b<=15, 1<=L<=32");
-    CK(cudaSetDevice(device));
-    DevBuf din, d16, dout, dflag;
-    int st = LAT_OK;
-    int h_flag = 0;
-    cudaError_t e = cudaSuccess;
-    do {
-        if ((st = din.ensure(count * ELEM_BYTES)) || (st = d16.ensure(count * L * LAT_RING_DEGREE * sizeof(int16_t))) ||
-            (st = dout.ensure(count * L * ELEM_BYTES)) || (st = dflag.ensure(sizeof(int))))
-            break;
-        if ((e = cudaMemset(dflag.p, 0, sizeof(int))) != cudaSuccess) break;
-        if ((e = cudaMemcpy(din.p, in, count * ELEM_BYTES, cudaMemcpyHostToDevice)) != cudaSuccess) break;
-        lat::launch_witness(din.as<u64>(), count, (int)log2_b, (int)L, repr == LAT_REPR_MONTGOMERY, true,
-                            d16.as<int16_t>(), dout.as<u64>(), nullptr, nullptr, dflag.as<int>(), nullptr);
-        if ((e = cudaGetLastError()) != cudaSuccess) break;
-        if ((e = cudaMemcpy(out, dout.p, count * L * ELEM_BYTES, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
-        if ((e = cudaMemcpy(&h_flag, dflag.p, sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) break;
-    } while (0);
-    din.release(); d16.release(); dout.release(); dflag.release();
+    ScratchLock sc;
+    int st = sc.open(device, count * ELEM_BYTES, count * L * LAT_RING_DEGREE * sizeof(int16_t), count * L * ELEM_BYTES, sizeof(int));
     if (st) return st;
-    if (e != cudaSuccess) return fail_cuda(e, "lat_ring_gadget_decompose", __LINE__);
-    if (h_flag) return fail(LAT_E_DIGIT_OVERFLOW, "a coefficient needs more than L digits");
+    CK(cudaMemsetAsync(sc.at<int>(3), 0, sizeof(int), sc.stream()));
+    CK(cudaMemcpyAsync(sc.at<u64>(0), in, count * ELEM_BYTES, cudaMemcpyHostToDevice, sc.stream()));
+    lat::launch_witness(sc.at<u64>(0), count, (int)log2_b, (int)L, repr == LAT_REPR_MONTGOMERY, true, sc.at<int16_t>(1),
+                        sc.at<u64>(2), nullptr, nullptr, sc.at<int>(3), sc.stream());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, sc.at<u64>(2), count * L * ELEM_BYTES, cudaMemcpyDeviceToHost, sc.stream()));
+    CK(cudaMemcpyAsync(sc.s->h_flag, sc.at<int>(3), sizeof(int), cudaMemcpyDeviceToHost, sc.stream()));
+    CK(cudaStreamSynchronize(sc.stream()));
+    if (*sc.s->h_flag) return fail(LAT_E_DIGIT_OVERFLOW, "a coefficient needs more than L digits");
     return LAT_OK;
 }
 
@@ -1120,19 +1157,14 @@ int lat_ntt_negacyclic(const uint64_t *in, uint64_t batch, uint32_t log2_d, int 
     if (batch == 0) return LAT_OK;
     if (!in || !out) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
     if (log2_d < 1 || log2_d > LAT_NTT_MAX_LOG2_D) return fail(LAT_E_INVALID_ARGUMENT, "need 1 <= log2_d <= 14");
-    CK(cudaSetDevice(device));
     const size_t bytes = (size_t)(batch << log2_d) * sizeof(uint64_t);
-    DevBuf buf;
-    int st = buf.ensure(bytes);
+    ScratchLock sc;
+    int st = sc.open(device, bytes);
     if (st) return st;
-    cudaError_t e = cudaMemcpy(buf.p, in, bytes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
-        st = lat_ntt_negacyclic_dev(buf.as<uint64_t>(), batch, log2_d, inverse, buf.as<uint64_t>(), nullptr);
-        if (st == LAT_OK) e = cudaMemcpy(out, buf.p, bytes, cudaMemcpyDeviceToHost);  // synchronises the default stream
-    }
-    buf.release();
-    if (st) return st;
-    if (e != cudaSuccess) return fail_cuda(e, "lat_ntt_negacyclic", __LINE__);
+    CK(cudaMemcpyAsync(sc.at<u64>(0), in, bytes, cudaMemcpyHostToDevice, sc.stream()));
+    if ((st = lat_ntt_negacyclic_dev(sc.at<uint64_t>(0), batch, log2_d, inverse, sc.at<uint64_t>(0), sc.stream()))) return st;
+    CK(cudaMemcpyAsync(out, sc.at<u64>(0), bytes, cudaMemcpyDeviceToHost, sc.stream()));
+    CK(cudaStreamSynchronize(sc.stream()));
     return LAT_OK;
 }
 
@@ -1222,21 +1254,14 @@ int lat_commitment_exchange_dev(const uint64_t *partial_dev, uint64_t words, int
 int lat_commitment_sum(const uint64_t *parts, uint32_t count, uint64_t words, uint64_t *out, int device) {
     if (words == 0) return LAT_OK;
     if (!parts || !out) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
-    CK(cudaSetDevice(device));
-    DevBuf din, dout;
-    int st;
-    if ((st = din.ensure((size_t)count * words * 8)) || (st = dout.ensure(words * 8))) {
-        din.release(); dout.release();
-        return st;
-    }
-    cudaError_t e = cudaMemcpy(din.p, parts, (size_t)count * words * 8, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
-        lat::launch_commitment_sum(din.as<u64>(), count, words, dout.as<u64>(), nullptr);
-        e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaMemcpy(out, dout.p, words * 8, cudaMemcpyDeviceToHost);
-    din.release(); dout.release();
-    if (e != cudaSuccess) return fail_cuda(e, "lat_commitment_sum", __LINE__);
+    ScratchLock sc;
+    int st = sc.open(device, (size_t)count * words * 8, words * 8);
+    if (st) return st;
+    CK(cudaMemcpyAsync(sc.at<u64>(0), parts, (size_t)count * words * 8, cudaMemcpyHostToDevice, sc.stream()));
+    lat::launch_commitment_sum(sc.at<u64>(0), count, words, sc.at<u64>(1), sc.stream());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, sc.at<u64>(1), words * 8, cudaMemcpyDeviceToHost, sc.stream()));
+    CK(cudaStreamSynchronize(sc.stream()));
     return LAT_OK;
 }
 

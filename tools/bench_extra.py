@@ -87,6 +87,11 @@ out["fold_side"] = {"what": "decompose_witness + commit_witnesses for one side: 
                     "imad_wide_per_s": wide / (mac_ms / mac_n * 1e-3), "imad_wide_peak_per_s": 9.154e12,
                     "imad_pipe_frac": wide / (mac_ms / mac_n * 1e-3) / 9.154e12}
 print(out["fold_side"], flush=True)
+# pack + planes kernels alone (no matrix commits): the decomposition's own cost
+t_planes = timeit(lambda: L.lat_ajtai_decompose_commit_dev(scheme._h, fc_dev.data_ptr(), N, None, None, None, None), reps=10)
+out["planes_only"] = {"what": "pack_coeff + planes_kernel (15 planes, extended layout, 569 MB written)", "ms": t_planes,
+                      "GBps_written": K * N * 48 * 8 / t_planes / 1e6}
+print(out["planes_only"], flush=True)
 # 28-witness batch through commit_ntt_batch (both sides in one launch)
 fs = torch.from_numpy(rng.integers(0, 2**63, size=(28, N, 24), dtype=np.int64)).cuda()
 cms28 = torch.empty((28, KAPPA, 24), dtype=torch.int64, device="cuda")
@@ -130,4 +135,4 @@ out["commit_n_2_20"] = {"what": "commit_ntt, kappa = 32, n = 2^20, one GPU (A = 
                         "hbm_frac": KAPPA * N20 * 192 / (mac_ms / mac_n) / 1e6 / 6548.8}
 print(out["commit_n_2_20"], flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/extra.json", "w"), indent=1)
+json.dump(out, open(os.environ.get("EXTRA_OUT", "gpurun_out/extra.json"), "w"), indent=1)
