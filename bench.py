@@ -486,8 +486,9 @@ def run_single(args, ctx):
         scheme_o.close()
 
     # -- the whole fold step and the configs[4] commit on this one GPU ----------------------------------------------------
-    fold_step = None if args.quick else fold_step_leg(args, ctx, LB, scheme, eng, mont, w_canon)
+    # (the bandwidth-bound n = 2^20 commit first: the multiply-bound fold step heats the board into its power cap)
     big = None if args.quick else single_gpu_2_20_leg(args, ctx, LB)
+    fold_step = None if args.quick else fold_step_leg(args, ctx, LB, scheme, eng, mont, w_canon)
 
     # -- CPU baseline beside it: the oracle port on the host cores, bounded sample; parity of the timed results ------------
     cpu_baseline, parity = None, None

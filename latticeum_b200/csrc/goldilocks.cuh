@@ -200,9 +200,12 @@ __device__ __forceinline__ void add65(u64 a, u64 b, u64 &s, u32 &c) {
         : "=l"(s), "=r"(c)
         : "l"(a), "l"(b));
 }
-// acc += (s + c * 2^64) * y,  c in {0, 1}
+// acc += (s + c * 2^64) * y,  c in {0, 1}.  (A predicated add.cc/addc pair instead of select-then-add looks cheaper in
+// PTX, but ptxas then merges the guarded results with extra IMAD.MOV / IMAD.X: 1019 instead of 951 instructions in the
+// unrolled tile loop -- -DLAT_MAC65_PREDICATED keeps that variant for the record.)
 __device__ __forceinline__ void mac65(WideAcc &A, u64 s, u32 c, u64 y) {
     A.mac(s, y);
+#ifndef LAT_MAC65_PREDICATED
     asm("{\n\t"
         ".reg .pred p;\n\t"
         ".reg .u64 ym;\n\t"
@@ -213,6 +216,16 @@ __device__ __forceinline__ void mac65(WideAcc &A, u64 s, u32 c, u64 y) {
         "}"
         : "+l"(A.c2.acc), "+r"(A.c2.ov)
         : "r"(c), "l"(y));
+#else
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.u32 p, %2, 0;\n\t"
+        "@p add.cc.u64 %0, %0, %3;\n\t"
+        "@p addc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "+l"(A.c2.acc), "+r"(A.c2.ov)
+        : "r"(c), "l"(y));
+#endif
 }
 
 // Matrix-side Karatsuba pre-addition folded back to 64 bits: a + b = s + c * 2^64 and 2^64 = 2^32 - 1 (mod q), so
