@@ -16,7 +16,7 @@
 // Same values as ring24.cuh, bit for bit: all maps are exact.
 //
 // The header is self-contained and also compiles as plain C++ (the carry chains fall back to 64-bit arithmetic), which
-// is how tests/test_ring96_cpu.py checks the network against the oracle without a GPU.
+// is how tests/test_ring96_cpu.py checks the network on the CPU.
 #pragma once
 #include <cstdint>
 
