@@ -32,6 +32,7 @@
 #include "kernels.h"
 #include "ring24.cuh"
 #include "spin.cuh"
+#include "witness_cta.cuh"
 
 namespace lat {
 using gl::u32;
@@ -216,11 +217,19 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define TRACE(k)
 #endif
 
-template <int PT, int RG>
+// FUSED (0 = off, 1 = canonical limbs, 2 = Montgomery limbs; PT = 1 and one row block only): the launch also runs
+// Witness::from_w_ccs.  Every CTA first transforms the w_ccs elements behind ITS OWN column range (witness_cta.cuh) --
+// reading them in place over PCIe when they live in mapped host memory -- writes the digits and the extended witness, and
+// then streams its tiles as usual.  No separate witness kernel, no grid-wide dependency between the two stages: a CTA
+// whose input has arrived starts on the matrix while its neighbours still wait for theirs, so the upload of a
+// host-buffer call overlaps the matrix stream instead of preceding it.
+template <int PT, int RG, int FUSED>
 __global__ void __launch_bounds__(MacGeo<PT, RG>::THREADS, MacGeo<PT, RG>::MIN_CTAS)
 mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__ Fx, u64 f_stride, uint32_t planes,
-           uint32_t stages, u64 *__restrict__ ws, u64 *__restrict__ cms, uint32_t dependent_launch, MacReport report) {
+           uint32_t stages, u64 *__restrict__ ws, u64 *__restrict__ cms, uint32_t dependent_launch, MacReport report,
+           FusedWitness fw) {
     using G = MacGeo<PT, RG>;
+    static_assert(!FUSED || PT == 1, "the fused launch commits one witness");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // after the stages: [full mbarrier x stages][release counter x stages]
     u64 *bars = reinterpret_cast<u64 *>(smem_raw + (size_t)stages * G::STAGE_BYTES);
@@ -291,15 +300,40 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
         // still draining.  The matrix does not depend on it, so the first tiles' matrix halves are requested at
         // once; only the witness halves wait for the producer grid to complete.
         const u32 pre = min(stages, my_tiles);
-        for (u32 nt = 0; nt < pre; ++nt) issue_matrix(nt, nt);
-        if (dependent_launch) asm volatile("griddepcontrol.wait;" ::: "memory");
-        // Only now may the kernel behind this one start (the next step's witness kernel, if the caller allows the
-        // overlap): once every CTA has passed its wait the producer grid -- and through its block 0 the previous
-        // commitment -- is complete, so that kernel can reuse the buffers of two steps back.
-        asm volatile("griddepcontrol.launch_dependents;");
-        for (u32 nt = 0; nt < pre; ++nt) issue_witness(nt, nt);
+        if constexpr (FUSED) {
+            // the last stage doubles as the transform's digit tile until the tile loop starts: prefetch into the others
+            for (u32 nt = 0; nt + 1 < pre; ++nt) issue_matrix(nt, nt);
+            asm volatile("griddepcontrol.launch_dependents;");
+        } else {
+            for (u32 nt = 0; nt < pre; ++nt) issue_matrix(nt, nt);
+            if (dependent_launch) asm volatile("griddepcontrol.wait;" ::: "memory");
+            // Only now may the kernel behind this one start (the next step's witness kernel, if the caller allows the
+            // overlap): once every CTA has passed its wait the producer grid -- and through its block 0 the previous
+            // commitment -- is complete, so that kernel can reuse the buffers of two steps back.
+            asm volatile("griddepcontrol.launch_dependents;");
+            for (u32 nt = 0; nt < pre; ++nt) issue_witness(nt, nt);
+        }
     }
     __syncthreads();
+    if constexpr (FUSED) {
+        if (fw.ready_flag) {  // a ticketed step: the upload runs on a copy engine, its ticket lands behind the data
+            if (threadIdx.x == 0) spin_until_equals(fw.ready_flag, fw.ready_value, fw.guard, SPIN_UPLOAD_TICKET, fw.ready_value);
+            __syncthreads();
+        }
+        const u64 col0 = t_begin * G::TJ, col1 = min(lay.n, t_end * G::TJ);
+        int16_t *tile = reinterpret_cast<int16_t *>(smem_raw + (size_t)(stages - 1) * G::STAGE_BYTES);
+        cta_witness<FUSED == 2>(fw.w, fw.w_len, fw.log2b, fw.L, col0, col1, fw.f16, fw.fx, fw.flag, tile);
+        // The extended witness was written through the generic proxy and is read back by bulk copies (async proxy), and
+        // the digit tile's stage is about to be overwritten by one: order both, on every writing thread, before the
+        // barrier behind which thread 0 issues the copies.
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const u32 pre = min(stages, my_tiles);
+            if (pre) issue_matrix(pre - 1, pre - 1);
+            for (u32 nt = 0; nt < pre; ++nt) issue_witness(nt, nt);
+        }
+    }
 
     const u32 rgi = warp / G::CG, cgi = warp % G::CG;
     const u32 il = rgi * 4 + (lane >> 3), s = lane & 7;
@@ -362,6 +396,11 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
     // its 32-bit halves and added with two 64-bit REDs into ws[2*idx], ws[2*idx+1] (a few hundred addends cannot
     // overflow); the last CTA to finish folds lo + 2^32 hi mod q into cms and leaves the workspace zeroed for the
     // next launch.  No second kernel, no partials round trip.
+    if constexpr (FUSED) {
+        // launched beside the tail of the previous commitment (programmatic launch): its workspace sums, its counter and
+        // its output must be complete before this grid adds to them
+        if (dependent_launch) asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     const u32 row = rbk * G::RB + il;
     if (row < lay.kappa) {
 #pragma unroll
@@ -456,26 +495,27 @@ MacPlan plan_mac(const MatLayout &lay, uint32_t planes, int sm_count) {
     return m;
 }
 
-template <int PT, int RG>
+template <int PT, int RG, int FUSED>
 static void launch_mac_t(dim3 grid, const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes,
-                         const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream, bool pdl, const MacReport &report) {
+                         const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream, bool pdl, const MacReport &report,
+                         const FusedWitness &fw) {
     // function attributes are per device: a process may hold handles on several GPUs
     static bool attr_set_on[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     bool &attr_set = attr_set_on[dev & 63];
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mac_kernel<PT, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // minus the static bytes
-        if (e != cudaSuccess) fprintf(stderr, "lattice_ajtai: cudaFuncSetAttribute(mac_kernel<%d,%d>): %s\n", PT, RG, cudaGetErrorString(e));
+        cudaError_t e = cudaFuncSetAttribute(mac_kernel<PT, RG, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // minus the static bytes
+        if (e != cudaSuccess) fprintf(stderr, "lattice_ajtai: cudaFuncSetAttribute(mac_kernel<%d,%d,%d>): %s\n", PT, RG, FUSED, cudaGetErrorString(e));
         attr_set = true;
     }
     if (getenv("LAT_DEBUG")) {
         cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, mac_kernel<PT, RG>);
+        cudaFuncGetAttributes(&fa, mac_kernel<PT, RG, FUSED>);
         int occ = -1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mac_kernel<PT, RG>, MacGeo<PT, RG>::THREADS, plan.smem_bytes);
-        fprintf(stderr, "mac_kernel<%d,%d>: grid=(%u,%u,%u) block=%d smem=%zu stages=%u regs=%d maxDyn=%d static=%zu occ=%d maxThreads=%d\n",
-                PT, RG, grid.x, grid.y, grid.z, MacGeo<PT, RG>::THREADS, plan.smem_bytes, plan.stages, fa.numRegs,
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mac_kernel<PT, RG, FUSED>, MacGeo<PT, RG>::THREADS, plan.smem_bytes);
+        fprintf(stderr, "mac_kernel<%d,%d,%d>: grid=(%u,%u,%u) block=%d smem=%zu stages=%u regs=%d maxDyn=%d static=%zu occ=%d maxThreads=%d\n",
+                PT, RG, FUSED, grid.x, grid.y, grid.z, MacGeo<PT, RG>::THREADS, plan.smem_bytes, plan.stages, fa.numRegs,
                 fa.maxDynamicSharedSizeBytes, fa.sharedSizeBytes, occ, fa.maxThreadsPerBlock);
     }
     cudaLaunchConfig_t cfg = {};
@@ -488,22 +528,26 @@ static void launch_mac_t(dim3 grid, const u64 *A_dev, const MatLayout &lay, cons
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, mac_kernel<PT, RG>, A_dev, lay, Fx, f_stride, planes, plan.stages, workspace, cms, (uint32_t)(pdl ? 1 : 0), report);
+    cudaLaunchKernelEx(&cfg, mac_kernel<PT, RG, FUSED>, A_dev, lay, Fx, f_stride, planes, plan.stages, workspace, cms,
+                       (uint32_t)(pdl ? 1 : 0), report, fw);
 }
 
-template <int PT>
+template <int PT, int FUSED>
 static void launch_mac_pt(dim3 grid, const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes,
-                          const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream, bool pdl, const MacReport &report) {
+                          const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream, bool pdl, const MacReport &report,
+                          const FusedWitness &fw) {
+#define LAT_MAC_CASE(rg) launch_mac_t<PT, rg, FUSED>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report, fw)
     switch (lay.rg) {
-        case 1: launch_mac_t<PT, 1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
-        case 2: launch_mac_t<PT, 2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
-        case 3: launch_mac_t<PT, 3>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
-        case 4: launch_mac_t<PT, 4>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
-        case 5: launch_mac_t<PT, 5>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
-        case 6: launch_mac_t<PT, 6>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
-        case 7: launch_mac_t<PT, 7>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
-        default: launch_mac_t<PT, 8>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 1: LAT_MAC_CASE(1); break;
+        case 2: LAT_MAC_CASE(2); break;
+        case 3: LAT_MAC_CASE(3); break;
+        case 4: LAT_MAC_CASE(4); break;
+        case 5: LAT_MAC_CASE(5); break;
+        case 6: LAT_MAC_CASE(6); break;
+        case 7: LAT_MAC_CASE(7); break;
+        default: LAT_MAC_CASE(8); break;
     }
+#undef LAT_MAC_CASE
 }
 
 void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes, const MacPlan &plan,
@@ -514,8 +558,23 @@ void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_str
     static const bool pdl_off = getenv("LAT_NO_PDL") != nullptr;
     const bool pdl = !ev_begin && !pdl_off;
     if (ev_begin) cudaEventRecord(ev_begin, stream);
-    if (plan.pt == 1) launch_mac_pt<1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report);
-    else launch_mac_pt<2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report);
+    const FusedWitness none{};
+    if (plan.pt == 1) launch_mac_pt<1, 0>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report, none);
+    else launch_mac_pt<2, 0>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report, none);
+    if (ev_end) cudaEventRecord(ev_end, stream);
+}
+
+// Witness::from_w_ccs + commit in ONE launch (see mac_kernel, FUSED).  chained: the previous kernel in the stream is this
+// handle's previous commitment and this launch may start beside its tail (it writes the OTHER witness buffer).
+void launch_witness_mac(const u64 *A_dev, const MatLayout &lay, const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream,
+                        bool mont, bool chained, const FusedWitness &fw, cudaEvent_t ev_begin, cudaEvent_t ev_end,
+                        const MacReport &report) {
+    dim3 grid(plan.grid_x, 1, 1);
+    static const bool pdl_off = getenv("LAT_NO_PDL") != nullptr;
+    const bool pdl = chained && !ev_begin && !pdl_off;
+    if (ev_begin) cudaEventRecord(ev_begin, stream);
+    if (mont) launch_mac_pt<1, 2>(grid, A_dev, lay, fw.fx, lay.n, 1, plan, workspace, cms, stream, pdl, report, fw);
+    else launch_mac_pt<1, 1>(grid, A_dev, lay, fw.fx, lay.n, 1, plan, workspace, cms, stream, pdl, report, fw);
     if (ev_end) cudaEventRecord(ev_end, stream);
 }
 
