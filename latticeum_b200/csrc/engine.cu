@@ -324,7 +324,12 @@ struct lat_ajtai {
         fw.ready_value = ready_value;
         guard.timeout_ns = spin_timeout_ns();
         fw.guard = guard;
-        lat::launch_witness_mac(A.as<u64>(), lay, plan, ws.as<u64>(), cm_dev, stream, mont, chained, fw, e0, e1, report);
+        static const bool no_pipelined = getenv("LAT_NO_WMAC") != nullptr;
+        if (lay.rg == 8 && L <= 8 && !no_pipelined)  // the zkVM's shape: interleaved jobs, transform inside the tile loop
+            lat::launch_step_commit(A.as<u64>(), lay, (uint32_t)(2 * sm_count), ws.as<u64>(), cm_dev, stream, mont, chained, fw, e0, e1,
+                                    report);
+        else
+            lat::launch_witness_mac(A.as<u64>(), lay, plan, ws.as<u64>(), cm_dev, stream, mont, chained, fw, e0, e1, report);
         CK(cudaGetLastError());
         has_resident = true;
         last_mac_src = fxp;

@@ -125,6 +125,13 @@ void launch_witness_mac(const u64 *A_dev, const MatLayout &lay, const MacPlan &p
                         bool mont, bool chained, const FusedWitness &fw, cudaEvent_t ev_begin = nullptr,
                         cudaEvent_t ev_end = nullptr, const MacReport &report = MacReport());
 
+// The pipelined form of the same (mac_kernels.cu, wmac_kernel): column ownership interleaved over the CTAs in jobs of L
+// tiles, each job's elements transformed right before its tiles are requested, w_ccs fetched two jobs ahead by bulk
+// copies -- the upload of a host-buffer call overlaps the matrix stream.  kappa in 29..32 (RG = 8) and L <= 8 only.
+void launch_step_commit(const u64 *A_dev, const MatLayout &lay, uint32_t grid_x, u64 *workspace, u64 *cms, cudaStream_t stream,
+                        bool mont, bool chained, const FusedWitness &fw, cudaEvent_t ev_begin = nullptr,
+                        cudaEvent_t ev_end = nullptr, const MacReport &report = MacReport());
+
 // cms[0] = cm - sum_{k=1..K-1} 2^k cms[k]      (LF/nifs/decomposition.rs:189-197)
 void launch_y0(const u64 *cm, u64 *cms, uint32_t K, uint32_t kappa, cudaStream_t stream);
 

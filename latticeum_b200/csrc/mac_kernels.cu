@@ -578,6 +578,325 @@ void launch_witness_mac(const u64 *A_dev, const MatLayout &lay, const MacPlan &p
     if (ev_end) cudaEventRecord(ev_end, stream);
 }
 
+// ---- Witness::from_w_ccs + commit as one PIPELINED launch (kappa in 29..32: RG = 8, one row block) ----------------------------
+// The tile loop of mac_kernel<1,8>, with the witness transform folded in and the column ownership interleaved:
+//   * Work is cut into JOBS of L consecutive tiles = TJ * L columns = TJ whole w_ccs elements.  Job i of CTA c is job number
+//     i * gridDim.x + c of the vector, so all CTAs walk the vector front to back TOGETHER; what is left after the last full
+//     round is dealt out in tiles (jobs of 1..L tiles whose element range may overlap a neighbour's by one element: the
+//     transform is per element and every CTA writes only its own columns).
+//   * Before a job's first tile is requested, the CTA transforms the job's w_ccs elements -- iCRT, digits, CRT of the
+//     limbs -- and writes the digits and the extended witness rows (they stay in L2 until its own bulk copies fetch them a
+//     few microseconds later).  The elements themselves come in through a two-slot shared-memory ring filled by bulk
+//     copies TWO jobs ahead, straight from page-locked host memory when that is where w_ccs lives.
+// Hence a host-buffer call needs the first 1/9th of the upload before the matrix stream starts, not all of it: the PCIe
+// transfer (76 us at the zkVM's size) runs beside the 607 MB matrix stream instead of in front of it.  Device-resident
+// calls gain what the separate witness kernel cost (its launch, its tail, the grid-wide dependency): the two CTAs of an SM
+// are rarely in their transform at the same time, so one CTA's transform runs in the issue slots the other's wait leaves.
+struct StepJobs {   // the jobs of one CTA, in the order it runs them
+    u32 grid, cta, L, rounds_full;
+    u64 ntiles, left_base, left_off;  // first tile of the leftover region, this CTA's offset into it
+    u32 left_cnt;
+    __device__ __forceinline__ u32 njobs() const { return rounds_full + (left_cnt ? 1u : 0u); }
+    __device__ __forceinline__ u64 tile0(u32 k) const { return k < rounds_full ? ((u64)k * grid + cta) * L : left_base + left_off; }
+    __device__ __forceinline__ u32 count(u32 k) const { return k < rounds_full ? L : left_cnt; }
+    __device__ __forceinline__ u32 total() const { return rounds_full * L + left_cnt; }
+};
+__device__ __forceinline__ StepJobs make_jobs(u64 ntiles, u32 L, u32 grid, u32 cta) {
+    StepJobs j;
+    j.grid = grid; j.cta = cta; j.L = L; j.ntiles = ntiles;
+    j.rounds_full = (u32)(ntiles / ((u64)grid * L));
+    j.left_base = (u64)j.rounds_full * grid * L;
+    const u64 left = ntiles - j.left_base;          // < grid * L tiles
+    const u32 base = (u32)(left / grid), rem = (u32)(left % grid);
+    j.left_cnt = base + (cta < rem ? 1u : 0u);
+    j.left_off = (u64)cta * base + min(cta, rem);
+    return j;
+}
+
+constexpr int WM_TJ = geo_tj(8), WM_RB = 32, WM_THREADS = 256, WM_STAGES = 2;
+constexpr u32 WM_TILE_ELEMS = WM_TJ * 3 * WM_RB * 8, WM_TILE_BYTES = WM_TILE_ELEMS * 8, WM_F_BYTES = WM_TJ * FX * 8;
+constexpr u32 WM_STAGE_BYTES = WM_TILE_BYTES + WM_F_BYTES;
+constexpr int WM_MAX_L = 8;
+constexpr u32 WM_PIECE_ELEMS = WM_TJ + 2;                              // w_ccs elements behind one job, worst alignment
+constexpr u32 WM_PIECE_BYTES = WM_PIECE_ELEMS * ring::D * 8;           // 1920
+constexpr u32 WM_DIGIT_BYTES = WM_PIECE_ELEMS * WM_MAX_L * ring::D * 2;  // 3840
+constexpr u32 WM_SMEM = WM_STAGES * WM_STAGE_BYTES + 2 * WM_PIECE_BYTES + WM_DIGIT_BYTES + 64;
+
+template <bool MONT>
+__global__ void __launch_bounds__(WM_THREADS, 2)
+wmac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, u64 *__restrict__ ws, u64 *__restrict__ cms, uint32_t dependent_launch,
+            MacReport report, FusedWitness fw) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *wring = smem_raw + WM_STAGES * WM_STAGE_BYTES;
+    int16_t *dtile = reinterpret_cast<int16_t *>(wring + 2 * WM_PIECE_BYTES);
+    u64 *bars = reinterpret_cast<u64 *>(wring + 2 * WM_PIECE_BYTES + WM_DIGIT_BYTES);  // [tile full x2][piece full x2]
+    u64 *wbar = bars + WM_STAGES;
+    u32 *released = reinterpret_cast<u32 *>(wbar + 2);
+
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 L = (u32)fw.L;
+    const StepJobs jobs = make_jobs(lay.ntiles, L, gridDim.x, blockIdx.x);
+    const u32 my_tiles = jobs.total(), njobs = jobs.njobs();
+    TRACE(0);
+
+    // flattened tile t of this CTA -> tile index of the matrix
+    auto tile_of = [&](u32 t) -> u64 {
+        const u32 k = t / L;  // full-round jobs have exactly L tiles, the leftover job comes last
+        return jobs.tile0(k) + (t - k * L);
+    };
+    auto witness_bytes = [&](u64 tile) { return (u32)min((u64)WM_TJ, lay.n - tile * WM_TJ) * FX * 8; };
+    auto issue_matrix = [&](u32 t, u32 st) {
+        const u64 tile = tile_of(t);
+        mbar_arrive_expect_tx(&bars[st], WM_TILE_BYTES + witness_bytes(tile));
+#ifndef LAT_NO_L2_HINT
+        tma_bulk_g2s_hint(smem_raw + (size_t)st * WM_STAGE_BYTES, A_dev + tile * WM_TILE_ELEMS, WM_TILE_BYTES, &bars[st], L2_EVICT_FIRST);
+#else
+        tma_bulk_g2s(smem_raw + (size_t)st * WM_STAGE_BYTES, A_dev + tile * WM_TILE_ELEMS, WM_TILE_BYTES, &bars[st]);
+#endif
+    };
+    auto issue_witness = [&](u32 t, u32 st) {
+        const u64 tile = tile_of(t);
+        tma_bulk_g2s(smem_raw + (size_t)st * WM_STAGE_BYTES + WM_TILE_BYTES, fw.fx + tile * WM_TJ * FX, witness_bytes(tile), &bars[st]);
+    };
+    // the w_ccs elements behind job k: [e0, e1)
+    auto job_elems = [&](u32 k, u64 &e0, u64 &e1) {
+        const u64 c0 = jobs.tile0(k) * WM_TJ, c1 = min(lay.n, (jobs.tile0(k) + jobs.count(k)) * WM_TJ);
+        e0 = c0 / L;
+        e1 = (c1 + L - 1) / L;
+    };
+    auto issue_piece = [&](u32 k) {  // one thread
+        u64 e0, e1;
+        job_elems(k, e0, e1);
+        const u32 bytes = (u32)(e1 - e0) * ring::D * 8;
+        mbar_arrive_expect_tx(&wbar[k & 1], bytes);
+        tma_bulk_g2s(wring + (k & 1) * WM_PIECE_BYTES, fw.w + e0 * ring::D, bytes, &wbar[k & 1]);
+    };
+
+    if (threadIdx.x == 0) {
+        for (u32 st = 0; st < WM_STAGES; ++st) {
+            mbar_init(&bars[st], 1);
+            mbar_init(&wbar[st], 1);
+            released[st] = 0;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (u32 t = 0; t < min((u32)WM_STAGES, my_tiles); ++t) issue_matrix(t, t);  // the matrix does not wait for anything
+        asm volatile("griddepcontrol.launch_dependents;");
+        if (fw.ready_flag)  // a ticketed step: the upload runs on a copy engine, its ticket lands behind the data
+            spin_until_equals(fw.ready_flag, fw.ready_value, fw.guard, SPIN_UPLOAD_TICKET, fw.ready_value);
+        for (u32 k = 0; k < min(2u, njobs); ++k) issue_piece(k);
+    }
+    __syncthreads();
+
+    // ---- the transform of one job (all threads; ends with the bulk-copy proxy fence + barrier) ----
+    const ring8::Twiddles tw = ring8::make_twiddles(threadIdx.x & 7);
+    const u64 Bd = 1ull << fw.log2b, halfB = Bd >> 1;
+    auto transform = [&](u32 k) {
+        u64 e0, e1;
+        job_elems(k, e0, e1);
+        const u32 ne = (u32)(e1 - e0);
+        const u64 c0 = jobs.tile0(k) * WM_TJ, c1 = min(lay.n, (jobs.tile0(k) + jobs.count(k)) * WM_TJ);
+        mbar_wait(&wbar[k & 1], (k >> 1) & 1);
+        // phase A: eight lanes per element; warps without a valid element skip (shuffles stay inside an octet's warp)
+        const u32 sl = threadIdx.x & 7, oct = threadIdx.x >> 3;
+        if ((oct & ~3u) < ne) {  // this warp's first octet is in range: the whole warp takes part
+            const bool valid = oct < ne;
+            const u64 *p = reinterpret_cast<const u64 *>(wring + (k & 1) * WM_PIECE_BYTES) + (valid ? oct : 0) * ring::D + 3 * sl;
+            u64 c[3] = {p[0], p[1], p[2]};
+            ring8::icrt8(c, tw);
+            bool negative[3];
+            u64 m[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                if constexpr (MONT) c[q] = gl::from_mont(c[q]);
+                ring::signed_rep(c[q], negative[q], m[q]);
+            }
+            int16_t *trow = dtile + (valid ? oct : 0) * (L * ring::D) + 3 * sl;
+            for (u32 l = 0; l < L; ++l) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    u64 rem = m[q] & (Bd - 1);
+                    m[q] >>= fw.log2b;
+                    int dg = (int)rem;
+                    if (rem > halfB) {  // |rem| == b/2 is kept (balanced_decomposition/mod.rs:79)
+                        dg -= (int)Bd;
+                        m[q] += 1;
+                    }
+                    if (negative[q]) dg = -dg;
+                    if (valid) trow[l * ring::D + q] = (int16_t)dg;
+                }
+            }
+            if (valid && (m[0] | m[1] | m[2])) atomicOr(fw.flag, 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && k + 2 < njobs) issue_piece(k + 2);  // the slot is free again
+        const u64 row0 = e0 * L;
+        const u32 nrows = ne * L;
+        {   // the resident int16 digits
+            const uint4 *src = reinterpret_cast<const uint4 *>(dtile);
+            uint4 *dst = reinterpret_cast<uint4 *>(fw.f16 + row0 * ring::D);
+            for (u32 u = threadIdx.x; u < nrows * 3; u += WM_THREADS) {
+                const u64 row = row0 + u / 3;
+                if (row >= c0 && row < c1) dst[u] = src[u];
+            }
+        }
+        // phase B: one thread per limb element of [c0, c1)
+        if (threadIdx.x < nrows) {
+            const u64 row = row0 + threadIdx.x;
+            if (row >= c0 && row < c1) {
+                int d[ring::D];
+                load_i16x24_cta(dtile + threadIdx.x * ring::D, d);
+                u64 x[ring::D];
+                r96::crt24_small<MONT>(d, x);
+                u64 *o = fw.fx + row * FX;
+#pragma unroll
+                for (int s2 = 0; s2 < ring::NSLOT; s2 += 2) {
+                    const u64 a0 = x[3 * s2], a1 = x[3 * s2 + 1], a2 = x[3 * s2 + 2];
+                    const u64 b0 = x[3 * s2 + 3], b1 = x[3 * s2 + 4], b2 = x[3 * s2 + 5];
+                    st256(o + s2 * 6, a0, a1, a2, gl::add_lazy(a0, a1));
+                    st256(o + s2 * 6 + 4, gl::add_lazy(a0, a2), gl::add_lazy(a1, a2), b0, b1);
+                    st256(o + s2 * 6 + 8, b2, gl::add_lazy(b0, b1), gl::add_lazy(b0, b2), gl::add_lazy(b1, b2));
+                }
+            }
+        }
+        // the rows were written through the generic proxy and are fetched by bulk copies (async proxy) of THIS CTA
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __syncthreads();
+    };
+
+    u32 transformed = 0;  // jobs [0, transformed) have their witness rows in place
+    auto ensure = [&](u32 t) {  // ... up to the job of flattened tile t
+        const u32 need = min(t / L, njobs - 1) + 1;
+        while (transformed < need) transform(transformed++);
+    };
+    if (my_tiles) {
+        ensure(min((u32)WM_STAGES, my_tiles) - 1);
+        if (threadIdx.x == 0)
+            for (u32 t = 0; t < min((u32)WM_STAGES, my_tiles); ++t) issue_witness(t, t);
+    }
+
+    const u32 il = warp * 4 + (lane >> 3), s = lane & 7;  // RG = 8, CG = 1: warp w owns rows 4w .. 4w+3
+    gl::Fq3Acc acc;
+    acc.clear();
+    u32 st = 0, ph = 0;
+    bool ready = false;
+    for (u32 t = 0; t < my_tiles; ++t) {
+        // the tile requested at the end of this iteration is t + 2: its job must have been transformed by then
+        if (t + WM_STAGES < my_tiles && (t + WM_STAGES) / L >= transformed) {
+            ensure(t + WM_STAGES);
+            ready = false;
+        }
+        if (!ready) mbar_wait(&bars[st], ph);
+#ifdef LAT_MAC_TRACE
+        if (t == 0) TRACE(1);
+#endif
+        const u64 *sa = reinterpret_cast<const u64 *>(smem_raw + (size_t)st * WM_STAGE_BYTES) + il * 8 + s;
+        const ulonglong2 *sf = reinterpret_cast<const ulonglong2 *>(smem_raw + (size_t)st * WM_STAGE_BYTES + WM_TILE_BYTES) + s * 3;
+        u32 st_n = st + 1, ph_n = ph;
+        if (st_n == WM_STAGES) {
+            st_n = 0;
+            ph_n ^= 1;
+        }
+        ready = (t + 1 < my_tiles) && mbar_test(&bars[st_n], ph_n);
+#pragma unroll
+        for (int jj = 0; jj < WM_TJ; ++jj) {
+            const u64 *pa = sa + jj * (3 * WM_RB * 8);
+            const u64 a0 = pa[0], a1 = pa[WM_RB * 8], a2 = pa[2 * WM_RB * 8];
+            const ulonglong2 x = sf[jj * (FX / 2)], y = sf[jj * (FX / 2) + 1], z = sf[jj * (FX / 2) + 2];
+            acc.mac(a0, a1, a2, x.x, x.y, y.x, y.y, z.x, z.y);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (atomicAdd(&released[st], 1u) == WM_THREADS / 32 - 1) {
+                released[st] = 0;
+                if (t + WM_STAGES < my_tiles) {
+                    issue_matrix(t + WM_STAGES, st);
+                    issue_witness(t + WM_STAGES, st);
+                }
+            }
+        }
+        st = st_n;
+        ph = ph_n;
+    }
+    TRACE(2);
+
+    // ===== epilogue: as mac_kernel ===============================================================================
+    if (dependent_launch) asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous commitment's sums and output
+    if (il < lay.kappa) {
+        u64 c[3];
+        acc.finish(c[0], c[1], c[2]);
+        u64 *dst = ws + 2 * ((u64)il * ring::D + s * 3);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            atomicAdd(reinterpret_cast<unsigned long long *>(dst + 2 * q), c[q] & 0xFFFFFFFFull);
+            atomicAdd(reinterpret_cast<unsigned long long *>(dst + 2 * q + 1), c[q] >> 32);
+        }
+    }
+    __shared__ u32 s_last;
+    const u64 nout = (u64)lay.kappa * ring::D;
+    u64 *counter = ws + 2 * nout;
+    __threadfence();
+    __syncthreads();
+    TRACE(3);
+    if (threadIdx.x == 0)
+        s_last = (atomicAdd(reinterpret_cast<unsigned long long *>(counter), 1ull) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        for (u64 i = threadIdx.x; i < nout; i += blockDim.x) {
+            const u64 lo = __ldcg(ws + 2 * i), hi = __ldcg(ws + 2 * i + 1);
+            const u64 v_lo = lo + (hi << 32);
+            const u64 v_hi = (hi >> 32) + (v_lo < lo ? 1ull : 0ull);
+            const u64 v = gl::reduce128(v_lo, v_hi);
+            cms[i] = v;
+            if (report.cm_host) report.cm_host[i] = v;
+            ws[2 * i] = 0;
+            ws[2 * i + 1] = 0;
+        }
+        if (threadIdx.x == 0) *counter = 0;
+        if (threadIdx.x == 0 && report.flag_dev) {
+            *report.flag_host = *reinterpret_cast<volatile int *>(report.flag_dev);
+            *report.flag_dev = 0;
+        }
+        if (report.done_host) {
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0)
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(report.done_host), "l"(report.done_value) : "memory");
+        }
+    }
+    TRACE(4);
+}
+
+// kappa in 29..32 only (RG = 8, one row block); the caller checks.  grid_x CTAs, two per SM.
+void launch_step_commit(const u64 *A_dev, const MatLayout &lay, uint32_t grid_x, u64 *workspace, u64 *cms, cudaStream_t stream,
+                        bool mont, bool chained, const FusedWitness &fw, cudaEvent_t ev_begin, cudaEvent_t ev_end,
+                        const MacReport &report) {
+    static bool attr_set_on[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set_on[dev & 63]) {
+        cudaFuncSetAttribute(wmac_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WM_SMEM);
+        cudaFuncSetAttribute(wmac_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WM_SMEM);
+        attr_set_on[dev & 63] = true;
+    }
+    static const bool pdl_off = getenv("LAT_NO_PDL") != nullptr;
+    const bool pdl = chained && !ev_begin && !pdl_off;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid_x);
+    cfg.blockDim = dim3(WM_THREADS);
+    cfg.dynamicSmemBytes = WM_SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    if (ev_begin) cudaEventRecord(ev_begin, stream);
+    if (mont) cudaLaunchKernelEx(&cfg, wmac_kernel<true>, A_dev, lay, workspace, cms, (uint32_t)(pdl ? 1 : 0), report, fw);
+    else cudaLaunchKernelEx(&cfg, wmac_kernel<false>, A_dev, lay, workspace, cms, (uint32_t)(pdl ? 1 : 0), report, fw);
+    if (ev_end) cudaEventRecord(ev_end, stream);
+}
+
 // cms[0] = cm - sum_{k>=1} 2^k cms[k]: Horner from the top plane, (acc + y_k) * 2.  decomposition.rs:189-197
 __global__ void __launch_bounds__(256)
 y0_kernel(const u64 *__restrict__ cm, u64 *__restrict__ cms, uint32_t K, uint32_t nwords) {
