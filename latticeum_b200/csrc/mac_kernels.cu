@@ -593,22 +593,22 @@ void launch_witness_mac(const u64 *A_dev, const MatLayout &lay, const MacPlan &p
 // calls gain what the separate witness kernel cost (its launch, its tail, the grid-wide dependency): the two CTAs of an SM
 // are rarely in their transform at the same time, so one CTA's transform runs in the issue slots the other's wait leaves.
 struct StepJobs {   // the jobs of one CTA, in the order it runs them
-    u32 grid, cta, L, rounds_full;
+    u32 grid, cta, J, rounds_full;
     u64 ntiles, left_base, left_off;  // first tile of the leftover region, this CTA's offset into it
     u32 left_cnt;
     __device__ __forceinline__ u32 njobs() const { return rounds_full + (left_cnt ? 1u : 0u); }
-    __device__ __forceinline__ u64 tile0(u32 k) const { return k < rounds_full ? ((u64)k * grid + cta) * L : left_base + left_off; }
-    __device__ __forceinline__ u32 count(u32 k) const { return k < rounds_full ? L : left_cnt; }
-    __device__ __forceinline__ u32 total() const { return rounds_full * L + left_cnt; }
+    __device__ __forceinline__ u64 tile0(u32 k) const { return k < rounds_full ? ((u64)k * grid + cta) * J : left_base + left_off; }
+    __device__ __forceinline__ u32 count(u32 k) const { return k < rounds_full ? J : left_cnt; }
+    __device__ __forceinline__ u32 total() const { return rounds_full * J + left_cnt; }
 };
-__device__ __forceinline__ StepJobs make_jobs(u64 ntiles, u32 L, u32 grid, u32 cta) {
+__device__ __forceinline__ StepJobs make_jobs(u64 ntiles, u32 J, u32 grid, u32 cta) {
     StepJobs j;
-    j.grid = grid; j.cta = cta; j.L = L; j.ntiles = ntiles;
-    j.rounds_full = (u32)(ntiles / ((u64)grid * L));
-    j.left_base = (u64)j.rounds_full * grid * L;
-    const u64 left = ntiles - j.left_base;          // < grid * L tiles
+    j.grid = grid; j.cta = cta; j.J = J; j.ntiles = ntiles;
+    j.rounds_full = (u32)(ntiles / ((u64)grid * J));
+    j.left_base = (u64)j.rounds_full * grid * J;
+    const u64 left = ntiles - j.left_base;          // < grid * J tiles
     const u32 base = (u32)(left / grid), rem = (u32)(left % grid);
-    j.left_cnt = base + (cta < rem ? 1u : 0u);
+    j.left_cnt = base + (cta < rem ? 1u : 0u);      // <= J
     j.left_off = (u64)cta * base + min(cta, rem);
     return j;
 }
@@ -616,33 +616,45 @@ __device__ __forceinline__ StepJobs make_jobs(u64 ntiles, u32 L, u32 grid, u32 c
 constexpr int WM_TJ = geo_tj(8), WM_RB = 32, WM_THREADS = 256, WM_STAGES = 2;
 constexpr u32 WM_TILE_ELEMS = WM_TJ * 3 * WM_RB * 8, WM_TILE_BYTES = WM_TILE_ELEMS * 8, WM_F_BYTES = WM_TJ * FX * 8;
 constexpr u32 WM_STAGE_BYTES = WM_TILE_BYTES + WM_F_BYTES;
-constexpr int WM_MAX_L = 8;
-constexpr u32 WM_PIECE_ELEMS = WM_TJ + 2;                              // w_ccs elements behind one job, worst alignment
-constexpr u32 WM_PIECE_BYTES = WM_PIECE_ELEMS * ring::D * 8;           // 1920
-constexpr u32 WM_DIGIT_BYTES = WM_PIECE_ELEMS * WM_MAX_L * ring::D * 2;  // 3840
-constexpr u32 WM_SMEM = WM_STAGES * WM_STAGE_BYTES + 2 * WM_PIECE_BYTES + WM_DIGIT_BYTES + 64;
+constexpr u32 WM_SYNC_BYTES = 48;  // 2 tile barriers, 2 piece barriers, 2 release counters
+// A job of m * L tiles covers m * TJ whole elements when it is aligned (the full rounds) and touches at most one more when
+// it is not (the leftover job, which has at most as many tiles).
+__host__ __device__ constexpr u32 wm_piece_elems(u32 m) { return m * WM_TJ + 1; }
+__host__ __device__ constexpr u32 wm_piece_bytes(u32 m) { return wm_piece_elems(m) * ring::D * 8; }
+__host__ __device__ constexpr u32 wm_digit_bytes(u32 m, u32 L) { return wm_piece_elems(m) * L * ring::D * 2; }
+__host__ __device__ constexpr u32 wm_smem(u32 m, u32 L) {
+    return WM_STAGES * WM_STAGE_BYTES + 2 * wm_piece_bytes(m) + wm_digit_bytes(m, L) + WM_SYNC_BYTES;
+}
+constexpr u32 WM_SMEM_LIMIT = (228 * 1024 - 2 * 1024) / 2;  // two CTAs per SM, 1 KB reserved for each
 
 template <bool MONT>
 __global__ void __launch_bounds__(WM_THREADS, 2)
 wmac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, u64 *__restrict__ ws, u64 *__restrict__ cms, uint32_t dependent_launch,
-            MacReport report, FusedWitness fw) {
+            uint32_t m, MacReport report, FusedWitness fw) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    const u32 L = (u32)fw.L, J = m * L, piece_bytes = wm_piece_bytes(m);
     unsigned char *wring = smem_raw + WM_STAGES * WM_STAGE_BYTES;
-    int16_t *dtile = reinterpret_cast<int16_t *>(wring + 2 * WM_PIECE_BYTES);
-    u64 *bars = reinterpret_cast<u64 *>(wring + 2 * WM_PIECE_BYTES + WM_DIGIT_BYTES);  // [tile full x2][piece full x2]
+    int16_t *dtile = reinterpret_cast<int16_t *>(wring + 2 * piece_bytes);
+    u64 *bars = reinterpret_cast<u64 *>(wring + 2 * piece_bytes + wm_digit_bytes(m, L));  // [tile full x2][piece full x2]
     u64 *wbar = bars + WM_STAGES;
     u32 *released = reinterpret_cast<u32 *>(wbar + 2);
 
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const u32 L = (u32)fw.L;
-    const StepJobs jobs = make_jobs(lay.ntiles, L, gridDim.x, blockIdx.x);
+    const StepJobs jobs = make_jobs(lay.ntiles, J, gridDim.x, blockIdx.x);
     const u32 my_tiles = jobs.total(), njobs = jobs.njobs();
     TRACE(0);
+#ifdef LAT_MAC_TRACE
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        if (blockIdx.x < 8192) g_mac_trace[blockIdx.x * 8 + 5] = smid;
+    }
+#endif
 
     // flattened tile t of this CTA -> tile index of the matrix
     auto tile_of = [&](u32 t) -> u64 {
-        const u32 k = t / L;  // full-round jobs have exactly L tiles, the leftover job comes last
-        return jobs.tile0(k) + (t - k * L);
+        const u32 k = t / J;  // full-round jobs have exactly J tiles, the leftover job comes last
+        return jobs.tile0(k) + (t - k * J);
     };
     auto witness_bytes = [&](u64 tile) { return (u32)min((u64)WM_TJ, lay.n - tile * WM_TJ) * FX * 8; };
     auto issue_matrix = [&](u32 t, u32 st) {
@@ -658,18 +670,19 @@ wmac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, u64 *__restrict__ ws, 
         const u64 tile = tile_of(t);
         tma_bulk_g2s(smem_raw + (size_t)st * WM_STAGE_BYTES + WM_TILE_BYTES, fw.fx + tile * WM_TJ * FX, witness_bytes(tile), &bars[st]);
     };
-    // the w_ccs elements behind job k: [e0, e1)
-    auto job_elems = [&](u32 k, u64 &e0, u64 &e1) {
-        const u64 c0 = jobs.tile0(k) * WM_TJ, c1 = min(lay.n, (jobs.tile0(k) + jobs.count(k)) * WM_TJ);
+    // job k: its columns [c0, c1) and the w_ccs elements [e0, e1) behind them
+    auto job_range = [&](u32 k, u64 &c0, u64 &c1, u64 &e0, u64 &e1) {
+        c0 = jobs.tile0(k) * WM_TJ;
+        c1 = min(lay.n, (jobs.tile0(k) + jobs.count(k)) * WM_TJ);
         e0 = c0 / L;
         e1 = (c1 + L - 1) / L;
     };
     auto issue_piece = [&](u32 k) {  // one thread
-        u64 e0, e1;
-        job_elems(k, e0, e1);
+        u64 c0, c1, e0, e1;
+        job_range(k, c0, c1, e0, e1);
         const u32 bytes = (u32)(e1 - e0) * ring::D * 8;
         mbar_arrive_expect_tx(&wbar[k & 1], bytes);
-        tma_bulk_g2s(wring + (k & 1) * WM_PIECE_BYTES, fw.w + e0 * ring::D, bytes, &wbar[k & 1]);
+        tma_bulk_g2s(wring + (k & 1) * piece_bytes, fw.w + e0 * ring::D, bytes, &wbar[k & 1]);
     };
 
     if (threadIdx.x == 0) {
@@ -691,41 +704,43 @@ wmac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, u64 *__restrict__ ws, 
     const ring8::Twiddles tw = ring8::make_twiddles(threadIdx.x & 7);
     const u64 Bd = 1ull << fw.log2b, halfB = Bd >> 1;
     auto transform = [&](u32 k) {
-        u64 e0, e1;
-        job_elems(k, e0, e1);
+        u64 c0, c1, e0, e1;
+        job_range(k, c0, c1, e0, e1);
         const u32 ne = (u32)(e1 - e0);
-        const u64 c0 = jobs.tile0(k) * WM_TJ, c1 = min(lay.n, (jobs.tile0(k) + jobs.count(k)) * WM_TJ);
         mbar_wait(&wbar[k & 1], (k >> 1) & 1);
-        // phase A: eight lanes per element; warps without a valid element skip (shuffles stay inside an octet's warp)
-        const u32 sl = threadIdx.x & 7, oct = threadIdx.x >> 3;
-        if ((oct & ~3u) < ne) {  // this warp's first octet is in range: the whole warp takes part
-            const bool valid = oct < ne;
-            const u64 *p = reinterpret_cast<const u64 *>(wring + (k & 1) * WM_PIECE_BYTES) + (valid ? oct : 0) * ring::D + 3 * sl;
-            u64 c[3] = {p[0], p[1], p[2]};
-            ring8::icrt8(c, tw);
-            bool negative[3];
-            u64 m[3];
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                if constexpr (MONT) c[q] = gl::from_mont(c[q]);
-                ring::signed_rep(c[q], negative[q], m[q]);
-            }
-            int16_t *trow = dtile + (valid ? oct : 0) * (L * ring::D) + 3 * sl;
-            for (u32 l = 0; l < L; ++l) {
+        // phase A: eight lanes per element, 32 elements per pass; warps whose octets are all out of range skip the pass
+        const u32 sl = threadIdx.x & 7;
+        for (u32 base = 0; base < ne; base += WM_THREADS / 8) {
+            const u32 oct = base + (threadIdx.x >> 3);
+            if ((oct & ~3u) < ne) {  // warp-uniform: the shuffles of an octet stay inside its warp
+                const bool valid = oct < ne;
+                const u64 *p = reinterpret_cast<const u64 *>(wring + (k & 1) * piece_bytes) + (valid ? oct : 0) * ring::D + 3 * sl;
+                u64 c[3] = {p[0], p[1], p[2]};
+                ring8::icrt8(c, tw);
+                bool negative[3];
+                u64 mg[3];
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
-                    u64 rem = m[q] & (Bd - 1);
-                    m[q] >>= fw.log2b;
-                    int dg = (int)rem;
-                    if (rem > halfB) {  // |rem| == b/2 is kept (balanced_decomposition/mod.rs:79)
-                        dg -= (int)Bd;
-                        m[q] += 1;
-                    }
-                    if (negative[q]) dg = -dg;
-                    if (valid) trow[l * ring::D + q] = (int16_t)dg;
+                    if constexpr (MONT) c[q] = gl::from_mont(c[q]);
+                    ring::signed_rep(c[q], negative[q], mg[q]);
                 }
+                int16_t *trow = dtile + (valid ? oct : 0) * (L * ring::D) + 3 * sl;
+                for (u32 l = 0; l < L; ++l) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        u64 rem = mg[q] & (Bd - 1);
+                        mg[q] >>= fw.log2b;
+                        int dg = (int)rem;
+                        if (rem > halfB) {  // |rem| == b/2 is kept (balanced_decomposition/mod.rs:79)
+                            dg -= (int)Bd;
+                            mg[q] += 1;
+                        }
+                        if (negative[q]) dg = -dg;
+                        if (valid) trow[l * ring::D + q] = (int16_t)dg;
+                    }
+                }
+                if (valid && (mg[0] | mg[1] | mg[2])) atomicOr(fw.flag, 1);
             }
-            if (valid && (m[0] | m[1] | m[2])) atomicOr(fw.flag, 1);
         }
         __syncthreads();
         if (threadIdx.x == 0 && k + 2 < njobs) issue_piece(k + 2);  // the slot is free again
@@ -740,22 +755,21 @@ wmac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, u64 *__restrict__ ws, 
             }
         }
         // phase B: one thread per limb element of [c0, c1)
-        if (threadIdx.x < nrows) {
-            const u64 row = row0 + threadIdx.x;
-            if (row >= c0 && row < c1) {
-                int d[ring::D];
-                load_i16x24_cta(dtile + threadIdx.x * ring::D, d);
-                u64 x[ring::D];
-                r96::crt24_small<MONT>(d, x);
-                u64 *o = fw.fx + row * FX;
+        for (u32 r = threadIdx.x; r < nrows; r += WM_THREADS) {
+            const u64 row = row0 + r;
+            if (row < c0 || row >= c1) continue;
+            int d[ring::D];
+            load_i16x24_cta(dtile + r * ring::D, d);
+            u64 x[ring::D];
+            r96::crt24_small<MONT>(d, x);
+            u64 *o = fw.fx + row * FX;
 #pragma unroll
-                for (int s2 = 0; s2 < ring::NSLOT; s2 += 2) {
-                    const u64 a0 = x[3 * s2], a1 = x[3 * s2 + 1], a2 = x[3 * s2 + 2];
-                    const u64 b0 = x[3 * s2 + 3], b1 = x[3 * s2 + 4], b2 = x[3 * s2 + 5];
-                    st256(o + s2 * 6, a0, a1, a2, gl::add_lazy(a0, a1));
-                    st256(o + s2 * 6 + 4, gl::add_lazy(a0, a2), gl::add_lazy(a1, a2), b0, b1);
-                    st256(o + s2 * 6 + 8, b2, gl::add_lazy(b0, b1), gl::add_lazy(b0, b2), gl::add_lazy(b1, b2));
-                }
+            for (int s2 = 0; s2 < ring::NSLOT; s2 += 2) {
+                const u64 a0 = x[3 * s2], a1 = x[3 * s2 + 1], a2 = x[3 * s2 + 2];
+                const u64 b0 = x[3 * s2 + 3], b1 = x[3 * s2 + 4], b2 = x[3 * s2 + 5];
+                st256(o + s2 * 6, a0, a1, a2, gl::add_lazy(a0, a1));
+                st256(o + s2 * 6 + 4, gl::add_lazy(a0, a2), gl::add_lazy(a1, a2), b0, b1);
+                st256(o + s2 * 6 + 8, b2, gl::add_lazy(b0, b1), gl::add_lazy(b0, b2), gl::add_lazy(b1, b2));
             }
         }
         // the rows were written through the generic proxy and are fetched by bulk copies (async proxy) of THIS CTA
@@ -764,15 +778,16 @@ wmac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, u64 *__restrict__ ws, 
     };
 
     u32 transformed = 0;  // jobs [0, transformed) have their witness rows in place
-    auto ensure = [&](u32 t) {  // ... up to the job of flattened tile t
-        const u32 need = min(t / L, njobs - 1) + 1;
-        while (transformed < need) transform(transformed++);
-    };
     if (my_tiles) {
-        ensure(min((u32)WM_STAGES, my_tiles) - 1);
+        const u32 need = min((min((u32)WM_STAGES, my_tiles) - 1) / J, njobs - 1) + 1;
+        while (transformed < need) transform(transformed++);
         if (threadIdx.x == 0)
             for (u32 t = 0; t < min((u32)WM_STAGES, my_tiles); ++t) issue_witness(t, t);
     }
+    // Where in a job the NEXT job is transformed: at the latest possible tile for even CTAs, half a job earlier for odd ones.
+    // The two CTAs of an SM are neighbours in blockIdx, so one of them is in its matrix loop (and alone has the SM's issue
+    // slots) while the other is in its transform, whose latency is thereby hidden.
+    const u32 trigger = (J >= 4 && (blockIdx.x & 1)) ? (J / 2 >= WM_STAGES ? J / 2 - WM_STAGES : 0) : (J >= WM_STAGES ? J - WM_STAGES : 0);
 
     const u32 il = warp * 4 + (lane >> 3), s = lane & 7;  // RG = 8, CG = 1: warp w owns rows 4w .. 4w+3
     gl::Fq3Acc acc;
@@ -781,8 +796,9 @@ wmac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, u64 *__restrict__ ws, 
     bool ready = false;
     for (u32 t = 0; t < my_tiles; ++t) {
         // the tile requested at the end of this iteration is t + 2: its job must have been transformed by then
-        if (t + WM_STAGES < my_tiles && (t + WM_STAGES) / L >= transformed) {
-            ensure(t + WM_STAGES);
+        const u32 kt = t / J, off = t - kt * J;
+        if (transformed < njobs && ((off >= trigger && transformed == kt + 1) || (t + WM_STAGES) / J >= transformed)) {
+            transform(transformed++);
             ready = false;
         }
         if (!ready) mbar_wait(&bars[st], ph);
@@ -867,7 +883,7 @@ wmac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, u64 *__restrict__ ws, 
     TRACE(4);
 }
 
-// kappa in 29..32 only (RG = 8, one row block); the caller checks.  grid_x CTAs, two per SM.
+// kappa in 29..32 only (RG = 8, one row block), L <= 8; the caller checks.  grid_x CTAs, two per SM.
 void launch_step_commit(const u64 *A_dev, const MatLayout &lay, uint32_t grid_x, u64 *workspace, u64 *cms, cudaStream_t stream,
                         bool mont, bool chained, const FusedWitness &fw, cudaEvent_t ev_begin, cudaEvent_t ev_end,
                         const MacReport &report) {
@@ -875,16 +891,21 @@ void launch_step_commit(const u64 *A_dev, const MatLayout &lay, uint32_t grid_x,
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set_on[dev & 63]) {
-        cudaFuncSetAttribute(wmac_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WM_SMEM);
-        cudaFuncSetAttribute(wmac_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WM_SMEM);
+        cudaFuncSetAttribute(wmac_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WM_SMEM_LIMIT);
+        cudaFuncSetAttribute(wmac_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WM_SMEM_LIMIT);
         attr_set_on[dev & 63] = true;
     }
+    // job = m * L tiles = m * TJ elements: as long as two CTAs still fit an SM, the larger job amortises the transform's
+    // latency over twice the tiles (and leaves the other CTA of the SM enough matrix work to cover it)
+    uint32_t m = 2;
+    if (const char *e = getenv("LAT_WMAC_M")) m = (uint32_t)atoi(e);
+    while (m > 1 && wm_smem(m, (uint32_t)fw.L) > WM_SMEM_LIMIT) --m;
     static const bool pdl_off = getenv("LAT_NO_PDL") != nullptr;
     const bool pdl = chained && !ev_begin && !pdl_off;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid_x);
     cfg.blockDim = dim3(WM_THREADS);
-    cfg.dynamicSmemBytes = WM_SMEM;
+    cfg.dynamicSmemBytes = wm_smem(m, (uint32_t)fw.L);
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -892,8 +913,8 @@ void launch_step_commit(const u64 *A_dev, const MatLayout &lay, uint32_t grid_x,
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     if (ev_begin) cudaEventRecord(ev_begin, stream);
-    if (mont) cudaLaunchKernelEx(&cfg, wmac_kernel<true>, A_dev, lay, workspace, cms, (uint32_t)(pdl ? 1 : 0), report, fw);
-    else cudaLaunchKernelEx(&cfg, wmac_kernel<false>, A_dev, lay, workspace, cms, (uint32_t)(pdl ? 1 : 0), report, fw);
+    if (mont) cudaLaunchKernelEx(&cfg, wmac_kernel<true>, A_dev, lay, workspace, cms, (uint32_t)(pdl ? 1 : 0), m, report, fw);
+    else cudaLaunchKernelEx(&cfg, wmac_kernel<false>, A_dev, lay, workspace, cms, (uint32_t)(pdl ? 1 : 0), m, report, fw);
     if (ev_end) cudaEventRecord(ev_end, stream);
 }
 
