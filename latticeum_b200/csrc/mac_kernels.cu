@@ -616,7 +616,7 @@ __device__ __forceinline__ StepJobs make_jobs(u64 ntiles, u32 J, u32 grid, u32 c
 constexpr int WM_TJ = geo_tj(8), WM_RB = 32, WM_THREADS = 256, WM_STAGES = 2;
 constexpr u32 WM_TILE_ELEMS = WM_TJ * 3 * WM_RB * 8, WM_TILE_BYTES = WM_TILE_ELEMS * 8, WM_F_BYTES = WM_TJ * FX * 8;
 constexpr u32 WM_STAGE_BYTES = WM_TILE_BYTES + WM_F_BYTES;
-constexpr u32 WM_SYNC_BYTES = 48;  // 2 tile barriers, 2 piece barriers, 2 release counters
+constexpr u32 WM_SYNC_BYTES = 48 + 160;  // 2 tile barriers, 2 piece barriers, 2 release counters; the transform's context (WmCtx)
 // A job of m * L tiles covers m * TJ whole elements when it is aligned (the full rounds) and touches at most one more when
 // it is not (the leftover job, which has at most as many tiles).
 __host__ __device__ constexpr u32 wm_piece_elems(u32 m) { return m * WM_TJ + 1; }
@@ -626,6 +626,116 @@ __host__ __device__ constexpr u32 wm_smem(u32 m, u32 L) {
     return WM_STAGES * WM_STAGE_BYTES + 2 * wm_piece_bytes(m) + wm_digit_bytes(m, L) + WM_SYNC_BYTES;
 }
 constexpr u32 WM_SMEM_LIMIT = (228 * 1024 - 2 * 1024) / 2;  // two CTAs per SM, 1 KB reserved for each
+
+// What the transform of a job needs, kept in shared memory so that the (deliberately out-of-line) transform holds none of
+// it in registers across the tile loop: the loop itself then compiles exactly like mac_kernel<1,8>'s.
+struct WmCtx {
+    StepJobs jobs;
+    const u64 *w;
+    int16_t *f16;
+    u64 *fx;
+    int *flag;
+    u64 n;
+    u32 L, log2b, piece_bytes, njobs;
+    unsigned char *wring;
+    int16_t *dtile;
+    u64 *wbar;
+};
+__device__ __forceinline__ void wm_job_range(const WmCtx &cx, u32 k, u64 &c0, u64 &c1, u64 &e0, u64 &e1) {
+    c0 = cx.jobs.tile0(k) * WM_TJ;
+    c1 = min(cx.n, (cx.jobs.tile0(k) + cx.jobs.count(k)) * WM_TJ);
+    e0 = c0 / cx.L;
+    e1 = (c1 + cx.L - 1) / cx.L;
+}
+__device__ __forceinline__ void wm_issue_piece(const WmCtx &cx, u32 k) {  // one thread
+    u64 c0, c1, e0, e1;
+    wm_job_range(cx, k, c0, c1, e0, e1);
+    const u32 bytes = (u32)(e1 - e0) * ring::D * 8;
+    mbar_arrive_expect_tx(&cx.wbar[k & 1], bytes);
+    tma_bulk_g2s(cx.wring + (k & 1) * cx.piece_bytes, cx.w + e0 * ring::D, bytes, &cx.wbar[k & 1]);
+}
+// Transform of job k by the whole block: iCRT -> digits -> CRT of the limbs for the job's w_ccs elements (already in the
+// ring slot k & 1), digits and extended rows of the job's columns written to global memory; ends with the proxy fence
+// and a barrier, after which any thread may request those rows with a bulk copy.
+template <bool MONT>
+__device__ __noinline__ void wm_transform(const WmCtx *cxp, u32 k) {
+    const WmCtx &cx = *cxp;
+    const u32 L = cx.L;
+    u64 c0, c1, e0, e1;
+    wm_job_range(cx, k, c0, c1, e0, e1);
+    const u32 ne = (u32)(e1 - e0);
+    mbar_wait(&cx.wbar[k & 1], (k >> 1) & 1);
+    {   // phase A: eight lanes per element, 32 elements per pass; warps whose octets are all out of range skip the pass
+        const u32 sl = threadIdx.x & 7;
+        const ring8::Twiddles tw = ring8::make_twiddles(sl);
+        const u64 Bd = 1ull << cx.log2b, halfB = Bd >> 1;
+        for (u32 base = 0; base < ne; base += WM_THREADS / 8) {
+            const u32 oct = base + (threadIdx.x >> 3);
+            if ((oct & ~3u) < ne) {  // warp-uniform: the shuffles of an octet stay inside its warp
+                const bool valid = oct < ne;
+                const u64 *p = reinterpret_cast<const u64 *>(cx.wring + (k & 1) * cx.piece_bytes) + (valid ? oct : 0) * ring::D + 3 * sl;
+                u64 c[3] = {p[0], p[1], p[2]};
+                ring8::icrt8(c, tw);
+                bool negative[3];
+                u64 mg[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    if constexpr (MONT) c[q] = gl::from_mont(c[q]);
+                    ring::signed_rep(c[q], negative[q], mg[q]);
+                }
+                int16_t *trow = cx.dtile + (valid ? oct : 0) * (L * ring::D) + 3 * sl;
+                for (u32 l = 0; l < L; ++l) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        u64 rem = mg[q] & (Bd - 1);
+                        mg[q] >>= cx.log2b;
+                        int dg = (int)rem;
+                        if (rem > halfB) {  // |rem| == b/2 is kept (balanced_decomposition/mod.rs:79)
+                            dg -= (int)Bd;
+                            mg[q] += 1;
+                        }
+                        if (negative[q]) dg = -dg;
+                        if (valid) trow[l * ring::D + q] = (int16_t)dg;
+                    }
+                }
+                if (valid && (mg[0] | mg[1] | mg[2])) atomicOr(cx.flag, 1);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && k + 2 < cx.njobs) wm_issue_piece(cx, k + 2);  // the slot is free again
+    const u64 row0 = e0 * L;
+    const u32 nrows = ne * L;
+    {   // the resident int16 digits
+        const uint4 *src = reinterpret_cast<const uint4 *>(cx.dtile);
+        uint4 *dst = reinterpret_cast<uint4 *>(cx.f16 + row0 * ring::D);
+        for (u32 u = threadIdx.x; u < nrows * 3; u += WM_THREADS) {
+            const u64 row = row0 + u / 3;
+            if (row >= c0 && row < c1) dst[u] = src[u];
+        }
+    }
+    // phase B: one thread per limb element of [c0, c1)
+    for (u32 r = threadIdx.x; r < nrows; r += WM_THREADS) {
+        const u64 row = row0 + r;
+        if (row < c0 || row >= c1) continue;
+        int d[ring::D];
+        load_i16x24_cta(cx.dtile + r * ring::D, d);
+        u64 x[ring::D];
+        r96::crt24_small<MONT>(d, x);
+        u64 *o = cx.fx + row * FX;
+#pragma unroll
+        for (int s2 = 0; s2 < ring::NSLOT; s2 += 2) {
+            const u64 a0 = x[3 * s2], a1 = x[3 * s2 + 1], a2 = x[3 * s2 + 2];
+            const u64 b0 = x[3 * s2 + 3], b1 = x[3 * s2 + 4], b2 = x[3 * s2 + 5];
+            st256(o + s2 * 6, a0, a1, a2, gl::add_lazy(a0, a1));
+            st256(o + s2 * 6 + 4, gl::add_lazy(a0, a2), gl::add_lazy(a1, a2), b0, b1);
+            st256(o + s2 * 6 + 8, b2, gl::add_lazy(b0, b1), gl::add_lazy(b0, b2), gl::add_lazy(b1, b2));
+        }
+    }
+    // the rows were written through the generic proxy and are fetched by bulk copies (async proxy) of THIS CTA
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+}
 
 template <bool MONT>
 __global__ void __launch_bounds__(WM_THREADS, 2)
@@ -651,12 +761,15 @@ wmac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, u64 *__restrict__ ws, 
     }
 #endif
 
-    // flattened tile t of this CTA -> tile index of the matrix
+    WmCtx *cx = reinterpret_cast<WmCtx *>(released + 2);
+    // Flattened tile t of this CTA -> tile index of the matrix.  Everything the refill path needs is read from the
+    // shared-memory context at the moment of use (the barriers in between keep those loads from being hoisted), so none
+    // of it is live in registers across the tile loop.
     auto tile_of = [&](u32 t) -> u64 {
-        const u32 k = t / J;  // full-round jobs have exactly J tiles, the leftover job comes last
-        return jobs.tile0(k) + (t - k * J);
+        const u32 jj = cx->jobs.J, k = t / jj;  // full-round jobs have exactly J tiles, the leftover job comes last
+        return cx->jobs.tile0(k) + (t - k * jj);
     };
-    auto witness_bytes = [&](u64 tile) { return (u32)min((u64)WM_TJ, lay.n - tile * WM_TJ) * FX * 8; };
+    auto witness_bytes = [&](u64 tile) { return (u32)min((u64)WM_TJ, cx->n - tile * WM_TJ) * FX * 8; };
     auto issue_matrix = [&](u32 t, u32 st) {
         const u64 tile = tile_of(t);
         mbar_arrive_expect_tx(&bars[st], WM_TILE_BYTES + witness_bytes(tile));
@@ -668,24 +781,13 @@ wmac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, u64 *__restrict__ ws, 
     };
     auto issue_witness = [&](u32 t, u32 st) {
         const u64 tile = tile_of(t);
-        tma_bulk_g2s(smem_raw + (size_t)st * WM_STAGE_BYTES + WM_TILE_BYTES, fw.fx + tile * WM_TJ * FX, witness_bytes(tile), &bars[st]);
+        tma_bulk_g2s(smem_raw + (size_t)st * WM_STAGE_BYTES + WM_TILE_BYTES, cx->fx + tile * WM_TJ * FX, witness_bytes(tile), &bars[st]);
     };
-    // job k: its columns [c0, c1) and the w_ccs elements [e0, e1) behind them
-    auto job_range = [&](u32 k, u64 &c0, u64 &c1, u64 &e0, u64 &e1) {
-        c0 = jobs.tile0(k) * WM_TJ;
-        c1 = min(lay.n, (jobs.tile0(k) + jobs.count(k)) * WM_TJ);
-        e0 = c0 / L;
-        e1 = (c1 + L - 1) / L;
-    };
-    auto issue_piece = [&](u32 k) {  // one thread
-        u64 c0, c1, e0, e1;
-        job_range(k, c0, c1, e0, e1);
-        const u32 bytes = (u32)(e1 - e0) * ring::D * 8;
-        mbar_arrive_expect_tx(&wbar[k & 1], bytes);
-        tma_bulk_g2s(wring + (k & 1) * piece_bytes, fw.w + e0 * ring::D, bytes, &wbar[k & 1]);
-    };
-
     if (threadIdx.x == 0) {
+        cx->jobs = jobs;
+        cx->w = fw.w; cx->f16 = fw.f16; cx->fx = fw.fx; cx->flag = fw.flag;
+        cx->n = lay.n; cx->L = L; cx->log2b = (u32)fw.log2b; cx->piece_bytes = piece_bytes; cx->njobs = njobs;
+        cx->wring = wring; cx->dtile = dtile; cx->wbar = wbar;
         for (u32 st = 0; st < WM_STAGES; ++st) {
             mbar_init(&bars[st], 1);
             mbar_init(&wbar[st], 1);
@@ -696,91 +798,14 @@ wmac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, u64 *__restrict__ ws, 
         asm volatile("griddepcontrol.launch_dependents;");
         if (fw.ready_flag)  // a ticketed step: the upload runs on a copy engine, its ticket lands behind the data
             spin_until_equals(fw.ready_flag, fw.ready_value, fw.guard, SPIN_UPLOAD_TICKET, fw.ready_value);
-        for (u32 k = 0; k < min(2u, njobs); ++k) issue_piece(k);
+        for (u32 k = 0; k < min(2u, njobs); ++k) wm_issue_piece(*cx, k);
     }
     __syncthreads();
-
-    // ---- the transform of one job (all threads; ends with the bulk-copy proxy fence + barrier) ----
-    const ring8::Twiddles tw = ring8::make_twiddles(threadIdx.x & 7);
-    const u64 Bd = 1ull << fw.log2b, halfB = Bd >> 1;
-    auto transform = [&](u32 k) {
-        u64 c0, c1, e0, e1;
-        job_range(k, c0, c1, e0, e1);
-        const u32 ne = (u32)(e1 - e0);
-        mbar_wait(&wbar[k & 1], (k >> 1) & 1);
-        // phase A: eight lanes per element, 32 elements per pass; warps whose octets are all out of range skip the pass
-        const u32 sl = threadIdx.x & 7;
-        for (u32 base = 0; base < ne; base += WM_THREADS / 8) {
-            const u32 oct = base + (threadIdx.x >> 3);
-            if ((oct & ~3u) < ne) {  // warp-uniform: the shuffles of an octet stay inside its warp
-                const bool valid = oct < ne;
-                const u64 *p = reinterpret_cast<const u64 *>(wring + (k & 1) * piece_bytes) + (valid ? oct : 0) * ring::D + 3 * sl;
-                u64 c[3] = {p[0], p[1], p[2]};
-                ring8::icrt8(c, tw);
-                bool negative[3];
-                u64 mg[3];
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    if constexpr (MONT) c[q] = gl::from_mont(c[q]);
-                    ring::signed_rep(c[q], negative[q], mg[q]);
-                }
-                int16_t *trow = dtile + (valid ? oct : 0) * (L * ring::D) + 3 * sl;
-                for (u32 l = 0; l < L; ++l) {
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        u64 rem = mg[q] & (Bd - 1);
-                        mg[q] >>= fw.log2b;
-                        int dg = (int)rem;
-                        if (rem > halfB) {  // |rem| == b/2 is kept (balanced_decomposition/mod.rs:79)
-                            dg -= (int)Bd;
-                            mg[q] += 1;
-                        }
-                        if (negative[q]) dg = -dg;
-                        if (valid) trow[l * ring::D + q] = (int16_t)dg;
-                    }
-                }
-                if (valid && (mg[0] | mg[1] | mg[2])) atomicOr(fw.flag, 1);
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0 && k + 2 < njobs) issue_piece(k + 2);  // the slot is free again
-        const u64 row0 = e0 * L;
-        const u32 nrows = ne * L;
-        {   // the resident int16 digits
-            const uint4 *src = reinterpret_cast<const uint4 *>(dtile);
-            uint4 *dst = reinterpret_cast<uint4 *>(fw.f16 + row0 * ring::D);
-            for (u32 u = threadIdx.x; u < nrows * 3; u += WM_THREADS) {
-                const u64 row = row0 + u / 3;
-                if (row >= c0 && row < c1) dst[u] = src[u];
-            }
-        }
-        // phase B: one thread per limb element of [c0, c1)
-        for (u32 r = threadIdx.x; r < nrows; r += WM_THREADS) {
-            const u64 row = row0 + r;
-            if (row < c0 || row >= c1) continue;
-            int d[ring::D];
-            load_i16x24_cta(dtile + r * ring::D, d);
-            u64 x[ring::D];
-            r96::crt24_small<MONT>(d, x);
-            u64 *o = fw.fx + row * FX;
-#pragma unroll
-            for (int s2 = 0; s2 < ring::NSLOT; s2 += 2) {
-                const u64 a0 = x[3 * s2], a1 = x[3 * s2 + 1], a2 = x[3 * s2 + 2];
-                const u64 b0 = x[3 * s2 + 3], b1 = x[3 * s2 + 4], b2 = x[3 * s2 + 5];
-                st256(o + s2 * 6, a0, a1, a2, gl::add_lazy(a0, a1));
-                st256(o + s2 * 6 + 4, gl::add_lazy(a0, a2), gl::add_lazy(a1, a2), b0, b1);
-                st256(o + s2 * 6 + 8, b2, gl::add_lazy(b0, b1), gl::add_lazy(b0, b2), gl::add_lazy(b1, b2));
-            }
-        }
-        // the rows were written through the generic proxy and are fetched by bulk copies (async proxy) of THIS CTA
-        asm volatile("fence.proxy.async;" ::: "memory");
-        __syncthreads();
-    };
 
     u32 transformed = 0;  // jobs [0, transformed) have their witness rows in place
     if (my_tiles) {
         const u32 need = min((min((u32)WM_STAGES, my_tiles) - 1) / J, njobs - 1) + 1;
-        while (transformed < need) transform(transformed++);
+        while (transformed < need) wm_transform<MONT>(cx, transformed++);
         if (threadIdx.x == 0)
             for (u32 t = 0; t < min((u32)WM_STAGES, my_tiles); ++t) issue_witness(t, t);
     }
@@ -794,44 +819,53 @@ wmac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, u64 *__restrict__ ws, 
     acc.clear();
     u32 st = 0, ph = 0;
     bool ready = false;
-    for (u32 t = 0; t < my_tiles; ++t) {
-        // the tile requested at the end of this iteration is t + 2: its job must have been transformed by then
-        const u32 kt = t / J, off = t - kt * J;
-        if (transformed < njobs && ((off >= trigger && transformed == kt + 1) || (t + WM_STAGES) / J >= transformed)) {
-            transform(transformed++);
-            ready = false;
-        }
-        if (!ready) mbar_wait(&bars[st], ph);
+    // tiles [t0, t1) of this CTA: the tile loop of mac_kernel<1,8>, free of calls so that the accumulators stay in registers
+    auto mac_tiles = [&](u32 t0, u32 t1) {
+        for (u32 t = t0; t < t1; ++t) {
+            if (!ready) mbar_wait(&bars[st], ph);
 #ifdef LAT_MAC_TRACE
-        if (t == 0) TRACE(1);
+            if (t == 0) TRACE(1);
 #endif
-        const u64 *sa = reinterpret_cast<const u64 *>(smem_raw + (size_t)st * WM_STAGE_BYTES) + il * 8 + s;
-        const ulonglong2 *sf = reinterpret_cast<const ulonglong2 *>(smem_raw + (size_t)st * WM_STAGE_BYTES + WM_TILE_BYTES) + s * 3;
-        u32 st_n = st + 1, ph_n = ph;
-        if (st_n == WM_STAGES) {
-            st_n = 0;
-            ph_n ^= 1;
-        }
-        ready = (t + 1 < my_tiles) && mbar_test(&bars[st_n], ph_n);
+            const u64 *sa = reinterpret_cast<const u64 *>(smem_raw + (size_t)st * WM_STAGE_BYTES) + il * 8 + s;
+            const ulonglong2 *sf = reinterpret_cast<const ulonglong2 *>(smem_raw + (size_t)st * WM_STAGE_BYTES + WM_TILE_BYTES) + s * 3;
+            u32 st_n = st + 1, ph_n = ph;
+            if (st_n == WM_STAGES) {
+                st_n = 0;
+                ph_n ^= 1;
+            }
+            ready = (t + 1 < my_tiles) && mbar_test(&bars[st_n], ph_n);
 #pragma unroll
-        for (int jj = 0; jj < WM_TJ; ++jj) {
-            const u64 *pa = sa + jj * (3 * WM_RB * 8);
-            const u64 a0 = pa[0], a1 = pa[WM_RB * 8], a2 = pa[2 * WM_RB * 8];
-            const ulonglong2 x = sf[jj * (FX / 2)], y = sf[jj * (FX / 2) + 1], z = sf[jj * (FX / 2) + 2];
-            acc.mac(a0, a1, a2, x.x, x.y, y.x, y.y, z.x, z.y);
-        }
-        __syncwarp();
-        if (lane == 0) {
-            if (atomicAdd(&released[st], 1u) == WM_THREADS / 32 - 1) {
-                released[st] = 0;
-                if (t + WM_STAGES < my_tiles) {
-                    issue_matrix(t + WM_STAGES, st);
-                    issue_witness(t + WM_STAGES, st);
+            for (int jj = 0; jj < WM_TJ; ++jj) {
+                const u64 *pa = sa + jj * (3 * WM_RB * 8);
+                const u64 a0 = pa[0], a1 = pa[WM_RB * 8], a2 = pa[2 * WM_RB * 8];
+                const ulonglong2 x = sf[jj * (FX / 2)], y = sf[jj * (FX / 2) + 1], z = sf[jj * (FX / 2) + 2];
+                acc.mac(a0, a1, a2, x.x, x.y, y.x, y.y, z.x, z.y);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (atomicAdd(&released[st], 1u) == WM_THREADS / 32 - 1) {
+                    released[st] = 0;
+                    if (t + WM_STAGES < my_tiles) {
+                        issue_matrix(t + WM_STAGES, st);
+                        issue_witness(t + WM_STAGES, st);
+                    }
                 }
             }
+            st = st_n;
+            ph = ph_n;
         }
-        st = st_n;
-        ph = ph_n;
+    };
+    // Job by job; the NEXT job is transformed at a fixed tile of the current one (between two call-free tile loops).  A tile
+    // requested while tile t runs is t + 2, so everything up to that tile's job must be in place before the second loop.
+    for (u32 tb = 0; tb < my_tiles; tb += J) {
+        const u32 te = min(my_tiles, tb + J), tm = min(te, tb + trigger);
+        mac_tiles(tb, tm);
+        const u32 need = min(max((te - 1 + WM_STAGES) / J, tb / J + 1), njobs - 1) + 1;
+        if (transformed < need) {
+            while (transformed < need) wm_transform<MONT>(cx, transformed++);
+            ready = false;
+        }
+        mac_tiles(tm, te);
     }
     TRACE(2);
 
