@@ -616,14 +616,14 @@ __device__ __forceinline__ StepJobs make_jobs(u64 ntiles, u32 J, u32 grid, u32 c
 constexpr int WM_TJ = geo_tj(8), WM_RB = 32, WM_THREADS = 256, WM_STAGES = 2;
 constexpr u32 WM_TILE_ELEMS = WM_TJ * 3 * WM_RB * 8, WM_TILE_BYTES = WM_TILE_ELEMS * 8, WM_F_BYTES = WM_TJ * FX * 8;
 constexpr u32 WM_STAGE_BYTES = WM_TILE_BYTES + WM_F_BYTES;
-constexpr u32 WM_SYNC_BYTES = 48 + 160;  // 2 tile barriers, 2 piece barriers, 2 release counters; the transform's context (WmCtx)
+constexpr u32 WM_HDR_BYTES = 256;  // at offset 0: 2 tile barriers, 2 piece barriers, 2 release counters, the context (WmCtx)
 // A job of m * L tiles covers m * TJ whole elements when it is aligned (the full rounds) and touches at most one more when
 // it is not (the leftover job, which has at most as many tiles).
 __host__ __device__ constexpr u32 wm_piece_elems(u32 m) { return m * WM_TJ + 1; }
 __host__ __device__ constexpr u32 wm_piece_bytes(u32 m) { return wm_piece_elems(m) * ring::D * 8; }
 __host__ __device__ constexpr u32 wm_digit_bytes(u32 m, u32 L) { return wm_piece_elems(m) * L * ring::D * 2; }
 __host__ __device__ constexpr u32 wm_smem(u32 m, u32 L) {
-    return WM_STAGES * WM_STAGE_BYTES + 2 * wm_piece_bytes(m) + wm_digit_bytes(m, L) + WM_SYNC_BYTES;
+    return WM_HDR_BYTES + WM_STAGES * WM_STAGE_BYTES + 2 * wm_piece_bytes(m) + wm_digit_bytes(m, L);
 }
 constexpr u32 WM_SMEM_LIMIT = (228 * 1024 - 2 * 1024) / 2;  // two CTAs per SM, 1 KB reserved for each
 
@@ -640,7 +640,10 @@ struct WmCtx {
     unsigned char *wring;
     int16_t *dtile;
     u64 *wbar;
+    const u64 *A;
+    u32 my_tiles, trigger;
 };
+static_assert(sizeof(WmCtx) + 48 <= WM_HDR_BYTES, "shared-memory header of wmac_kernel");
 __device__ __forceinline__ void wm_job_range(const WmCtx &cx, u32 k, u64 &c0, u64 &c1, u64 &e0, u64 &e1) {
     c0 = cx.jobs.tile0(k) * WM_TJ;
     c1 = min(cx.n, (cx.jobs.tile0(k) + cx.jobs.count(k)) * WM_TJ);
@@ -657,9 +660,18 @@ __device__ __forceinline__ void wm_issue_piece(const WmCtx &cx, u32 k) {  // one
 // Transform of job k by the whole block: iCRT -> digits -> CRT of the limbs for the job's w_ccs elements (already in the
 // ring slot k & 1), digits and extended rows of the job's columns written to global memory; ends with the proxy fence
 // and a barrier, after which any thread may request those rows with a bulk copy.
+#ifdef LAT_WMAC_DEBUG
+__device__ int g_wmac_debug;  // tuning builds: 1 = no phase A arithmetic, 2 = no phase B arithmetic, 4 = no proxy fence,
+                              // 8 = no transform at all (no barriers either), 16 = contiguous tile order
+extern "C" int lat_debug_wmac(int v) { return (int)cudaMemcpyToSymbol(g_wmac_debug, &v, sizeof(int)); }
+#define WM_DBG(bit) (g_wmac_debug & (bit))
+#else
+#define WM_DBG(bit) 0
+#endif
 template <bool MONT>
 __device__ __noinline__ void wm_transform(const WmCtx *cxp, u32 k) {
     const WmCtx &cx = *cxp;
+    if (WM_DBG(8)) return;
     const u32 L = cx.L;
     u64 c0, c1, e0, e1;
     wm_job_range(cx, k, c0, c1, e0, e1);
@@ -671,7 +683,7 @@ __device__ __noinline__ void wm_transform(const WmCtx *cxp, u32 k) {
         const u64 Bd = 1ull << cx.log2b, halfB = Bd >> 1;
         for (u32 base = 0; base < ne; base += WM_THREADS / 8) {
             const u32 oct = base + (threadIdx.x >> 3);
-            if ((oct & ~3u) < ne) {  // warp-uniform: the shuffles of an octet stay inside its warp
+            if ((oct & ~3u) < ne && !WM_DBG(1)) {  // warp-uniform: the shuffles of an octet stay inside its warp
                 const bool valid = oct < ne;
                 const u64 *p = reinterpret_cast<const u64 *>(cx.wring + (k & 1) * cx.piece_bytes) + (valid ? oct : 0) * ring::D + 3 * sl;
                 u64 c[3] = {p[0], p[1], p[2]};
@@ -717,7 +729,7 @@ __device__ __noinline__ void wm_transform(const WmCtx *cxp, u32 k) {
     // phase B: one thread per limb element of [c0, c1)
     for (u32 r = threadIdx.x; r < nrows; r += WM_THREADS) {
         const u64 row = row0 + r;
-        if (row < c0 || row >= c1) continue;
+        if (row < c0 || row >= c1 || WM_DBG(2)) continue;
         int d[ring::D];
         load_i16x24_cta(cx.dtile + r * ring::D, d);
         u64 x[ring::D];
@@ -733,7 +745,7 @@ __device__ __noinline__ void wm_transform(const WmCtx *cxp, u32 k) {
         }
     }
     // the rows were written through the generic proxy and are fetched by bulk copies (async proxy) of THIS CTA
-    asm volatile("fence.proxy.async;" ::: "memory");
+    if (!WM_DBG(4)) asm volatile("fence.proxy.async;" ::: "memory");
     __syncthreads();
 }
 
@@ -742,16 +754,15 @@ __global__ void __launch_bounds__(WM_THREADS, 2)
 wmac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, u64 *__restrict__ ws, u64 *__restrict__ cms, uint32_t dependent_launch,
             uint32_t m, MacReport report, FusedWitness fw) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const u32 L = (u32)fw.L, J = m * L, piece_bytes = wm_piece_bytes(m);
-    unsigned char *wring = smem_raw + WM_STAGES * WM_STAGE_BYTES;
-    int16_t *dtile = reinterpret_cast<int16_t *>(wring + 2 * piece_bytes);
-    u64 *bars = reinterpret_cast<u64 *>(wring + 2 * piece_bytes + wm_digit_bytes(m, L));  // [tile full x2][piece full x2]
-    u64 *wbar = bars + WM_STAGES;
-    u32 *released = reinterpret_cast<u32 *>(wbar + 2);
+    // header at fixed offsets (so that the tile loop addresses everything as smem base + constant), then the two stages,
+    // the two-slot w_ccs ring and the digit tile
+    u64 *bars = reinterpret_cast<u64 *>(smem_raw);            // [tile full x2]
+    u64 *wbar = bars + WM_STAGES;                             // [piece full x2]
+    u32 *released = reinterpret_cast<u32 *>(wbar + 2);        // [x2]
+    WmCtx *cx = reinterpret_cast<WmCtx *>(smem_raw + 48);
+    unsigned char *stages = smem_raw + WM_HDR_BYTES;
 
-    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const StepJobs jobs = make_jobs(lay.ntiles, J, gridDim.x, blockIdx.x);
-    const u32 my_tiles = jobs.total(), njobs = jobs.njobs();
+    const u32 lane = threadIdx.x & 31;
     TRACE(0);
 #ifdef LAT_MAC_TRACE
     if (threadIdx.x == 0) {
@@ -760,74 +771,80 @@ wmac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, u64 *__restrict__ ws, 
         if (blockIdx.x < 8192) g_mac_trace[blockIdx.x * 8 + 5] = smid;
     }
 #endif
-
-    WmCtx *cx = reinterpret_cast<WmCtx *>(released + 2);
     // Flattened tile t of this CTA -> tile index of the matrix.  Everything the refill path needs is read from the
     // shared-memory context at the moment of use (the barriers in between keep those loads from being hoisted), so none
     // of it is live in registers across the tile loop.
     auto tile_of = [&](u32 t) -> u64 {
+        if (WM_DBG(16)) return (u64)blockIdx.x * 41 + t;  // tuning only: contiguous ranges (the last tiles are skipped)
         const u32 jj = cx->jobs.J, k = t / jj;  // full-round jobs have exactly J tiles, the leftover job comes last
         return cx->jobs.tile0(k) + (t - k * jj);
     };
-    auto witness_bytes = [&](u64 tile) { return (u32)min((u64)WM_TJ, cx->n - tile * WM_TJ) * FX * 8; };
-    auto issue_matrix = [&](u32 t, u32 st) {
+    auto issue_tile = [&](u32 t, u32 st, bool matrix, bool witness) {
         const u64 tile = tile_of(t);
-        mbar_arrive_expect_tx(&bars[st], WM_TILE_BYTES + witness_bytes(tile));
+        const u32 fb = (u32)min((u64)WM_TJ, cx->n - tile * WM_TJ) * FX * 8;
+        if (matrix) {
+            mbar_arrive_expect_tx(&bars[st], WM_TILE_BYTES + fb);
 #ifndef LAT_NO_L2_HINT
-        tma_bulk_g2s_hint(smem_raw + (size_t)st * WM_STAGE_BYTES, A_dev + tile * WM_TILE_ELEMS, WM_TILE_BYTES, &bars[st], L2_EVICT_FIRST);
+            tma_bulk_g2s_hint(stages + (size_t)st * WM_STAGE_BYTES, cx->A + tile * WM_TILE_ELEMS, WM_TILE_BYTES, &bars[st], L2_EVICT_FIRST);
 #else
-        tma_bulk_g2s(smem_raw + (size_t)st * WM_STAGE_BYTES, A_dev + tile * WM_TILE_ELEMS, WM_TILE_BYTES, &bars[st]);
+            tma_bulk_g2s(stages + (size_t)st * WM_STAGE_BYTES, cx->A + tile * WM_TILE_ELEMS, WM_TILE_BYTES, &bars[st]);
 #endif
+        }
+        if (witness) tma_bulk_g2s(stages + (size_t)st * WM_STAGE_BYTES + WM_TILE_BYTES, cx->fx + tile * WM_TJ * FX, fb, &bars[st]);
     };
-    auto issue_witness = [&](u32 t, u32 st) {
-        const u64 tile = tile_of(t);
-        tma_bulk_g2s(smem_raw + (size_t)st * WM_STAGE_BYTES + WM_TILE_BYTES, cx->fx + tile * WM_TJ * FX, witness_bytes(tile), &bars[st]);
-    };
+
     if (threadIdx.x == 0) {
-        cx->jobs = jobs;
-        cx->w = fw.w; cx->f16 = fw.f16; cx->fx = fw.fx; cx->flag = fw.flag;
-        cx->n = lay.n; cx->L = L; cx->log2b = (u32)fw.log2b; cx->piece_bytes = piece_bytes; cx->njobs = njobs;
-        cx->wring = wring; cx->dtile = dtile; cx->wbar = wbar;
+        const u32 L = (u32)fw.L, J = m * L;
+        cx->jobs = make_jobs(lay.ntiles, J, gridDim.x, blockIdx.x);
+        cx->w = fw.w; cx->f16 = fw.f16; cx->fx = fw.fx; cx->flag = fw.flag; cx->A = A_dev;
+        cx->n = lay.n; cx->L = L; cx->log2b = (u32)fw.log2b; cx->piece_bytes = wm_piece_bytes(m); cx->njobs = cx->jobs.njobs();
+        cx->wring = stages + WM_STAGES * WM_STAGE_BYTES;
+        cx->dtile = reinterpret_cast<int16_t *>(cx->wring + 2 * wm_piece_bytes(m));
+        cx->wbar = wbar;
+        cx->my_tiles = cx->jobs.total();
+        // Where in a job the NEXT job is transformed: at the latest possible tile for even CTAs, half a job earlier for odd
+        // ones.  The two CTAs of an SM are neighbours in blockIdx, so one of them is in its matrix loop (and alone has the
+        // SM's issue slots) while the other is in its transform, whose latency is thereby hidden.
+        cx->trigger = (J >= 4 && (blockIdx.x & 1)) ? (J / 2 >= WM_STAGES ? J / 2 - WM_STAGES : 0) : (J >= WM_STAGES ? J - WM_STAGES : 0);
         for (u32 st = 0; st < WM_STAGES; ++st) {
             mbar_init(&bars[st], 1);
             mbar_init(&wbar[st], 1);
             released[st] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (u32 t = 0; t < min((u32)WM_STAGES, my_tiles); ++t) issue_matrix(t, t);  // the matrix does not wait for anything
+        for (u32 t = 0; t < min((u32)WM_STAGES, cx->my_tiles); ++t) issue_tile(t, t, true, false);  // the matrix waits for nothing
         asm volatile("griddepcontrol.launch_dependents;");
         if (fw.ready_flag)  // a ticketed step: the upload runs on a copy engine, its ticket lands behind the data
             spin_until_equals(fw.ready_flag, fw.ready_value, fw.guard, SPIN_UPLOAD_TICKET, fw.ready_value);
-        for (u32 k = 0; k < min(2u, njobs); ++k) wm_issue_piece(*cx, k);
+        for (u32 k = 0; k < min(2u, cx->njobs); ++k) wm_issue_piece(*cx, k);
     }
     __syncthreads();
 
     u32 transformed = 0;  // jobs [0, transformed) have their witness rows in place
-    if (my_tiles) {
-        const u32 need = min((min((u32)WM_STAGES, my_tiles) - 1) / J, njobs - 1) + 1;
-        while (transformed < need) wm_transform<MONT>(cx, transformed++);
-        if (threadIdx.x == 0)
-            for (u32 t = 0; t < min((u32)WM_STAGES, my_tiles); ++t) issue_witness(t, t);
+    {
+        const u32 my_tiles = cx->my_tiles;
+        if (my_tiles) {
+            const u32 need = min((min((u32)WM_STAGES, my_tiles) - 1) / cx->jobs.J, cx->njobs - 1) + 1;
+            while (transformed < need) wm_transform<MONT>(cx, transformed++);
+            if (threadIdx.x == 0)
+                for (u32 t = 0; t < min((u32)WM_STAGES, my_tiles); ++t) issue_tile(t, t, false, true);
+        }
     }
-    // Where in a job the NEXT job is transformed: at the latest possible tile for even CTAs, half a job earlier for odd ones.
-    // The two CTAs of an SM are neighbours in blockIdx, so one of them is in its matrix loop (and alone has the SM's issue
-    // slots) while the other is in its transform, whose latency is thereby hidden.
-    const u32 trigger = (J >= 4 && (blockIdx.x & 1)) ? (J / 2 >= WM_STAGES ? J / 2 - WM_STAGES : 0) : (J >= WM_STAGES ? J - WM_STAGES : 0);
 
-    const u32 il = warp * 4 + (lane >> 3), s = lane & 7;  // RG = 8, CG = 1: warp w owns rows 4w .. 4w+3
     gl::Fq3Acc acc;
     acc.clear();
     u32 st = 0, ph = 0;
     bool ready = false;
     // tiles [t0, t1) of this CTA: the tile loop of mac_kernel<1,8>, free of calls so that the accumulators stay in registers
-    auto mac_tiles = [&](u32 t0, u32 t1) {
+    // (RG = 8, CG = 1: warp w owns rows 4w .. 4w+3, lane = (row within the group) * 8 + slot)
+    auto mac_tiles = [&](u32 t0, u32 t1, u32 my_tiles) {
         for (u32 t = t0; t < t1; ++t) {
             if (!ready) mbar_wait(&bars[st], ph);
 #ifdef LAT_MAC_TRACE
             if (t == 0) TRACE(1);
 #endif
-            const u64 *sa = reinterpret_cast<const u64 *>(smem_raw + (size_t)st * WM_STAGE_BYTES) + il * 8 + s;
-            const ulonglong2 *sf = reinterpret_cast<const ulonglong2 *>(smem_raw + (size_t)st * WM_STAGE_BYTES + WM_TILE_BYTES) + s * 3;
+            const u64 *sa = reinterpret_cast<const u64 *>(stages + (size_t)st * WM_STAGE_BYTES) + threadIdx.x;
+            const ulonglong2 *sf = reinterpret_cast<const ulonglong2 *>(stages + (size_t)st * WM_STAGE_BYTES + WM_TILE_BYTES) + (lane & 7) * 3;
             u32 st_n = st + 1, ph_n = ph;
             if (st_n == WM_STAGES) {
                 st_n = 0;
@@ -845,10 +862,7 @@ wmac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, u64 *__restrict__ ws, 
             if (lane == 0) {
                 if (atomicAdd(&released[st], 1u) == WM_THREADS / 32 - 1) {
                     released[st] = 0;
-                    if (t + WM_STAGES < my_tiles) {
-                        issue_matrix(t + WM_STAGES, st);
-                        issue_witness(t + WM_STAGES, st);
-                    }
+                    if (t + WM_STAGES < my_tiles) issue_tile(t + WM_STAGES, st, true, true);
                 }
             }
             st = st_n;
@@ -857,18 +871,20 @@ wmac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, u64 *__restrict__ ws, 
     };
     // Job by job; the NEXT job is transformed at a fixed tile of the current one (between two call-free tile loops).  A tile
     // requested while tile t runs is t + 2, so everything up to that tile's job must be in place before the second loop.
-    for (u32 tb = 0; tb < my_tiles; tb += J) {
-        const u32 te = min(my_tiles, tb + J), tm = min(te, tb + trigger);
-        mac_tiles(tb, tm);
-        const u32 need = min(max((te - 1 + WM_STAGES) / J, tb / J + 1), njobs - 1) + 1;
+    for (u32 tb = 0; tb < cx->my_tiles; tb += cx->jobs.J) {
+        const u32 my_tiles = cx->my_tiles, J = cx->jobs.J;
+        const u32 te = min(my_tiles, tb + J), tm = min(te, tb + cx->trigger);
+        mac_tiles(tb, tm, my_tiles);
+        const u32 need = min(max((te - 1 + WM_STAGES) / J, tb / J + 1), cx->njobs - 1) + 1;
         if (transformed < need) {
             while (transformed < need) wm_transform<MONT>(cx, transformed++);
             ready = false;
         }
-        mac_tiles(tm, te);
+        mac_tiles(tm, te, my_tiles);
     }
     TRACE(2);
 
+    const u32 il = threadIdx.x >> 3, s = lane & 7;
     // ===== epilogue: as mac_kernel ===============================================================================
     if (dependent_launch) asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous commitment's sums and output
     if (il < lay.kappa) {
