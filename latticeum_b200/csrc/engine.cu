@@ -292,50 +292,6 @@ struct lat_ajtai {
         last_op_was_mac = true;
         return LAT_OK;
     }
-    // Witness::from_w_ccs + commit as ONE launch (mac_kernel FUSED): possible when the matrix is one row block
-    bool fused_ok() const {
-        static const bool off = getenv("LAT_NO_FUSED") != nullptr;
-        return !off && lay.nrb == 1;
-    }
-    int mac_fused(const u64 *w_src, u64 w_len, u64 *fxp, int *flag_dev, u64 *cm_dev, bool chained,
-                  const unsigned long long *ready_flag = nullptr, unsigned long long ready_value = 0,
-                  const lat::MacReport &report = lat::MacReport()) {
-        lat::MacPlan plan = lat::plan_mac(lay, 1, sm_count);
-        int st = ws.ensure(plan.ws_elems * sizeof(u64));  // sized and zeroed at creation
-        if (st) return st;
-        cudaEvent_t e0 = nullptr, e1 = nullptr;
-        if (profiling) {
-            int i = ev_next;
-            ev_next = (ev_next + 1) % EV_POOL;
-            if ((st = drain_slot(i))) return st;
-            e0 = ev0[i];
-            e1 = ev1[i];
-            ev_pending[i] = 1;
-        }
-        lat::FusedWitness fw;
-        fw.w = w_src;
-        fw.w_len = w_len;
-        fw.log2b = (int)log2_B;
-        fw.L = (int)L;
-        fw.f16 = f16.as<int16_t>();
-        fw.fx = fxp;
-        fw.flag = flag_dev;
-        fw.ready_flag = ready_flag;
-        fw.ready_value = ready_value;
-        guard.timeout_ns = spin_timeout_ns();
-        fw.guard = guard;
-        static const bool no_pipelined = getenv("LAT_NO_WMAC") != nullptr;
-        if (lay.rg == 8 && L <= 8 && !no_pipelined)  // the zkVM's shape: interleaved jobs, transform inside the tile loop
-            lat::launch_step_commit(A.as<u64>(), lay, (uint32_t)(2 * sm_count), ws.as<u64>(), cm_dev, stream, mont, chained, fw, e0, e1,
-                                    report);
-        else
-            lat::launch_witness_mac(A.as<u64>(), lay, plan, ws.as<u64>(), cm_dev, stream, mont, chained, fw, e0, e1, report);
-        CK(cudaGetLastError());
-        has_resident = true;
-        last_mac_src = fxp;
-        last_op_was_mac = true;
-        return LAT_OK;
-    }
     // same for caller-supplied plain CRT-form witnesses (count x stride x 24): extend first
     int mac(const u64 *F, u64 stride, uint32_t count, u64 *cms_dev) {
         int st = fx.ensure((size_t)count * n * lat::FX_WORDS * sizeof(u64));
@@ -616,8 +572,6 @@ static int witness_core(lat_ajtai *h, const u64 *w_dev, u64 w_len, bool in_coeff
     u64 *fxp = h->fx.as<u64>();
     const bool chained = h->step_overlap && cm_dev && h->mac_was_last && !h->profiling;
     if (chained && h->last_mac_src == h->fx.p) fxp = h->fx_alt.as<u64>();
-    if (cm_dev && !in_coeff && !f_coeff_dev && !f_dev && h->fused_ok())  // one launch: transform per CTA, then its tiles
-        return h->mac_fused(w_dev, w_len, fxp, h->flag.as<int>(), cm_dev, chained, ready_flag, ready_value);
     h->guard.timeout_ns = spin_timeout_ns();
     lat::launch_witness(w_dev, w_len, (int)h->log2_B, (int)h->L, h->mont, in_coeff, h->f16.as<int16_t>(), f_coeff_dev,
                         f_dev, cm_dev ? fxp : nullptr, h->flag.as<int>(), h->stream, chained, ready_flag, ready_value, h->guard);
@@ -667,17 +621,6 @@ static int witness_enqueue(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool
             w_mapped = static_cast<const u64 *>(attr.devicePointer);
         else
             cudaGetLastError();  // pageable memory: not an error, take the copy path
-    }
-    if (cm_dev && !in_coeff && !d_fc && !d_f && !early_downloads && h->fused_ok()) {
-        // Commitment only: ONE launch.  Each CTA of the matrix-vector kernel reads the w_ccs elements behind its own
-        // columns (in place over PCIe when the buffer is page-locked) and starts on the matrix as soon as THEY have
-        // arrived, so the upload overlaps the matrix stream instead of preceding it.
-        const u64 *src = w_mapped;
-        if (!src) {
-            CK(cudaMemcpyAsync(h->in.p, w, in_bytes, cudaMemcpyHostToDevice, h->stream));
-            src = h->in.as<u64>();
-        }
-        return h->mac_fused(src, w_len, h->fx.as<u64>(), h->flag.as<int>(), cm_dev, false);
     }
     u64 nchunks = w_len >= 4096 ? 4 : 1;
     if (w_mapped) {
@@ -793,12 +736,9 @@ int lat_ajtai_submit_w_ccs(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_len, 
     u64 *fxp = h->fx.as<u64>();
     const bool chained = h->mac_was_last && !h->profiling;
     if (chained && h->last_mac_src == h->fx.p) fxp = h->fx_alt.as<u64>();
-    const bool fused = h->fused_ok();
-    if (!fused) {
-        lat::launch_witness(sl.in.as<u64>(), w_len, (int)h->log2_B, (int)h->L, h->mont, false, h->f16.as<int16_t>(), nullptr, nullptr,
-                            fxp, sl.flag.as<int>(), h->stream, chained, sl.ready.as<unsigned long long>(), tk, h->guard);
-        CK(cudaGetLastError());
-    }
+    lat::launch_witness(sl.in.as<u64>(), w_len, (int)h->log2_B, (int)h->L, h->mont, false, h->f16.as<int16_t>(), nullptr, nullptr,
+                        fxp, sl.flag.as<int>(), h->stream, chained, sl.ready.as<unsigned long long>(), tk, h->guard);
+    CK(cudaGetLastError());
     h->has_resident = true;
     // the matrix-vector kernel reports straight into mapped host memory: commitment, overflow flag, then the ticket
     lat::MacReport rep;
@@ -810,19 +750,13 @@ int lat_ajtai_submit_w_ccs(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_len, 
     if (!h->has_peers) {
         rep.done_host = done_dev;
         rep.done_value = tk;
-        if (fused) st = h->mac_fused(sl.in.as<u64>(), w_len, fxp, sl.flag.as<int>(), sl.cm.as<u64>(), chained,
-                                     sl.ready.as<unsigned long long>(), tk, rep);
-        else st = h->mac_fx(fxp, h->n, 1, sl.cm.as<u64>(), rep);
-        if (st) return st;
+        if ((st = h->mac_fx(fxp, h->n, 1, sl.cm.as<u64>(), rep))) return st;
     } else {
         // sharded: the matrix-vector kernel only moves the overflow flag; the exchange kernel behind it (part of the
         // same kernel chain) sums the partial commitments of all ranks and reports the full one
         u64 *cm_map = rep.cm_host;
         rep.cm_host = nullptr;
-        if (fused) st = h->mac_fused(sl.in.as<u64>(), w_len, fxp, sl.flag.as<int>(), sl.cm.as<u64>(), chained,
-                                     sl.ready.as<unsigned long long>(), tk, rep);
-        else st = h->mac_fx(fxp, h->n, 1, sl.cm.as<u64>(), rep);
-        if (st) return st;
+        if ((st = h->mac_fx(fxp, h->n, 1, sl.cm.as<u64>(), rep))) return st;
         lat::launch_exchange(sl.cm.as<u64>(), (u64)h->kappa * LAT_RING_DEGREE, h->peer_rank, h->peer_world, h->peers,
                              h->peer_epoch++, sl.out.as<u64>(), h->stream, cm_map, done_dev, tk, h->guard);
         CK(cudaGetLastError());

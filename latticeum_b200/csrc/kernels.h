@@ -105,33 +105,6 @@ void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_str
                 u64 *workspace, u64 *cms, cudaStream_t stream, cudaEvent_t ev_begin = nullptr,
                 cudaEvent_t ev_end = nullptr, const MacReport &report = MacReport());
 
-// Witness::from_w_ccs + commit in one launch: every CTA of the matrix-vector kernel first transforms the w_ccs elements
-// behind its own column range (iCRT -> digits -> CRT), then streams its tiles.  Needs one row block (kappa <= 32).
-//   w      : w_len elements, CRT form (device memory or mapped page-locked host memory)
-//   f16    : n x 24 int16 digits (written);   fx : n x 48 extended witness (written, then streamed by the same launch)
-//   flag   : OR-ed with 1 on digit overflow;   ready_flag / ready_value / guard: optional upload ticket (see SpinGuard)
-struct FusedWitness {
-    const u64 *w = nullptr;
-    u64 w_len = 0;
-    int log2b = 0, L = 0;
-    int16_t *f16 = nullptr;
-    u64 *fx = nullptr;
-    int *flag = nullptr;
-    const unsigned long long *ready_flag = nullptr;
-    unsigned long long ready_value = 0;
-    SpinGuard guard;
-};
-void launch_witness_mac(const u64 *A_dev, const MatLayout &lay, const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream,
-                        bool mont, bool chained, const FusedWitness &fw, cudaEvent_t ev_begin = nullptr,
-                        cudaEvent_t ev_end = nullptr, const MacReport &report = MacReport());
-
-// The pipelined form of the same (mac_kernels.cu, wmac_kernel): column ownership interleaved over the CTAs in jobs of L
-// tiles, each job's elements transformed right before its tiles are requested, w_ccs fetched two jobs ahead by bulk
-// copies -- the upload of a host-buffer call overlaps the matrix stream.  kappa in 29..32 (RG = 8) and L <= 8 only.
-void launch_step_commit(const u64 *A_dev, const MatLayout &lay, uint32_t grid_x, u64 *workspace, u64 *cms, cudaStream_t stream,
-                        bool mont, bool chained, const FusedWitness &fw, cudaEvent_t ev_begin = nullptr,
-                        cudaEvent_t ev_end = nullptr, const MacReport &report = MacReport());
-
 // cms[0] = cm - sum_{k=1..K-1} 2^k cms[k]      (LF/nifs/decomposition.rs:189-197)
 void launch_y0(const u64 *cm, u64 *cms, uint32_t K, uint32_t kappa, cudaStream_t stream);
 

@@ -32,7 +32,6 @@
 #include "kernels.h"
 #include "ring24.cuh"
 #include "spin.cuh"
-#include "witness_cta.cuh"
 
 namespace lat {
 using gl::u32;
@@ -217,19 +216,11 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define TRACE(k)
 #endif
 
-// FUSED (0 = off, 1 = canonical limbs, 2 = Montgomery limbs; PT = 1 and one row block only): the launch also runs
-// Witness::from_w_ccs.  Every CTA first transforms the w_ccs elements behind ITS OWN column range (witness_cta.cuh) --
-// reading them in place over PCIe when they live in mapped host memory -- writes the digits and the extended witness, and
-// then streams its tiles as usual.  No separate witness kernel, no grid-wide dependency between the two stages: a CTA
-// whose input has arrived starts on the matrix while its neighbours still wait for theirs, so the upload of a
-// host-buffer call overlaps the matrix stream instead of preceding it.
-template <int PT, int RG, int FUSED>
+template <int PT, int RG>
 __global__ void __launch_bounds__(MacGeo<PT, RG>::THREADS, MacGeo<PT, RG>::MIN_CTAS)
 mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__ Fx, u64 f_stride, uint32_t planes,
-           uint32_t stages, u64 *__restrict__ ws, u64 *__restrict__ cms, uint32_t dependent_launch, MacReport report,
-           FusedWitness fw) {
+           uint32_t stages, u64 *__restrict__ ws, u64 *__restrict__ cms, uint32_t dependent_launch, MacReport report) {
     using G = MacGeo<PT, RG>;
-    static_assert(!FUSED || PT == 1, "the fused launch commits one witness");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // after the stages: [full mbarrier x stages][release counter x stages]
     u64 *bars = reinterpret_cast<u64 *>(smem_raw + (size_t)stages * G::STAGE_BYTES);
@@ -300,40 +291,15 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
         // still draining.  The matrix does not depend on it, so the first tiles' matrix halves are requested at
         // once; only the witness halves wait for the producer grid to complete.
         const u32 pre = min(stages, my_tiles);
-        if constexpr (FUSED) {
-            // the last stage doubles as the transform's digit tile until the tile loop starts: prefetch into the others
-            for (u32 nt = 0; nt + 1 < pre; ++nt) issue_matrix(nt, nt);
-            asm volatile("griddepcontrol.launch_dependents;");
-        } else {
-            for (u32 nt = 0; nt < pre; ++nt) issue_matrix(nt, nt);
-            if (dependent_launch) asm volatile("griddepcontrol.wait;" ::: "memory");
-            // Only now may the kernel behind this one start (the next step's witness kernel, if the caller allows the
-            // overlap): once every CTA has passed its wait the producer grid -- and through its block 0 the previous
-            // commitment -- is complete, so that kernel can reuse the buffers of two steps back.
-            asm volatile("griddepcontrol.launch_dependents;");
-            for (u32 nt = 0; nt < pre; ++nt) issue_witness(nt, nt);
-        }
+        for (u32 nt = 0; nt < pre; ++nt) issue_matrix(nt, nt);
+        if (dependent_launch) asm volatile("griddepcontrol.wait;" ::: "memory");
+        // Only now may the kernel behind this one start (the next step's witness kernel, if the caller allows the
+        // overlap): once every CTA has passed its wait the producer grid -- and through its block 0 the previous
+        // commitment -- is complete, so that kernel can reuse the buffers of two steps back.
+        asm volatile("griddepcontrol.launch_dependents;");
+        for (u32 nt = 0; nt < pre; ++nt) issue_witness(nt, nt);
     }
     __syncthreads();
-    if constexpr (FUSED) {
-        if (fw.ready_flag) {  // a ticketed step: the upload runs on a copy engine, its ticket lands behind the data
-            if (threadIdx.x == 0) spin_until_equals(fw.ready_flag, fw.ready_value, fw.guard, SPIN_UPLOAD_TICKET, fw.ready_value);
-            __syncthreads();
-        }
-        const u64 col0 = t_begin * G::TJ, col1 = min(lay.n, t_end * G::TJ);
-        int16_t *tile = reinterpret_cast<int16_t *>(smem_raw + (size_t)(stages - 1) * G::STAGE_BYTES);
-        cta_witness<FUSED == 2>(fw.w, fw.w_len, fw.log2b, fw.L, col0, col1, fw.f16, fw.fx, fw.flag, tile);
-        // The extended witness was written through the generic proxy and is read back by bulk copies (async proxy), and
-        // the digit tile's stage is about to be overwritten by one: order both, on every writing thread, before the
-        // barrier behind which thread 0 issues the copies.
-        asm volatile("fence.proxy.async;" ::: "memory");
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const u32 pre = min(stages, my_tiles);
-            if (pre) issue_matrix(pre - 1, pre - 1);
-            for (u32 nt = 0; nt < pre; ++nt) issue_witness(nt, nt);
-        }
-    }
 
     const u32 rgi = warp / G::CG, cgi = warp % G::CG;
     const u32 il = rgi * 4 + (lane >> 3), s = lane & 7;
@@ -396,11 +362,6 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
     // its 32-bit halves and added with two 64-bit REDs into ws[2*idx], ws[2*idx+1] (a few hundred addends cannot
     // overflow); the last CTA to finish folds lo + 2^32 hi mod q into cms and leaves the workspace zeroed for the
     // next launch.  No second kernel, no partials round trip.
-    if constexpr (FUSED) {
-        // launched beside the tail of the previous commitment (programmatic launch): its workspace sums, its counter and
-        // its output must be complete before this grid adds to them
-        if (dependent_launch) asm volatile("griddepcontrol.wait;" ::: "memory");
-    }
     const u32 row = rbk * G::RB + il;
     if (row < lay.kappa) {
 #pragma unroll
@@ -495,27 +456,26 @@ MacPlan plan_mac(const MatLayout &lay, uint32_t planes, int sm_count) {
     return m;
 }
 
-template <int PT, int RG, int FUSED>
+template <int PT, int RG>
 static void launch_mac_t(dim3 grid, const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes,
-                         const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream, bool pdl, const MacReport &report,
-                         const FusedWitness &fw) {
+                         const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream, bool pdl, const MacReport &report) {
     // function attributes are per device: a process may hold handles on several GPUs
     static bool attr_set_on[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     bool &attr_set = attr_set_on[dev & 63];
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mac_kernel<PT, RG, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // minus the static bytes
-        if (e != cudaSuccess) fprintf(stderr, "lattice_ajtai: cudaFuncSetAttribute(mac_kernel<%d,%d,%d>): %s\n", PT, RG, FUSED, cudaGetErrorString(e));
+        cudaError_t e = cudaFuncSetAttribute(mac_kernel<PT, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // minus the static bytes
+        if (e != cudaSuccess) fprintf(stderr, "lattice_ajtai: cudaFuncSetAttribute(mac_kernel<%d,%d>): %s\n", PT, RG, cudaGetErrorString(e));
         attr_set = true;
     }
     if (getenv("LAT_DEBUG")) {
         cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, mac_kernel<PT, RG, FUSED>);
+        cudaFuncGetAttributes(&fa, mac_kernel<PT, RG>);
         int occ = -1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mac_kernel<PT, RG, FUSED>, MacGeo<PT, RG>::THREADS, plan.smem_bytes);
-        fprintf(stderr, "mac_kernel<%d,%d,%d>: grid=(%u,%u,%u) block=%d smem=%zu stages=%u regs=%d maxDyn=%d static=%zu occ=%d maxThreads=%d\n",
-                PT, RG, FUSED, grid.x, grid.y, grid.z, MacGeo<PT, RG>::THREADS, plan.smem_bytes, plan.stages, fa.numRegs,
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mac_kernel<PT, RG>, MacGeo<PT, RG>::THREADS, plan.smem_bytes);
+        fprintf(stderr, "mac_kernel<%d,%d>: grid=(%u,%u,%u) block=%d smem=%zu stages=%u regs=%d maxDyn=%d static=%zu occ=%d maxThreads=%d\n",
+                PT, RG, grid.x, grid.y, grid.z, MacGeo<PT, RG>::THREADS, plan.smem_bytes, plan.stages, fa.numRegs,
                 fa.maxDynamicSharedSizeBytes, fa.sharedSizeBytes, occ, fa.maxThreadsPerBlock);
     }
     cudaLaunchConfig_t cfg = {};
@@ -528,26 +488,22 @@ static void launch_mac_t(dim3 grid, const u64 *A_dev, const MatLayout &lay, cons
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, mac_kernel<PT, RG, FUSED>, A_dev, lay, Fx, f_stride, planes, plan.stages, workspace, cms,
-                       (uint32_t)(pdl ? 1 : 0), report, fw);
+    cudaLaunchKernelEx(&cfg, mac_kernel<PT, RG>, A_dev, lay, Fx, f_stride, planes, plan.stages, workspace, cms, (uint32_t)(pdl ? 1 : 0), report);
 }
 
-template <int PT, int FUSED>
+template <int PT>
 static void launch_mac_pt(dim3 grid, const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes,
-                          const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream, bool pdl, const MacReport &report,
-                          const FusedWitness &fw) {
-#define LAT_MAC_CASE(rg) launch_mac_t<PT, rg, FUSED>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report, fw)
+                          const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream, bool pdl, const MacReport &report) {
     switch (lay.rg) {
-        case 1: LAT_MAC_CASE(1); break;
-        case 2: LAT_MAC_CASE(2); break;
-        case 3: LAT_MAC_CASE(3); break;
-        case 4: LAT_MAC_CASE(4); break;
-        case 5: LAT_MAC_CASE(5); break;
-        case 6: LAT_MAC_CASE(6); break;
-        case 7: LAT_MAC_CASE(7); break;
-        default: LAT_MAC_CASE(8); break;
+        case 1: launch_mac_t<PT, 1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 2: launch_mac_t<PT, 2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 3: launch_mac_t<PT, 3>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 4: launch_mac_t<PT, 4>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 5: launch_mac_t<PT, 5>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 6: launch_mac_t<PT, 6>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 7: launch_mac_t<PT, 7>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        default: launch_mac_t<PT, 8>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
     }
-#undef LAT_MAC_CASE
 }
 
 void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes, const MacPlan &plan,
@@ -558,413 +514,8 @@ void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_str
     static const bool pdl_off = getenv("LAT_NO_PDL") != nullptr;
     const bool pdl = !ev_begin && !pdl_off;
     if (ev_begin) cudaEventRecord(ev_begin, stream);
-    const FusedWitness none{};
-    if (plan.pt == 1) launch_mac_pt<1, 0>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report, none);
-    else launch_mac_pt<2, 0>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report, none);
-    if (ev_end) cudaEventRecord(ev_end, stream);
-}
-
-// Witness::from_w_ccs + commit in ONE launch (see mac_kernel, FUSED).  chained: the previous kernel in the stream is this
-// handle's previous commitment and this launch may start beside its tail (it writes the OTHER witness buffer).
-void launch_witness_mac(const u64 *A_dev, const MatLayout &lay, const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream,
-                        bool mont, bool chained, const FusedWitness &fw, cudaEvent_t ev_begin, cudaEvent_t ev_end,
-                        const MacReport &report) {
-    dim3 grid(plan.grid_x, 1, 1);
-    static const bool pdl_off = getenv("LAT_NO_PDL") != nullptr;
-    const bool pdl = chained && !ev_begin && !pdl_off;
-    if (ev_begin) cudaEventRecord(ev_begin, stream);
-    if (mont) launch_mac_pt<1, 2>(grid, A_dev, lay, fw.fx, lay.n, 1, plan, workspace, cms, stream, pdl, report, fw);
-    else launch_mac_pt<1, 1>(grid, A_dev, lay, fw.fx, lay.n, 1, plan, workspace, cms, stream, pdl, report, fw);
-    if (ev_end) cudaEventRecord(ev_end, stream);
-}
-
-// ---- Witness::from_w_ccs + commit as one PIPELINED launch (kappa in 29..32: RG = 8, one row block) ----------------------------
-// The tile loop of mac_kernel<1,8>, with the witness transform folded in and the column ownership interleaved:
-//   * Work is cut into JOBS of L consecutive tiles = TJ * L columns = TJ whole w_ccs elements.  Job i of CTA c is job number
-//     i * gridDim.x + c of the vector, so all CTAs walk the vector front to back TOGETHER; what is left after the last full
-//     round is dealt out in tiles (jobs of 1..L tiles whose element range may overlap a neighbour's by one element: the
-//     transform is per element and every CTA writes only its own columns).
-//   * Before a job's first tile is requested, the CTA transforms the job's w_ccs elements -- iCRT, digits, CRT of the
-//     limbs -- and writes the digits and the extended witness rows (they stay in L2 until its own bulk copies fetch them a
-//     few microseconds later).  The elements themselves come in through a two-slot shared-memory ring filled by bulk
-//     copies TWO jobs ahead, straight from page-locked host memory when that is where w_ccs lives.
-// Hence a host-buffer call needs the first 1/9th of the upload before the matrix stream starts, not all of it: the PCIe
-// transfer (76 us at the zkVM's size) runs beside the 607 MB matrix stream instead of in front of it.  Device-resident
-// calls gain what the separate witness kernel cost (its launch, its tail, the grid-wide dependency): the two CTAs of an SM
-// are rarely in their transform at the same time, so one CTA's transform runs in the issue slots the other's wait leaves.
-struct StepJobs {   // the jobs of one CTA, in the order it runs them
-    u32 grid, cta, J, rounds_full;
-    u64 ntiles, left_base, left_off;  // first tile of the leftover region, this CTA's offset into it
-    u32 left_cnt;
-    __device__ __forceinline__ u32 njobs() const { return rounds_full + (left_cnt ? 1u : 0u); }
-    __device__ __forceinline__ u64 tile0(u32 k) const { return k < rounds_full ? ((u64)k * grid + cta) * J : left_base + left_off; }
-    __device__ __forceinline__ u32 count(u32 k) const { return k < rounds_full ? J : left_cnt; }
-    __device__ __forceinline__ u32 total() const { return rounds_full * J + left_cnt; }
-};
-__device__ __forceinline__ StepJobs make_jobs(u64 ntiles, u32 J, u32 grid, u32 cta) {
-    StepJobs j;
-    j.grid = grid; j.cta = cta; j.J = J; j.ntiles = ntiles;
-    j.rounds_full = (u32)(ntiles / ((u64)grid * J));
-    j.left_base = (u64)j.rounds_full * grid * J;
-    const u64 left = ntiles - j.left_base;          // < grid * J tiles
-    const u32 base = (u32)(left / grid), rem = (u32)(left % grid);
-    j.left_cnt = base + (cta < rem ? 1u : 0u);      // <= J
-    j.left_off = (u64)cta * base + min(cta, rem);
-    return j;
-}
-
-constexpr int WM_TJ = geo_tj(8), WM_RB = 32, WM_THREADS = 256, WM_STAGES = 2;
-constexpr u32 WM_TILE_ELEMS = WM_TJ * 3 * WM_RB * 8, WM_TILE_BYTES = WM_TILE_ELEMS * 8, WM_F_BYTES = WM_TJ * FX * 8;
-constexpr u32 WM_STAGE_BYTES = WM_TILE_BYTES + WM_F_BYTES;
-constexpr u32 WM_HDR_BYTES = 256;  // at offset 0: 2 tile barriers, 2 piece barriers, 2 release counters, the context (WmCtx)
-// A job of m * L tiles covers m * TJ whole elements when it is aligned (the full rounds) and touches at most one more when
-// it is not (the leftover job, which has at most as many tiles).
-__host__ __device__ constexpr u32 wm_piece_elems(u32 m) { return m * WM_TJ + 1; }
-__host__ __device__ constexpr u32 wm_piece_bytes(u32 m) { return wm_piece_elems(m) * ring::D * 8; }
-__host__ __device__ constexpr u32 wm_digit_bytes(u32 m, u32 L) { return wm_piece_elems(m) * L * ring::D * 2; }
-__host__ __device__ constexpr u32 wm_smem(u32 m, u32 L) {
-    return WM_HDR_BYTES + WM_STAGES * WM_STAGE_BYTES + 2 * wm_piece_bytes(m) + wm_digit_bytes(m, L);
-}
-constexpr u32 WM_SMEM_LIMIT = (228 * 1024 - 2 * 1024) / 2;  // two CTAs per SM, 1 KB reserved for each
-
-// What the transform of a job needs, kept in shared memory so that the (deliberately out-of-line) transform holds none of
-// it in registers across the tile loop: the loop itself then compiles exactly like mac_kernel<1,8>'s.
-struct WmCtx {
-    StepJobs jobs;
-    const u64 *w;
-    int16_t *f16;
-    u64 *fx;
-    int *flag;
-    u64 n;
-    u32 L, log2b, piece_bytes, njobs;
-    unsigned char *wring;
-    int16_t *dtile;
-    u64 *wbar;
-    const u64 *A;
-    u32 my_tiles, trigger;
-};
-static_assert(sizeof(WmCtx) + 48 <= WM_HDR_BYTES, "shared-memory header of wmac_kernel");
-__device__ __forceinline__ void wm_job_range(const WmCtx &cx, u32 k, u64 &c0, u64 &c1, u64 &e0, u64 &e1) {
-    c0 = cx.jobs.tile0(k) * WM_TJ;
-    c1 = min(cx.n, (cx.jobs.tile0(k) + cx.jobs.count(k)) * WM_TJ);
-    e0 = c0 / cx.L;
-    e1 = (c1 + cx.L - 1) / cx.L;
-}
-__device__ __forceinline__ void wm_issue_piece(const WmCtx &cx, u32 k) {  // one thread
-    u64 c0, c1, e0, e1;
-    wm_job_range(cx, k, c0, c1, e0, e1);
-    const u32 bytes = (u32)(e1 - e0) * ring::D * 8;
-    mbar_arrive_expect_tx(&cx.wbar[k & 1], bytes);
-    tma_bulk_g2s(cx.wring + (k & 1) * cx.piece_bytes, cx.w + e0 * ring::D, bytes, &cx.wbar[k & 1]);
-}
-// Transform of job k by the whole block: iCRT -> digits -> CRT of the limbs for the job's w_ccs elements (already in the
-// ring slot k & 1), digits and extended rows of the job's columns written to global memory; ends with the proxy fence
-// and a barrier, after which any thread may request those rows with a bulk copy.
-#ifdef LAT_WMAC_DEBUG
-__device__ int g_wmac_debug;  // tuning builds: 1 = no phase A arithmetic, 2 = no phase B arithmetic, 4 = no proxy fence,
-                              // 8 = no transform at all (no barriers either), 16 = contiguous tile order
-extern "C" int lat_debug_wmac(int v) { return (int)cudaMemcpyToSymbol(g_wmac_debug, &v, sizeof(int)); }
-#define WM_DBG(bit) (g_wmac_debug & (bit))
-#else
-#define WM_DBG(bit) 0
-#endif
-template <bool MONT>
-__device__ __noinline__ void wm_transform(const WmCtx *cxp, u32 k) {
-    const WmCtx &cx = *cxp;
-    if (WM_DBG(8)) return;
-    const u32 L = cx.L;
-    u64 c0, c1, e0, e1;
-    wm_job_range(cx, k, c0, c1, e0, e1);
-    const u32 ne = (u32)(e1 - e0);
-    mbar_wait(&cx.wbar[k & 1], (k >> 1) & 1);
-    {   // phase A: eight lanes per element, 32 elements per pass; warps whose octets are all out of range skip the pass
-        const u32 sl = threadIdx.x & 7;
-        const ring8::Twiddles tw = ring8::make_twiddles(sl);
-        const u64 Bd = 1ull << cx.log2b, halfB = Bd >> 1;
-        for (u32 base = 0; base < ne; base += WM_THREADS / 8) {
-            const u32 oct = base + (threadIdx.x >> 3);
-            if ((oct & ~3u) < ne && !WM_DBG(1)) {  // warp-uniform: the shuffles of an octet stay inside its warp
-                const bool valid = oct < ne;
-                const u64 *p = reinterpret_cast<const u64 *>(cx.wring + (k & 1) * cx.piece_bytes) + (valid ? oct : 0) * ring::D + 3 * sl;
-                u64 c[3] = {p[0], p[1], p[2]};
-                ring8::icrt8(c, tw);
-                bool negative[3];
-                u64 mg[3];
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    if constexpr (MONT) c[q] = gl::from_mont(c[q]);
-                    ring::signed_rep(c[q], negative[q], mg[q]);
-                }
-                int16_t *trow = cx.dtile + (valid ? oct : 0) * (L * ring::D) + 3 * sl;
-                for (u32 l = 0; l < L; ++l) {
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        u64 rem = mg[q] & (Bd - 1);
-                        mg[q] >>= cx.log2b;
-                        int dg = (int)rem;
-                        if (rem > halfB) {  // |rem| == b/2 is kept (balanced_decomposition/mod.rs:79)
-                            dg -= (int)Bd;
-                            mg[q] += 1;
-                        }
-                        if (negative[q]) dg = -dg;
-                        if (valid) trow[l * ring::D + q] = (int16_t)dg;
-                    }
-                }
-                if (valid && (mg[0] | mg[1] | mg[2])) atomicOr(cx.flag, 1);
-            }
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && k + 2 < cx.njobs) wm_issue_piece(cx, k + 2);  // the slot is free again
-    const u64 row0 = e0 * L;
-    const u32 nrows = ne * L;
-    {   // the resident int16 digits
-        const uint4 *src = reinterpret_cast<const uint4 *>(cx.dtile);
-        uint4 *dst = reinterpret_cast<uint4 *>(cx.f16 + row0 * ring::D);
-        for (u32 u = threadIdx.x; u < nrows * 3; u += WM_THREADS) {
-            const u64 row = row0 + u / 3;
-            if (row >= c0 && row < c1) dst[u] = src[u];
-        }
-    }
-    // phase B: one thread per limb element of [c0, c1)
-    for (u32 r = threadIdx.x; r < nrows; r += WM_THREADS) {
-        const u64 row = row0 + r;
-        if (row < c0 || row >= c1 || WM_DBG(2)) continue;
-        int d[ring::D];
-        load_i16x24_cta(cx.dtile + r * ring::D, d);
-        u64 x[ring::D];
-        r96::crt24_small<MONT>(d, x);
-        u64 *o = cx.fx + row * FX;
-#pragma unroll
-        for (int s2 = 0; s2 < ring::NSLOT; s2 += 2) {
-            const u64 a0 = x[3 * s2], a1 = x[3 * s2 + 1], a2 = x[3 * s2 + 2];
-            const u64 b0 = x[3 * s2 + 3], b1 = x[3 * s2 + 4], b2 = x[3 * s2 + 5];
-            st256(o + s2 * 6, a0, a1, a2, gl::add_lazy(a0, a1));
-            st256(o + s2 * 6 + 4, gl::add_lazy(a0, a2), gl::add_lazy(a1, a2), b0, b1);
-            st256(o + s2 * 6 + 8, b2, gl::add_lazy(b0, b1), gl::add_lazy(b0, b2), gl::add_lazy(b1, b2));
-        }
-    }
-    // the rows were written through the generic proxy and are fetched by bulk copies (async proxy) of THIS CTA
-    if (!WM_DBG(4)) asm volatile("fence.proxy.async;" ::: "memory");
-    __syncthreads();
-}
-
-template <bool MONT>
-__global__ void __launch_bounds__(WM_THREADS, 2)
-wmac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, u64 *__restrict__ ws, u64 *__restrict__ cms, uint32_t dependent_launch,
-            uint32_t m, MacReport report, FusedWitness fw) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    // header at fixed offsets (so that the tile loop addresses everything as smem base + constant), then the two stages,
-    // the two-slot w_ccs ring and the digit tile
-    u64 *bars = reinterpret_cast<u64 *>(smem_raw);            // [tile full x2]
-    u64 *wbar = bars + WM_STAGES;                             // [piece full x2]
-    u32 *released = reinterpret_cast<u32 *>(wbar + 2);        // [x2]
-    WmCtx *cx = reinterpret_cast<WmCtx *>(smem_raw + 48);
-    unsigned char *stages = smem_raw + WM_HDR_BYTES;
-
-    const u32 lane = threadIdx.x & 31;
-    TRACE(0);
-#ifdef LAT_MAC_TRACE
-    if (threadIdx.x == 0) {
-        unsigned smid;
-        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-        if (blockIdx.x < 8192) g_mac_trace[blockIdx.x * 8 + 5] = smid;
-    }
-#endif
-    // Flattened tile t of this CTA -> tile index of the matrix.  Everything the refill path needs is read from the
-    // shared-memory context at the moment of use (the barriers in between keep those loads from being hoisted), so none
-    // of it is live in registers across the tile loop.
-    auto tile_of = [&](u32 t) -> u64 {
-        if (WM_DBG(16)) return (u64)blockIdx.x * 41 + t;  // tuning only: contiguous ranges (the last tiles are skipped)
-        const u32 jj = cx->jobs.J, k = t / jj;  // full-round jobs have exactly J tiles, the leftover job comes last
-        return cx->jobs.tile0(k) + (t - k * jj);
-    };
-    auto issue_tile = [&](u32 t, u32 st, bool matrix, bool witness) {
-        const u64 tile = tile_of(t);
-        const u32 fb = (u32)min((u64)WM_TJ, cx->n - tile * WM_TJ) * FX * 8;
-        if (matrix) {
-            mbar_arrive_expect_tx(&bars[st], WM_TILE_BYTES + fb);
-#ifndef LAT_NO_L2_HINT
-            tma_bulk_g2s_hint(stages + (size_t)st * WM_STAGE_BYTES, cx->A + tile * WM_TILE_ELEMS, WM_TILE_BYTES, &bars[st], L2_EVICT_FIRST);
-#else
-            tma_bulk_g2s(stages + (size_t)st * WM_STAGE_BYTES, cx->A + tile * WM_TILE_ELEMS, WM_TILE_BYTES, &bars[st]);
-#endif
-        }
-        if (witness) tma_bulk_g2s(stages + (size_t)st * WM_STAGE_BYTES + WM_TILE_BYTES, cx->fx + tile * WM_TJ * FX, fb, &bars[st]);
-    };
-
-    if (threadIdx.x == 0) {
-        const u32 L = (u32)fw.L, J = m * L;
-        cx->jobs = make_jobs(lay.ntiles, J, gridDim.x, blockIdx.x);
-        cx->w = fw.w; cx->f16 = fw.f16; cx->fx = fw.fx; cx->flag = fw.flag; cx->A = A_dev;
-        cx->n = lay.n; cx->L = L; cx->log2b = (u32)fw.log2b; cx->piece_bytes = wm_piece_bytes(m); cx->njobs = cx->jobs.njobs();
-        cx->wring = stages + WM_STAGES * WM_STAGE_BYTES;
-        cx->dtile = reinterpret_cast<int16_t *>(cx->wring + 2 * wm_piece_bytes(m));
-        cx->wbar = wbar;
-        cx->my_tiles = cx->jobs.total();
-        // Where in a job the NEXT job is transformed: at the latest possible tile for even CTAs, half a job earlier for odd
-        // ones.  The two CTAs of an SM are neighbours in blockIdx, so one of them is in its matrix loop (and alone has the
-        // SM's issue slots) while the other is in its transform, whose latency is thereby hidden.
-        cx->trigger = (J >= 4 && (blockIdx.x & 1)) ? (J / 2 >= WM_STAGES ? J / 2 - WM_STAGES : 0) : (J >= WM_STAGES ? J - WM_STAGES : 0);
-        for (u32 st = 0; st < WM_STAGES; ++st) {
-            mbar_init(&bars[st], 1);
-            mbar_init(&wbar[st], 1);
-            released[st] = 0;
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (u32 t = 0; t < min((u32)WM_STAGES, cx->my_tiles); ++t) issue_tile(t, t, true, false);  // the matrix waits for nothing
-        asm volatile("griddepcontrol.launch_dependents;");
-        if (fw.ready_flag)  // a ticketed step: the upload runs on a copy engine, its ticket lands behind the data
-            spin_until_equals(fw.ready_flag, fw.ready_value, fw.guard, SPIN_UPLOAD_TICKET, fw.ready_value);
-        for (u32 k = 0; k < min(2u, cx->njobs); ++k) wm_issue_piece(*cx, k);
-    }
-    __syncthreads();
-
-    u32 transformed = 0;  // jobs [0, transformed) have their witness rows in place
-    {
-        const u32 my_tiles = cx->my_tiles;
-        if (my_tiles) {
-            const u32 need = min((min((u32)WM_STAGES, my_tiles) - 1) / cx->jobs.J, cx->njobs - 1) + 1;
-            while (transformed < need) wm_transform<MONT>(cx, transformed++);
-            if (threadIdx.x == 0)
-                for (u32 t = 0; t < min((u32)WM_STAGES, my_tiles); ++t) issue_tile(t, t, false, true);
-        }
-    }
-
-    gl::Fq3Acc acc;
-    acc.clear();
-    u32 st = 0, ph = 0;
-    bool ready = false;
-    // tiles [t0, t1) of this CTA: the tile loop of mac_kernel<1,8>, free of calls so that the accumulators stay in registers
-    // (RG = 8, CG = 1: warp w owns rows 4w .. 4w+3, lane = (row within the group) * 8 + slot)
-    auto mac_tiles = [&](u32 t0, u32 t1, u32 my_tiles) {
-        for (u32 t = t0; t < t1; ++t) {
-            if (!ready) mbar_wait(&bars[st], ph);
-#ifdef LAT_MAC_TRACE
-            if (t == 0) TRACE(1);
-#endif
-            const u64 *sa = reinterpret_cast<const u64 *>(stages + (size_t)st * WM_STAGE_BYTES) + threadIdx.x;
-            const ulonglong2 *sf = reinterpret_cast<const ulonglong2 *>(stages + (size_t)st * WM_STAGE_BYTES + WM_TILE_BYTES) + (lane & 7) * 3;
-            u32 st_n = st + 1, ph_n = ph;
-            if (st_n == WM_STAGES) {
-                st_n = 0;
-                ph_n ^= 1;
-            }
-            ready = (t + 1 < my_tiles) && mbar_test(&bars[st_n], ph_n);
-#pragma unroll
-            for (int jj = 0; jj < WM_TJ; ++jj) {
-                const u64 *pa = sa + jj * (3 * WM_RB * 8);
-                const u64 a0 = pa[0], a1 = pa[WM_RB * 8], a2 = pa[2 * WM_RB * 8];
-                const ulonglong2 x = sf[jj * (FX / 2)], y = sf[jj * (FX / 2) + 1], z = sf[jj * (FX / 2) + 2];
-                acc.mac(a0, a1, a2, x.x, x.y, y.x, y.y, z.x, z.y);
-            }
-            __syncwarp();
-            if (lane == 0) {
-                if (atomicAdd(&released[st], 1u) == WM_THREADS / 32 - 1) {
-                    released[st] = 0;
-                    if (t + WM_STAGES < my_tiles) issue_tile(t + WM_STAGES, st, true, true);
-                }
-            }
-            st = st_n;
-            ph = ph_n;
-        }
-    };
-    // Job by job; the NEXT job is transformed at a fixed tile of the current one (between two call-free tile loops).  A tile
-    // requested while tile t runs is t + 2, so everything up to that tile's job must be in place before the second loop.
-    for (u32 tb = 0; tb < cx->my_tiles; tb += cx->jobs.J) {
-        const u32 my_tiles = cx->my_tiles, J = cx->jobs.J;
-        const u32 te = min(my_tiles, tb + J), tm = min(te, tb + cx->trigger);
-        mac_tiles(tb, tm, my_tiles);
-        const u32 need = min(max((te - 1 + WM_STAGES) / J, tb / J + 1), cx->njobs - 1) + 1;
-        if (transformed < need) {
-            while (transformed < need) wm_transform<MONT>(cx, transformed++);
-            ready = false;
-        }
-        mac_tiles(tm, te, my_tiles);
-    }
-    TRACE(2);
-
-    const u32 il = threadIdx.x >> 3, s = lane & 7;
-    // ===== epilogue: as mac_kernel ===============================================================================
-    if (dependent_launch) asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous commitment's sums and output
-    if (il < lay.kappa) {
-        u64 c[3];
-        acc.finish(c[0], c[1], c[2]);
-        u64 *dst = ws + 2 * ((u64)il * ring::D + s * 3);
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            atomicAdd(reinterpret_cast<unsigned long long *>(dst + 2 * q), c[q] & 0xFFFFFFFFull);
-            atomicAdd(reinterpret_cast<unsigned long long *>(dst + 2 * q + 1), c[q] >> 32);
-        }
-    }
-    __shared__ u32 s_last;
-    const u64 nout = (u64)lay.kappa * ring::D;
-    u64 *counter = ws + 2 * nout;
-    __threadfence();
-    __syncthreads();
-    TRACE(3);
-    if (threadIdx.x == 0)
-        s_last = (atomicAdd(reinterpret_cast<unsigned long long *>(counter), 1ull) == gridDim.x - 1) ? 1u : 0u;
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        for (u64 i = threadIdx.x; i < nout; i += blockDim.x) {
-            const u64 lo = __ldcg(ws + 2 * i), hi = __ldcg(ws + 2 * i + 1);
-            const u64 v_lo = lo + (hi << 32);
-            const u64 v_hi = (hi >> 32) + (v_lo < lo ? 1ull : 0ull);
-            const u64 v = gl::reduce128(v_lo, v_hi);
-            cms[i] = v;
-            if (report.cm_host) report.cm_host[i] = v;
-            ws[2 * i] = 0;
-            ws[2 * i + 1] = 0;
-        }
-        if (threadIdx.x == 0) *counter = 0;
-        if (threadIdx.x == 0 && report.flag_dev) {
-            *report.flag_host = *reinterpret_cast<volatile int *>(report.flag_dev);
-            *report.flag_dev = 0;
-        }
-        if (report.done_host) {
-            __threadfence_system();
-            __syncthreads();
-            if (threadIdx.x == 0)
-                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(report.done_host), "l"(report.done_value) : "memory");
-        }
-    }
-    TRACE(4);
-}
-
-// kappa in 29..32 only (RG = 8, one row block), L <= 8; the caller checks.  grid_x CTAs, two per SM.
-void launch_step_commit(const u64 *A_dev, const MatLayout &lay, uint32_t grid_x, u64 *workspace, u64 *cms, cudaStream_t stream,
-                        bool mont, bool chained, const FusedWitness &fw, cudaEvent_t ev_begin, cudaEvent_t ev_end,
-                        const MacReport &report) {
-    static bool attr_set_on[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attr_set_on[dev & 63]) {
-        cudaFuncSetAttribute(wmac_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WM_SMEM_LIMIT);
-        cudaFuncSetAttribute(wmac_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WM_SMEM_LIMIT);
-        attr_set_on[dev & 63] = true;
-    }
-    // job = m * L tiles = m * TJ elements: as long as two CTAs still fit an SM, the larger job amortises the transform's
-    // latency over twice the tiles (and leaves the other CTA of the SM enough matrix work to cover it)
-    uint32_t m = 2;
-    if (const char *e = getenv("LAT_WMAC_M")) m = (uint32_t)atoi(e);
-    while (m > 1 && wm_smem(m, (uint32_t)fw.L) > WM_SMEM_LIMIT) --m;
-    static const bool pdl_off = getenv("LAT_NO_PDL") != nullptr;
-    const bool pdl = chained && !ev_begin && !pdl_off;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid_x);
-    cfg.blockDim = dim3(WM_THREADS);
-    cfg.dynamicSmemBytes = wm_smem(m, (uint32_t)fw.L);
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    if (ev_begin) cudaEventRecord(ev_begin, stream);
-    if (mont) cudaLaunchKernelEx(&cfg, wmac_kernel<true>, A_dev, lay, workspace, cms, (uint32_t)(pdl ? 1 : 0), m, report, fw);
-    else cudaLaunchKernelEx(&cfg, wmac_kernel<false>, A_dev, lay, workspace, cms, (uint32_t)(pdl ? 1 : 0), m, report, fw);
+    if (plan.pt == 1) launch_mac_pt<1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report);
+    else launch_mac_pt<2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report);
     if (ev_end) cudaEventRecord(ev_end, stream);
 }
 
