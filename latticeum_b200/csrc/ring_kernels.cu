@@ -87,6 +87,21 @@ __device__ __forceinline__ void row_put_fx(ulonglong2 *tile, int row, const u64 
         p[3 * sl + 2] = make_ulonglong2(gl::add_lazy(f0, f2), gl::add_lazy(f1, f2));
     }
 }
+// One thread writes its own extended row (384 B) with twelve 256-bit stores: every store covers a whole 32-byte sector and
+// the row's three 128-byte lines are complete before they leave L2, so there is nothing to read-merge and no staging tile.
+__device__ __forceinline__ void st256(u64 *p, u64 a, u64 b, u64 c, u64 d) {
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+__device__ __forceinline__ void store_fx_row(u64 *__restrict__ o, const u64 (&x)[ring::D]) {
+#pragma unroll
+    for (int s = 0; s < ring::NSLOT; s += 2) {
+        const u64 a0 = x[3 * s], a1 = x[3 * s + 1], a2 = x[3 * s + 2];
+        const u64 b0 = x[3 * s + 3], b1 = x[3 * s + 4], b2 = x[3 * s + 5];
+        st256(o + s * 6, a0, a1, a2, gl::add_lazy(a0, a1));
+        st256(o + s * 6 + 4, gl::add_lazy(a0, a2), gl::add_lazy(a1, a2), b0, b1);
+        st256(o + s * 6 + 8, b2, gl::add_lazy(b0, b1), gl::add_lazy(b0, b2), gl::add_lazy(b1, b2));
+    }
+}
 // block-wide: copy `nrows` rows of ROW_UNITS units from the padded tile to the contiguous global run at `dst`
 template <int ROW_UNITS>
 __device__ __forceinline__ void rows_out(const ulonglong2 *tile, u64 *__restrict__ dst, u32 nrows) {
@@ -175,7 +190,8 @@ __device__ __forceinline__ void load_i16x24(const int16_t *p, int (&d)[ring::D])
 // (ring24.cuh: no general multiplies) straight from the tile, written in the plain and/or the MAC kernel's
 // extended layout through the coalescing tile.  The small vector (19 763 elements) gets the 8x parallelism where
 // it needs it, the large one (98 815 limb elements) gets the cheap transform.
-// Dynamic shared memory: OPB*L rows x (FX_UNITS + 1) x 16 B for the output tile.
+// Dynamic shared memory: OPB*L rows x (PLAIN_UNITS + 1) x 16 B, only when the plain CRT-form output is wanted (the extended
+// rows go out with 256-bit stores straight from registers).
 constexpr int WIT_MAX_L = 8;
 template <bool MONT>
 __device__ __forceinline__ void witness_body(const u64 *__restrict__ w, u64 w_len, int log2b, int L, bool in_coeff,
@@ -243,10 +259,7 @@ __device__ __forceinline__ void witness_body(const u64 *__restrict__ w, u64 w_le
         if (active) row_put(otile, threadIdx.x, c);
         rows_out<PLAIN_UNITS>(otile, f_plain + elem0 * ring::D, nrows);
     }
-    if (fx) {
-        if (active) row_put_fx(otile, threadIdx.x, c);
-        rows_out<FX_UNITS>(otile, fx + elem0 * FX_WORDS, nrows);
-    }
+    if (fx && active) store_fx_row(fx + (elem0 + threadIdx.x) * FX_WORDS, c);
 }
 
 // Programmatic dependent launches on both sides of this kernel (see mac_kernel):
@@ -278,7 +291,7 @@ void launch_witness(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool i
                     const unsigned long long *ready_flag, unsigned long long ready_value, const SpinGuard &guard) {
     if (!w_len) return;
     unsigned grid = (unsigned)((w_len + OPB - 1) / OPB);
-    size_t smem = (f_plain || fx) ? (size_t)OPB * L * (FX_UNITS + 1) * 16 : 0;  // 32 KB at L = 5
+    size_t smem = f_plain ? (size_t)OPB * L * (PLAIN_UNITS + 1) * 16 : 0;  // staging tile of the plain output only
     if (smem + sizeof(int16_t) * OPB * WIT_MAX_L * ring::D > 48 * 1024) {
         cudaFuncSetAttribute(witness_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(witness_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -309,7 +322,7 @@ __global__ void __launch_bounds__(PLANE_THREADS)
 planes_kernel(const int16_t *__restrict__ f16, u64 n, int K, u64 *__restrict__ planes_f, u64 *__restrict__ planes_fx,
               u64 *__restrict__ planes_coeff) {
     asm volatile("griddepcontrol.launch_dependents;");  // the MAC behind it may start its prologue (see mac_kernel)
-    __shared__ __align__(16) ulonglong2 otile[PLANE_THREADS * (FX_UNITS + 1)];  // 25.6 KB
+    __shared__ __align__(16) ulonglong2 otile[PLANE_THREADS * (PLAIN_UNITS + 1)];  // staging for the plain outputs only
     const u64 e0 = (u64)blockIdx.x * PLANE_THREADS;
     const u64 e = e0 + threadIdx.x;
     const bool active = e < n;
@@ -342,10 +355,7 @@ planes_kernel(const int16_t *__restrict__ f16, u64 n, int K, u64 *__restrict__ p
                 if (active) row_put(otile, threadIdx.x, c);
                 rows_out<PLAIN_UNITS>(otile, planes_f + elem0 * ring::D, nrows);
             }
-            if (planes_fx) {
-                if (active) row_put_fx(otile, threadIdx.x, c);
-                rows_out<FX_UNITS>(otile, planes_fx + elem0 * FX_WORDS, nrows);
-            }
+            if (planes_fx && active) store_fx_row(planes_fx + ((u64)k * n + e) * FX_WORDS, c);
         }
     }
 }

@@ -42,7 +42,7 @@ def launches(tag, path):
         out.append((r[ix["ID"]], name, to_unit(r[ix["Metric Value"]], r[ix["Metric Unit"]], "us")))
     dst = os.path.join(ROOT, "profiles", f"{tag}_launches.csv")
     with open(dst, "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none: every launch of `python bench.py --steps 2 --warmup 1 --no-cpu`\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none: the first 400 launches of `python bench.py --steps 2 --warmup 1 --no-cpu --quick`\n")
         f.write("# (cold-cache, serialised: compare SHARES, not absolutes)\nid,kernel,duration_us\n")
         for i, n, v in out:
             f.write(f"{i},{n},{v:.2f}\n")
@@ -75,7 +75,8 @@ def report(tag, path):
         _written.add(short)
         out = {"kernel": d["Kernel Name"], "source_report": os.path.basename(path),
                "command": "ncu --set full --clock-control none --import-source on -k regex:<kernels> -c 6 python "
-                          + ("tools/run_fold_once.py" if "fold" in os.path.basename(path) else "bench.py --steps 2 --warmup 1 --no-cpu")}
+                          + ("tools/run_crt_once.py" if "crt" in os.path.basename(path) else "tools/run_ntt_once.py" if "ntt" in os.path.basename(path) else
+                             "tools/run_fold_once.py" if "fold" in os.path.basename(path) else "bench.py --steps 2 --warmup 1 --no-cpu --quick")}
         for k in KEYS:
             if k in d and d[k] not in ("", "n/a"):
                 out[k] = {"value": float(d[k]), "unit": u[k]}
