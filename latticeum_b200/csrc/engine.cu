@@ -227,6 +227,12 @@ struct lat_ajtai {
         bool busy = false;
     };
     Slot slots[LAT_PIPELINE_DEPTH];
+    // the same report path for ONE blocking host call: commitment, flag and a sequence number written into mapped host
+    // memory by the last CTA, polled by the caller -- no device-to-host copy, no stream synchronisation on the way back
+    u64 *blk_cm = nullptr;
+    int *blk_flag = nullptr;
+    volatile unsigned long long *blk_done = nullptr;
+    unsigned long long blk_seq = 0;
     // column sharding of the pipelined steps (lat_ajtai_set_peers)
     bool has_peers = false;
     int peer_rank = 0, peer_world = 1;
@@ -339,6 +345,11 @@ struct lat_ajtai {
             *sl.h_flag = 0;
             *sl.h_done = ~0ull;
         }
+        CK(cudaHostAlloc((void **)&blk_cm, cm_bytes, cudaHostAllocMapped));
+        CK(cudaHostAlloc((void **)&blk_flag, sizeof(int), cudaHostAllocMapped));
+        CK(cudaHostAlloc((void **)&blk_done, sizeof(unsigned long long), cudaHostAllocMapped));
+        *blk_flag = 0;
+        *blk_done = 0;
         return LAT_OK;
     }
 };
@@ -447,6 +458,9 @@ void lat_ajtai_destroy(lat_ajtai *h) {
         if (sl.h_done) cudaFreeHost((void *)sl.h_done);
         if (sl.h_ticket) cudaFreeHost(sl.h_ticket);
     }
+    if (h->blk_cm) cudaFreeHost(h->blk_cm);
+    if (h->blk_flag) cudaFreeHost(h->blk_flag);
+    if (h->blk_done) cudaFreeHost((void *)h->blk_done);
     for (cudaEvent_t e : h->ev0) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev1) cudaEventDestroy(e);
     for (cudaEvent_t ev : h->copy_done)
@@ -601,10 +615,15 @@ int lat_ajtai_witness_from_w_ccs_gated_dev(lat_ajtai *h, const uint64_t *w_ccs_d
                         (const unsigned long long *)ready_flag_dev, ready_value);
 }
 
+static int device_view(void *host, void **dev) {
+    CK(cudaHostGetDevicePointer(dev, host, 0));
+    return LAT_OK;
+}
+
 // Host-buffer w (w_ccs, or coefficients when in_coeff) -> resident digits (+ optional u64 outputs on the device) and,
 // with want_cm, the commitment in cm_dev.  Enqueues only; the caller copies results out and calls finish().
 static int witness_enqueue(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool in_coeff, u64 *d_fc, u64 *d_f, u64 *cm_dev,
-                           bool early_downloads = false) {
+                           bool early_downloads = false, const lat::MacReport &report = lat::MacReport()) {
     int st;
     const size_t in_bytes = w_len * ELEM_BYTES;
     if ((st = h->in.ensure(in_bytes))) return st;
@@ -653,7 +672,7 @@ static int witness_enqueue(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool
         CK(cudaStreamWaitEvent(h->copy_stream, h->witness_done, 0));
         h->copy_stream_busy = true;
     }
-    if (cm_dev && (st = h->mac_fx(h->fx.as<u64>(), h->n, 1, cm_dev))) return st;
+    if (cm_dev && (st = h->mac_fx(h->fx.as<u64>(), h->n, 1, cm_dev, report))) return st;
     if (nchunks > 1) {  // the next call's copies must not overtake this call's kernels reading h->in
         CK(cudaEventRecord(h->work_done, h->stream));
         CK(cudaStreamWaitEvent(h->copy_stream, h->work_done, 0));
@@ -673,6 +692,34 @@ static int witness_host(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool in
     if (f && (st = h->f.ensure(n_bytes))) return st;
     u64 *d_fc = f_coeff ? h->fcoeff64.as<u64>() : nullptr, *d_f = f ? h->f.as<u64>() : nullptr;
     const bool early = cm && (f_coeff16 || f_coeff || f);
+    static const bool no_report = getenv("LAT_NO_BLOCKING_REPORT") != nullptr;
+    if (cm && !early && !no_report) {
+        // Commitment only: nothing comes back but 6 KB, so the last CTA of the matrix-vector kernel writes it (with the
+        // overflow flag and a sequence number) straight into mapped host memory and this thread polls the number -- the
+        // way back costs one PCIe write latency instead of a copy launch plus a stream synchronisation.
+        lat::MacReport rep;
+        unsigned long long *done_dev = nullptr;
+        if ((st = device_view(h->blk_cm, (void **)&rep.cm_host)) || (st = device_view(h->blk_flag, (void **)&rep.flag_host)) ||
+            (st = device_view(const_cast<unsigned long long *>(h->blk_done), (void **)&done_dev)))
+            return st;
+        rep.flag_dev = h->flag.as<int>();
+        rep.done_host = done_dev;
+        const unsigned long long seq = rep.done_value = ++h->blk_seq;
+        if ((st = witness_enqueue(h, w, w_len, in_coeff, nullptr, nullptr, h->cms.as<u64>(), false, rep))) return st;
+        for (unsigned spins = 0; *h->blk_done != seq; ++spins) {
+            if ((spins & 0xffff) == 0xffff) {  // look at the stream now and then: a device fault must not hang the caller
+                cudaError_t e = cudaStreamQuery(h->stream);
+                if (e != cudaSuccess && e != cudaErrorNotReady) return fail_cuda(e, "lat_ajtai_witness_from_w_ccs", __LINE__);
+                if (e == cudaSuccess && *h->blk_done != seq) return fail(LAT_E_CUDA, "stream idle but the call never reported completion");
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        if ((st = spin_status(h->device))) return st;
+        memcpy(cm, h->blk_cm, (size_t)h->kappa * ELEM_BYTES);
+        if (*h->blk_flag)
+            return fail(LAT_E_DIGIT_OVERFLOW, "a coefficient needs more digits than the decomposition padding allows");
+        return LAT_OK;
+    }
     if ((st = witness_enqueue(h, w, w_len, in_coeff, d_fc, d_f, cm ? h->cms.as<u64>() : nullptr, early))) return st;
     if (cm) CK(cudaMemcpyAsync(cm, h->cms.p, (size_t)h->kappa * ELEM_BYTES, cudaMemcpyDeviceToHost, h->stream));
     cudaStream_t ds = early ? h->copy_stream : h->stream;  // with a commitment to compute, the downloads run beside it
@@ -710,11 +757,6 @@ int lat_ajtai_decompose_and_commit_coeff(lat_ajtai *h, const uint64_t *w_coeff, 
 // independent of the commitment (the host's own work of the same step, independent provers): the IVC steps of one
 // zkVM run are strictly dependent -- step i+1's z is built from fold(cm_i, w_i) (ZKVM/main.rs:140-156,174-182) -- so a
 // drop-in caller gets one ticket's latency per step, not the overlapped throughput.
-static int device_view(void *host, void **dev) {
-    CK(cudaHostGetDevicePointer(dev, host, 0));
-    return LAT_OK;
-}
-
 int lat_ajtai_submit_w_ccs(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_len, uint64_t *cm, uint64_t *ticket) {
     if (!h || !w_ccs || !cm || !ticket) return fail(LAT_E_INVALID_ARGUMENT, "NULL argument");
     if (w_len * h->L != h->n) return h->wrong_len(w_len * h->L);
