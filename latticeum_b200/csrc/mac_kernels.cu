@@ -160,9 +160,26 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 }
 
 // ---- witness -> extended layout (only for caller-supplied CRT-form witnesses; the CRT kernels emit it directly) -----
+// One thread per PAIR of slots: 48 bytes in (three 16-byte loads), 96 bytes out as three 256-bit stores -- whole 32-byte
+// sectors, so L2 never has to read-merge a half-written one (the 16-byte stores of round 1 ran at 3.2 TB/s).
 __global__ void __launch_bounds__(256)
-fext_kernel(const u64 *__restrict__ f, u64 count_slots, u64 *__restrict__ fx) {
+fext_kernel(const u64 *__restrict__ f, u64 count_pairs, u64 *__restrict__ fx) {
     asm volatile("griddepcontrol.launch_dependents;");  // the MAC behind it may start its prologue (see mac_kernel)
+    const u64 i = (u64)blockIdx.x * 256 + threadIdx.x;  // (element, slot pair)
+    if (i >= count_pairs) return;
+    const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(f + i * 6);
+    const ulonglong2 v0 = p[0], v1 = p[1], v2 = p[2];
+    const u64 a0 = gl::reduce128(v0.x, 0), a1 = gl::reduce128(v0.y, 0), a2 = gl::reduce128(v1.x, 0);
+    const u64 b0 = gl::reduce128(v1.y, 0), b1 = gl::reduce128(v2.x, 0), b2 = gl::reduce128(v2.y, 0);
+    u64 *o = fx + i * 12;
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(o), "l"(a0), "l"(a1), "l"(a2), "l"(gl::add_lazy(a0, a1)) : "memory");
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "l"(gl::add_lazy(a0, a2)), "l"(gl::add_lazy(a1, a2)), "l"(b0), "l"(b1) : "memory");
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(o + 8), "l"(b2), "l"(gl::add_lazy(b0, b1)), "l"(gl::add_lazy(b0, b2)), "l"(gl::add_lazy(b1, b2)) : "memory");
+}
+// unaligned callers (a witness pointer that is not 16-byte aligned): one thread per slot, 8-byte accesses
+__global__ void __launch_bounds__(256)
+fext_kernel_unaligned(const u64 *__restrict__ f, u64 count_slots, u64 *__restrict__ fx) {
+    asm volatile("griddepcontrol.launch_dependents;");
     u64 i = (u64)blockIdx.x * 256 + threadIdx.x;  // (element, slot)
     if (i >= count_slots) return;
     u64 f0 = f[i * 3], f1 = f[i * 3 + 1], f2 = f[i * 3 + 2];
@@ -173,9 +190,14 @@ fext_kernel(const u64 *__restrict__ f, u64 count_slots, u64 *__restrict__ fx) {
     o[2] = make_ulonglong2(gl::add_lazy(f0, f2), gl::add_lazy(f1, f2));
 }
 void launch_fext(const u64 *f, u64 count, u64 *fx, cudaStream_t stream) {
-    u64 slots = count * ring::NSLOT;
-    if (!slots) return;
-    fext_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(f, slots, fx);
+    if (!count) return;
+    if ((reinterpret_cast<uintptr_t>(f) & 15) == 0 && (reinterpret_cast<uintptr_t>(fx) & 31) == 0) {
+        const u64 pairs = count * (ring::NSLOT / 2);
+        fext_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, stream>>>(f, pairs, fx);
+    } else {
+        const u64 slots = count * ring::NSLOT;
+        fext_kernel_unaligned<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(f, slots, fx);
+    }
 }
 
 // ---- the MAC kernel --------------------------------------------------------------------------------------------
