@@ -498,6 +498,42 @@ def test_zkvm_fold_both_sides_realistic_and_f0(zkvm):
     assert np.array_equal(wit0.f_coeff, CO.icrt(exp))
 
 
+def test_zkvm_fold_step_begin_finish_full_size(zkvm):
+    """The GPU side of one IVC step's fold at the zkVM's full size (kappa = 32, n = 98 815; zk_latticefold.rs:37-102) through
+    lat_ajtai_fold_step_begin / _finish, two dependent steps, against the oracle and the reference's own properties."""
+    A, scheme = zkvm
+    rng = np.random.default_rng(11)
+    acc_fc = signed_to_fq(np.clip(np.rint(rng.normal(0.0, 350.0, size=(LB.N, 24))), -(2**15 - 1), 2**15 - 1).astype(np.int64))
+    acc_cm = CO.commit(A, CO.crt(acc_fc))
+    fs = LB.FoldStep(scheme)
+    fs.set_accumulator(acc_fc, LB.Commitment(acc_cm))
+    two = S.ntt_from_scalar(2)
+    for step in range(2):
+        w = steady_state_w(90 + step)
+        rho = CO.crt(signed_to_fq(rng.integers(-32, 32, size=(2 * DP.K, 24))))
+        cm, ys_acc, ys_step, d16 = fs.begin(w)
+        f_coeff, f = CO.witness_from_w_ccs(w, DP.B, DP.L)
+        assert np.array_equal(cm.as_ref(), CO.commit(A, f))
+        assert np.array_equal(d16.astype(np.int64), fq_to_signed(f_coeff))
+        # recomposed commitments equal the undecomposed ones, on both sides     LF/nifs/decomposition/tests/mod.rs:340-369
+        for ys, whole in ((ys_acc, acc_cm), (ys_step, cm.as_ref())):
+            acc = LB.Commitment.zeroed(LB.KAPPA)
+            for y in reversed(ys):
+                acc = acc * two + y
+            assert np.array_equal(acc.as_ref(), whole)
+        _, pf0, e_acc = CO.decompose_commit(A, acc_fc, acc_cm, 2, DP.K)
+        _, pf1, e_step = CO.decompose_commit(A, f_coeff, cm.as_ref(), 2, DP.K)
+        for k in (0, 1, 9, 14):
+            assert np.array_equal(ys_acc[k].as_ref(), e_acc[k]) and np.array_equal(ys_step[k].as_ref(), e_step[k]), (step, k)
+        cm0, f0d, f0, w0 = fs.finish(rho, want_f0=True, want_w_ccs=True)
+        e_f0 = CO.compute_f0(rho, [pf0[k] for k in range(DP.K)] + [pf1[k] for k in range(DP.K)])
+        e_f0c = CO.icrt(e_f0)
+        assert np.array_equal(f0, e_f0) and np.array_equal(f0d.astype(np.int64), fq_to_signed(e_f0c))
+        assert np.array_equal(w0, CO.gadget_recompose_ntt(e_f0, DP.B, DP.L))
+        assert scheme.commit(f0) == cm0  # the folded commitment is the commitment of the folded witness
+        acc_fc, acc_cm = e_f0c, cm0.as_ref().copy()
+
+
 def test_sharded_config_shape_n_2_20():
     """BASELINE configs[2] / SURVEY 8d case 4 on one GPU: kappa = 32, n = 2^20 (A = 6.44 GB), uniform f in CRT form.
     Rows are generated, uploaded and checked one at a time so that the host never holds the matrix."""
