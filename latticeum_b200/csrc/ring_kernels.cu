@@ -320,8 +320,11 @@ void launch_witness(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool i
 // each): plane k of it = sign * bit_k(|c|), transformed with the compile-time shift twiddles; every output goes
 // through the coalescing tile.
 constexpr int PLANE_THREADS = 64;
+#ifndef LAT_PLANES_BLOCKS
+#define LAT_PLANES_BLOCKS 8  // 128 registers: 156.8 us for pack + planes against 160.2 at 6 (168 registers); 10 and 12 spill and lose
+#endif
 template <bool MONT>
-__global__ void __launch_bounds__(PLANE_THREADS)
+__global__ void __launch_bounds__(PLANE_THREADS, LAT_PLANES_BLOCKS)
 planes_kernel(const int16_t *__restrict__ f16, u64 n, int K, u64 *__restrict__ planes_f, u64 *__restrict__ planes_fx,
               u64 *__restrict__ planes_coeff) {
     asm volatile("griddepcontrol.launch_dependents;");  // the MAC behind it may start its prologue (see mac_kernel)
