@@ -644,8 +644,10 @@ static int witness_enqueue(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool
     u64 nchunks = w_len >= 4096 ? 4 : 1;
     if (w_mapped) {
         nchunks = 0;
+        static const bool no_stage = getenv("LAT_NO_STAGE_INPUT") != nullptr;
+        const bool stage = !no_stage && (reinterpret_cast<uintptr_t>(w_mapped) & 15) == 0;  // bulk copies want 16-byte alignment
         lat::launch_witness(w_mapped, w_len, (int)h->log2_B, (int)h->L, h->mont, in_coeff, h->f16.as<int16_t>(), d_fc, d_f,
-                            d_fx, h->flag.as<int>(), h->stream);
+                            d_fx, h->flag.as<int>(), h->stream, false, nullptr, 0, lat::SpinGuard(), stage);
         CK(cudaGetLastError());
     }
     for (u64 c = 0; c < nchunks; ++c) {

@@ -31,10 +31,11 @@ void launch_icrt(const u64 *in, u64 *out, u64 count, cudaStream_t stream);
 //   f_plain  : CRT form, w_len*L x 24, or nullptr
 //   fx       : CRT form in the MAC kernel's extended layout, w_len*L x 48, or nullptr
 //   flag     : device int, OR-ed with 1 when a coefficient does not fit in L digits
+//   stage_input: w lives in mapped page-locked host memory: fetch each block's elements with one bulk copy (w 16-B aligned)
 void launch_witness(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool in_coeff, int16_t *f16, u64 *f_coeff,
                     u64 *f_plain, u64 *fx, int *flag, cudaStream_t stream, bool overlap_previous = false,
                     const unsigned long long *ready_flag = nullptr, unsigned long long ready_value = 0,
-                    const SpinGuard &guard = SpinGuard());
+                    const SpinGuard &guard = SpinGuard(), bool stage_input = false);
 
 // int16 coefficients -> K base-2 digit planes: plane k of element j = sign * bit_k(|c|).
 //   planes_f     : K x n x 24 CRT form, or nullptr

@@ -32,6 +32,7 @@
 #include "kernels.h"
 #include "ring24.cuh"
 #include "spin.cuh"
+#include "tma.cuh"
 
 namespace lat {
 using gl::u32;
@@ -101,62 +102,6 @@ void launch_relayout(const u64 *rows, uint32_t row0, uint32_t nrows, u64 row_str
     unsigned grid = (unsigned)((total + 255) / 256);
     if (mont) relayout_kernel<true><<<grid, 256, 0, stream>>>(rows, row0, nrows, row_stride, lay, A_dev);
     else relayout_kernel<false><<<grid, 256, 0, stream>>>(rows, row0, nrows, row_stride, lay, A_dev);
-}
-
-// ---- mbarrier / TMA bulk-copy primitives (inline PTX; SASS: SYNCS.*, UBLKCP) -------------------------------------
-__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(u64 *bar, u32 bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(u64 *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
-    u32 done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ bool mbar_test(u64 *bar, u32 parity) {  // non-blocking
-    u32 done;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return done != 0;
-}
-// L2 eviction-priority descriptors for bulk copies (the pre-encoded createpolicy values CUTLASS names
-// TMA::CacheHintSm90::EVICT_FIRST / EVICT_LAST).  The single-witness matrix stream is read exactly once per launch:
-// marking it evict-first keeps the 38 MB extended witness -- written by the kernel just before -- resident in the
-// 126 MB L2 instead of being pushed out to HBM and read back (ncu: 650 MB of DRAM reads for 607 MB of matrix).
-constexpr u64 L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
-__device__ __forceinline__ void tma_bulk_g2s_hint(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar, u64 policy) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
 }
 
 // ---- witness -> extended layout (only for caller-supplied CRT-form witnesses; the CRT kernels emit it directly) -----

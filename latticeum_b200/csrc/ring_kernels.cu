@@ -20,6 +20,7 @@
 #include "ring8.cuh"
 #include "ring96.cuh"
 #include "spin.cuh"
+#include "tma.cuh"
 
 namespace lat {
 using gl::u32;
@@ -196,16 +197,33 @@ constexpr int WIT_MAX_L = 8;
 template <bool MONT>
 __device__ __forceinline__ void witness_body(const u64 *__restrict__ w, u64 w_len, int log2b, int L, bool in_coeff,
                                              int16_t *__restrict__ f16, u64 *__restrict__ f_coeff, u64 *__restrict__ f_plain,
-                                             u64 *__restrict__ fx, int *__restrict__ flag) {
+                                             u64 *__restrict__ fx, int *__restrict__ flag, bool stage_input) {
     __shared__ __align__(16) int16_t tile[OPB * WIT_MAX_L * ring::D];  // [octet][limb][24] = 6 KB
+    __shared__ __align__(128) u64 wstage[OPB * ring::D];               // the block's input elements, 3 KB
+    __shared__ __align__(8) u64 wbar;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     ulonglong2 *otile = reinterpret_cast<ulonglong2 *>(dyn_smem);
     const Octet o = octet_of(w_len);
     const bool tiled = L <= WIT_MAX_L;  // the engine's L is <= 8; only lat_ring_gadget_decompose allows more
+    if (stage_input) {
+        // Input in page-locked HOST memory: one bulk copy per block fetches its 16 elements (3 KB) over PCIe as a few large
+        // read requests instead of 128 lanes' 8-byte loads; the lanes then read shared memory.
+        const u64 e0 = (u64)blockIdx.x * OPB;
+        if (threadIdx.x == 0) {
+            mbar_init(&wbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const u32 bytes = (u32)min((u64)OPB, w_len - e0) * ring::D * 8;
+            mbar_arrive_expect_tx(&wbar, bytes);
+            tma_bulk_g2s(wstage, w + e0 * ring::D, bytes, &wbar);
+        }
+        __syncthreads();
+        mbar_wait(&wbar, 0);
+    }
     {
         const ring8::Twiddles tw = ring8::make_twiddles(o.sl);
         u64 c[3];
-        load3(w, o.e, o.sl, c);
+        if (stage_input) load3(wstage, o.e - (u64)blockIdx.x * OPB, o.sl, c);
+        else load3(w, o.e, o.sl, c);
         if (!in_coeff) ring8::icrt8(c, tw);
         bool negative[3];
         u64 m[3];
@@ -276,7 +294,8 @@ template <bool MONT>
 __global__ void __launch_bounds__(THREADS, LAT_WITNESS_BLOCKS)
 witness_kernel(const u64 *__restrict__ w, u64 w_len, int log2b, int L, bool in_coeff, int16_t *__restrict__ f16,
                u64 *__restrict__ f_coeff, u64 *__restrict__ f_plain, u64 *__restrict__ fx, int *__restrict__ flag, int chained,
-               const unsigned long long *__restrict__ ready_flag, unsigned long long ready_value, SpinGuard guard) {
+               const unsigned long long *__restrict__ ready_flag, unsigned long long ready_value, SpinGuard guard,
+               int stage_input) {
     asm volatile("griddepcontrol.launch_dependents;");
     if (ready_flag) {
         // pipelined host-buffer steps: the input is uploaded by a copy engine on another stream, followed by a copy of
@@ -285,15 +304,16 @@ witness_kernel(const u64 *__restrict__ w, u64 w_len, int log2b, int L, bool in_c
         if (threadIdx.x == 0) spin_until_equals(ready_flag, ready_value, guard, SPIN_UPLOAD_TICKET, ready_value);
         __syncthreads();
     }
-    witness_body<MONT>(w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag);
+    witness_body<MONT>(w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag, stage_input != 0);
     if (chained && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 void launch_witness(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool in_coeff, int16_t *f16, u64 *f_coeff,
                     u64 *f_plain, u64 *fx, int *flag, cudaStream_t stream, bool overlap_previous,
-                    const unsigned long long *ready_flag, unsigned long long ready_value, const SpinGuard &guard) {
+                    const unsigned long long *ready_flag, unsigned long long ready_value, const SpinGuard &guard, bool stage_input) {
     if (!w_len) return;
     unsigned grid = (unsigned)((w_len + OPB - 1) / OPB);
+    const int stage = stage_input ? 1 : 0;
     size_t smem = f_plain ? (size_t)OPB * L * (PLAIN_UNITS + 1) * 16 : 0;  // staging tile of the plain output only
     if (smem + sizeof(int16_t) * OPB * WIT_MAX_L * ring::D > 48 * 1024) {
         cudaFuncSetAttribute(witness_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -310,8 +330,8 @@ void launch_witness(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool i
     cfg.attrs = attr;
     cfg.numAttrs = overlap_previous ? 1 : 0;
     const int chained = overlap_previous ? 1 : 0;
-    if (mont) cudaLaunchKernelEx(&cfg, witness_kernel<true>, w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag, chained, ready_flag, ready_value, guard);
-    else cudaLaunchKernelEx(&cfg, witness_kernel<false>, w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag, chained, ready_flag, ready_value, guard);
+    if (mont) cudaLaunchKernelEx(&cfg, witness_kernel<true>, w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag, chained, ready_flag, ready_value, guard, stage);
+    else cudaLaunchKernelEx(&cfg, witness_kernel<false>, w, w_len, log2b, L, in_coeff, f16, f_coeff, f_plain, fx, flag, chained, ready_flag, ready_value, guard, stage);
 }
 
 // ---- int16 coefficients -> K sign*bit planes, each CRT'd ---------------------------------------------------
