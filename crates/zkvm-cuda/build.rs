@@ -14,7 +14,6 @@ fn main() {
         .file(format!("{src}/engine.cu"))
         .file(format!("{src}/ring_kernels.cu"))
         .file(format!("{src}/mac_kernels.cu"))
-        .file(format!("{src}/step_kernel.cu"))
         .file(format!("{src}/ntt_pow2.cu"))
         .compile("lattice_ajtai");
     println!("cargo:rustc-link-lib=stdc++");

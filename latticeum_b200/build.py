@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "liblattice_ajtai.so")
-SOURCES = ["engine.cu", "ring_kernels.cu", "mac_kernels.cu", "step_kernel.cu", "ntt_pow2.cu"]
+SOURCES = ["engine.cu", "ring_kernels.cu", "mac_kernels.cu", "ntt_pow2.cu"]
 HEADERS = ["goldilocks.cuh", "ring24.cuh", "ring8.cuh", "ring96.cuh", "spin.cuh", "tma.cuh", "kernels.h", os.path.join("..", "..", "include", "lattice_ajtai.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

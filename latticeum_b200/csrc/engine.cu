@@ -209,7 +209,6 @@ struct lat_ajtai {
     DevBuf cms;          // up to max(K, batch) x kappa x 24
     DevBuf cm_in;        // kappa x 24
     DevBuf ws;           // mac partials
-    DevBuf step_sync;    // counters of the one-launch step kernel (zero between launches)
     DevBuf flag;         // int
     int *h_flag = nullptr;  // pinned
     bool has_resident = false;
@@ -296,41 +295,6 @@ struct lat_ajtai {
         lat::launch_mac(A.as<u64>(), lay, Fx, stride, count, plan, ws.as<u64>(), cms_dev, stream, e0, e1, report);
         CK(cudaGetLastError());
         last_mac_src = Fx;
-        last_op_was_mac = true;
-        return LAT_OK;
-    }
-    // Witness::from_w_ccs + commit as ONE cooperative launch (step_kernel.cu): transform CTAs and matrix CTAs side by side,
-    // the matrix stream starts when the first chunk is transformed.  The zkVM's shape only; anything else, or a grid that
-    // cannot be co-resident, takes the two-kernel chain (returns 1 = "not taken").
-    int step_launch(const u64 *w_src, u64 w_len, u64 *cm_dev, const lat::MacReport &report = lat::MacReport()) {
-        static const bool off = getenv("LAT_NO_STEP_KERNEL") != nullptr;
-        if (off || lay.rg != 8 || lay.nrb != 1 || L > 8 || (reinterpret_cast<uintptr_t>(w_src) & 15)) return 1;
-        cudaEvent_t e0 = nullptr, e1 = nullptr;
-        int st;
-        if (profiling) {
-            int i = ev_next;
-            ev_next = (ev_next + 1) % EV_POOL;
-            if ((st = drain_slot(i))) return st;
-            e0 = ev0[i];
-            e1 = ev1[i];
-            ev_pending[i] = 1;
-        }
-        lat::FusedWitness fw;
-        fw.w = w_src;
-        fw.w_len = w_len;
-        fw.log2b = (int)log2_B;
-        fw.L = (int)L;
-        fw.f16 = f16.as<int16_t>();
-        fw.fx = fx.as<u64>();
-        fw.flag = flag.as<int>();
-        guard.timeout_ns = spin_timeout_ns();
-        fw.guard = guard;
-        if (lat::launch_step(A.as<u64>(), lay, sm_count, ws.as<u64>(), cm_dev, step_sync.as<uint32_t>(), stream, mont, fw, e0, e1, report)) {
-            if (profiling) ev_pending[(ev_next + EV_POOL - 1) % EV_POOL] = 0;
-            return 1;  // not launched (does not fit): the caller falls back
-        }
-        has_resident = true;
-        last_mac_src = fx.p;
         last_op_was_mac = true;
         return LAT_OK;
     }
@@ -459,8 +423,6 @@ int lat_ajtai_create(lat_ajtai **out, uint32_t kappa, uint64_t n, uint32_t log2_
             if ((st = h->ws.ensure(lat::plan_mac(h->lay, max_planes, h->sm_count).ws_elems * sizeof(u64)))) break;
             if ((e = cudaMemsetAsync(h->ws.p, 0, h->ws.bytes, h->stream)) != cudaSuccess) break;
         }
-        if ((st = h->step_sync.ensure(lat::step_sync_bytes()))) break;
-        if ((e = cudaMemsetAsync(h->step_sync.p, 0, h->step_sync.bytes, h->stream)) != cudaSuccess) break;
         if ((st = spin_guard(device, h->guard))) break;
         if ((st = h->slots_init())) break;
         if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) break;
@@ -481,7 +443,7 @@ void lat_ajtai_destroy(lat_ajtai *h) {
     if (h->stream && h->stream != h->own_stream) cudaStreamSynchronize(h->stream);  // steps in flight write into our buffers
     DevBuf *bufs[] = {&h->A, &h->stage, &h->in, &h->f16, &h->f, &h->fx, &h->fcoeff64, &h->planes, &h->planes_fx[0], &h->planes_fx[1],
                       &h->rho, &h->f0, &h->planes_coeff, &h->cms, &h->cm_in, &h->ws, &h->flag, &h->fx_alt,
-                      &h->f16_acc, &h->cms_side[0], &h->cms_side[1], &h->cm_step, &h->cm_acc, &h->step_sync};
+                      &h->f16_acc, &h->cms_side[0], &h->cms_side[1], &h->cm_step, &h->cm_acc};
     for (DevBuf *b : bufs) b->release();
     if (h->h_flag) cudaFreeHost(h->h_flag);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
@@ -623,10 +585,6 @@ static int witness_core(lat_ajtai *h, const u64 *w_dev, u64 w_len, bool in_coeff
     // makes the buffer of two steps back safe to reuse).  Event brackets (profiling) serialise the launches anyway.
     u64 *fxp = h->fx.as<u64>();
     const bool chained = h->step_overlap && cm_dev && h->mac_was_last && !h->profiling;
-    if (cm_dev && !in_coeff && !f_coeff_dev && !f_dev && !ready_flag && !h->step_overlap) {
-        const int st = h->step_launch(w_dev, w_len, cm_dev);
-        if (st != 1) return st;
-    }
     if (chained && h->last_mac_src == h->fx.p) fxp = h->fx_alt.as<u64>();
     h->guard.timeout_ns = spin_timeout_ns();
     lat::launch_witness(w_dev, w_len, (int)h->log2_B, (int)h->L, h->mont, in_coeff, h->f16.as<int16_t>(), f_coeff_dev,
@@ -682,12 +640,6 @@ static int witness_enqueue(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool
             w_mapped = static_cast<const u64 *>(attr.devicePointer);
         else
             cudaGetLastError();  // pageable memory: not an error, take the copy path
-    }
-    if (cm_dev && !in_coeff && !d_fc && !d_f && !early_downloads && w_mapped) {
-        // commitment only, page-locked input: one launch whose transform CTAs read w_ccs in place, chunk by chunk, while
-        // its matrix CTAs already stream the chunks that are done (step_kernel.cu)
-        st = h->step_launch(w_mapped, w_len, cm_dev, report);
-        if (st != 1) return st;
     }
     u64 nchunks = w_len >= 4096 ? 4 : 1;
     if (w_mapped) {

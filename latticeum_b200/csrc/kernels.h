@@ -17,7 +17,7 @@ struct SpinGuard {
     unsigned long long *status = nullptr;
     unsigned long long timeout_ns = 0;
 };
-constexpr unsigned long long SPIN_UPLOAD_TICKET = 1, SPIN_PEER_FLAG = 2, SPIN_CHUNK = 3;
+constexpr unsigned long long SPIN_UPLOAD_TICKET = 1, SPIN_PEER_FLAG = 2;
 
 // ---- ring_kernels.cu ------------------------------------------------------------------------------------
 // Batched CRT / iCRT of `count` ring elements of 24 u64 (in-place allowed).
@@ -105,27 +105,6 @@ struct MacReport {
 void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes, const MacPlan &plan,
                 u64 *workspace, u64 *cms, cudaStream_t stream, cudaEvent_t ev_begin = nullptr,
                 cudaEvent_t ev_end = nullptr, const MacReport &report = MacReport());
-
-// ---- step_kernel.cu: Witness::from_w_ccs + commit as one cooperative launch (kappa in 29..32, L <= 8) -------------------------
-//   w      : w_len elements, CRT form (device memory or mapped page-locked host memory, 16-byte aligned)
-//   f16    : n x 24 int16 digits (written);   fx : n x 48 extended witness (written by the transform CTAs, streamed by the others)
-//   flag   : OR-ed with 1 on digit overflow;   ready_flag / ready_value: optional upload ticket;   guard: bound on every wait
-struct FusedWitness {
-    const u64 *w = nullptr;
-    u64 w_len = 0;
-    int log2b = 0, L = 0;
-    int16_t *f16 = nullptr;
-    u64 *fx = nullptr;
-    int *flag = nullptr;
-    const unsigned long long *ready_flag = nullptr;
-    unsigned long long ready_value = 0;
-    SpinGuard guard;
-};
-size_t step_sync_bytes();  // zero-initialised device scratch the kernel keeps clean (arrival, role and chunk counters)
-// 0 = launched; a cudaError_t (as int) when the cooperative launch is not possible: the caller falls back to two kernels
-int launch_step(const u64 *A_dev, const MatLayout &lay, int sm_count, u64 *workspace, u64 *cms, uint32_t *sync, cudaStream_t stream,
-                bool mont, const FusedWitness &fw, cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr,
-                const MacReport &report = MacReport());
 
 // cms[0] = cm - sum_{k=1..K-1} 2^k cms[k]      (LF/nifs/decomposition.rs:189-197)
 void launch_y0(const u64 *cm, u64 *cms, uint32_t K, uint32_t kappa, cudaStream_t stream);

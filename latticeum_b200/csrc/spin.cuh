@@ -32,24 +32,4 @@ __device__ __forceinline__ bool spin_until_equals(const unsigned long long *word
     }
 }
 
-// The same for a 32-bit counter written by other CTAs of this GPU (acquire, gpu scope).
-__device__ __forceinline__ bool spin_until_equals_u32(const unsigned int *word, unsigned int want, const SpinGuard &g,
-                                                      unsigned long long code, unsigned long long detail) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(word) : "memory");
-    if (v == want) return true;
-    const unsigned long long t0 = global_timer_ns();
-    for (unsigned spins = 0;; ++spins) {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(word) : "memory");
-        if (v == want) return true;
-        if ((spins & 63) == 63 && g.timeout_ns && global_timer_ns() - t0 > g.timeout_ns) {
-            if (g.status) {
-                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(g.status), "l"(code | (detail << 8)) : "memory");
-                __threadfence_system();
-            }
-            return false;
-        }
-    }
-}
-
 }  // namespace lat
