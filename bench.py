@@ -170,6 +170,19 @@ def imad_peak():
         return {"error": f"{type(e).__name__}: {e}"}
 
 
+def bench_config(n_gpus):
+    """`config` of the JSON line: IDENTICAL in both arms (ours and --impl reference), so that the driver's same-config check
+    compares like with like; everything arm-specific goes to `details`."""
+    if n_gpus <= 1:
+        return {"workload": "zkvm_step_witness_commit", "kappa": KAPPA, "w_len": W_LEN, "n": N_COLS, "d": 24,
+                "B": 1 << LOG2_B, "L": L_LIMBS,
+                "pipeline": "iCRT -> gadget_decompose(2^15,5) -> CRT -> A*f (Witness::from_w_ccs + commit)",
+                "l2": "inputs larger than L2 (607 MB matrix streamed every step)"}
+    return {"workload": "sharded_commit_ntt_n_2_20", "kappa": KAPPA, "n_total": N_SHARDED, "d": 24,
+            "pipeline": "A * f for one CRT-form witness of n = 2^20 (commit_ntt), columns split over the GPUs",
+            "l2": "inputs larger than L2 (6.44 GB matrix streamed every step)"}
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -217,8 +230,6 @@ def run_reference(args):
         units = sample_w * L_LIMBS
         sample = (f"first {sample_w} of {W_LEN} w_ccs elements ({units} of {N_COLS} columns), kappa={KAPPA}; "
                   "throughput is linear in columns")
-        config = {"workload": "zkvm_step_witness_commit", "kappa": KAPPA, "w_len": W_LEN, "n": N_COLS, "d": 24,
-                  "B": 1 << LOG2_B, "L": L_LIMBS, "cpu_impl": "C restatement of the reference's rayon path (oracle/), OpenMP"}
         scaling = "weak"
     else:
         # configs[4]: commit_ntt of a CRT-form witness of n = 2^20 (the matrix-vector product alone), bounded sample
@@ -235,8 +246,6 @@ def run_reference(args):
         step = lambda: CO.commit(A, f)  # noqa: E731
         units = cols
         sample = f"first {cols} of {N_SHARDED} columns, kappa={KAPPA}; throughput is linear in columns"
-        config = {"workload": "sharded_commit_ntt_n_2_20", "kappa": KAPPA, "n_total": N_SHARDED, "d": 24,
-                  "cpu_impl": "C restatement of the reference's rayon path (oracle/), OpenMP"}
         scaling = "strong"
     for _ in range(args.warmup):
         step()
@@ -248,7 +257,9 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": scaling,
-        "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": bench_config(args.gpus),
+        "details": {"cpu_impl": "C restatement of the reference's rayon path (oracle/), OpenMP; canonical limbs (the arithmetic is "
+                                "representation-independent)"},
         "commitments_per_s": value / (N_COLS if args.gpus <= 1 else N_SHARDED),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -521,11 +532,9 @@ def run_single(args, ctx):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
-        "config": {"workload": "zkvm_step_witness_commit", "kappa": KAPPA, "w_len": W_LEN, "n": N_COLS, "d": 24,
-                   "B": 1 << LOG2_B, "L": L_LIMBS, "repr": args.repr,
-                   "pipeline": "iCRT -> gadget_decompose(2^15,5) -> CRT -> A*f (Witness::from_w_ccs + commit)",
-                   "l2": "inputs larger than L2 (607 MB matrix streamed every step)",
-                   "dependency": "value and e2e time dependent steps (no cross-step overlap, one blocking call per step)"},
+        "config": bench_config(1),
+        "details": {"repr": args.repr,
+                    "dependency": "value and e2e time dependent steps (no cross-step overlap, one blocking call per step)"},
         "commitments_per_s": 1e3 / ms_per_step,
         "e2e": e2e, "gpu_launches": args.steps * 2,
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_vs_cpu": parity,
@@ -768,12 +777,11 @@ def run_sharded(args, ctx):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
-        "config": {"workload": "sharded_commit_ntt_n_2_20", "kappa": KAPPA, "n_total": N_SHARDED, "n_per_gpu": n_local, "d": 24,
-                   "pipeline": "per rank: extend(f block) -> A block * f block; then one exchange of the 6 KB partials, summed mod q",
-                   "sharding": f"columns x{world}; exchange = {sharded.exchange}",
-                   "l2": f"inputs larger than L2 ({alg_bytes / 1e6:.0f} MB matrix block streamed every step)",
-                   "note": "N = 1 of this bench is the zkVM-width step commit (configs[1]); the one-GPU figure of THIS workload is "
-                           "the N = 1 line's n_2_20_single_gpu"},
+        "config": bench_config(world),
+        "details": {"n_per_gpu": n_local, "sharding": f"columns x{world}; exchange = {sharded.exchange}",
+                    "per_rank": "extend(f block) -> A block * f block; then one exchange of the 6 KB partials, summed mod q",
+                    "note": "N = 1 of this bench is the zkVM-width step commit (configs[1]); the one-GPU figure of THIS workload is "
+                            "the N = 1 line's n_2_20_single_gpu"},
         "commitments_per_s": 1e3 / ms_per_step,
         "e2e": e2e, "gpu_launches": args.steps * (3 if sharded.exchange == "p2p" else 3),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_vs_cpu": parity,
