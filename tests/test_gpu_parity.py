@@ -369,6 +369,54 @@ def test_commit_pipeline_errors():
     scheme.close()
 
 
+@pytest.mark.parametrize("log2_B,L,K", [(8, 8, 9), (12, 6, 13), (15, 5, 15), (4, 3, 5), (1, 2, 2)])
+@pytest.mark.parametrize("mont", [False, True], ids=["canonical", "montgomery"])
+def test_other_decomposition_parameters(log2_B, L, K, mont):
+    # DecompositionParams other than the zkVM's (LF/decomposition_parameters.rs:11-20): the kernels take B, L, K at run time
+    params = LB.DecompositionParams(B=1 << log2_B, L=L, B_SMALL=2, K=K)
+    kappa, wl = 6, 211
+    n = wl * L
+    A = CO.fill_uniform((kappa, n, 24), 300 + log2_B)
+    scheme = make_scheme(A, mont, params)
+    # w_ccs whose coefficients fit in L digits of base B: |c| <= (B/2) * (B^L - 1) / (B - 1)
+    bound = (1 << (log2_B - 1)) * ((1 << (log2_B * L)) - 1) // ((1 << log2_B) - 1) if log2_B > 1 else (1 << L) - 1
+    bound = min(bound, 2**62)
+    rng = np.random.default_rng(log2_B * 100 + L)
+    coeff = rng.integers(-bound, bound + 1, size=(wl, 24), dtype=np.int64)
+    coeff[0], coeff[1] = bound, -bound
+    w = CO.crt(signed_to_fq(coeff))
+    wit, cm = LB.Witness.from_w_ccs(scheme, maybe_mont(w, mont), commit=True)
+    f_coeff, f = CO.witness_from_w_ccs(w, params.B, L)
+    assert np.array_equal(unmont(wit.f_coeff, mont), f_coeff) and np.array_equal(unmont(wit.f, mont), f)
+    e_cm = CO.commit(A, f)
+    assert np.array_equal(unmont(cm.as_ref(), mont), e_cm)
+    if log2_B <= K:  # the limbs then fit the K bit planes: decompose_witness + commit_witnesses on the resident witness
+        _, ys = LB.LFDecompositionProver.decompose_and_commit(scheme, maybe_mont(f_coeff, mont), cm, want_planes=False, side=1)
+        _, pf1, e_ys = CO.decompose_commit(A, f_coeff, e_cm, 2, K)
+        assert all(np.array_equal(unmont(ys[k].as_ref(), mont), e_ys[k]) for k in range(K))
+        # and the fold step on top: an accumulator with |c| < 2^(K-1), short challenges
+        acc = rng.integers(-(1 << (K - 1)) + 1, 1 << (K - 1), size=(n, 24), dtype=np.int64)
+        acc_fc = signed_to_fq(acc // 8 if K > 4 else acc)
+        acc_cm = CO.commit(A, CO.crt(acc_fc))
+        fs = LB.FoldStep(scheme)
+        fs.set_accumulator(maybe_mont(acc_fc, mont), LB.Commitment(maybe_mont(acc_cm, mont), mont))
+        cm2, ys0, ys1, d16 = fs.begin(maybe_mont(w, mont))
+        _, pf0, e_ys0 = CO.decompose_commit(A, acc_fc, acc_cm, 2, K)
+        assert np.array_equal(unmont(cm2.as_ref(), mont), e_cm) and np.array_equal(d16.astype(np.int64), fq_to_signed(f_coeff))
+        assert all(np.array_equal(unmont(ys0[k].as_ref(), mont), e_ys0[k]) and np.array_equal(unmont(ys1[k].as_ref(), mont), e_ys[k])
+                   for k in range(K))
+        rho = CO.crt(signed_to_fq(rng.integers(-1, 2, size=(2 * K, 24))))  # tiny challenges keep f_0 inside 2^K for small K too
+        e_f0 = CO.compute_f0(rho, [pf0[k] for k in range(K)] + [pf1[k] for k in range(K)])
+        if np.abs(fq_to_signed(CO.icrt(e_f0))).max() < (1 << K):
+            cm0, f0d, f0, _ = fs.finish(maybe_mont(rho, mont), want_f0=True)
+            assert np.array_equal(unmont(f0, mont), e_f0) and np.array_equal(f0d.astype(np.int64), fq_to_signed(CO.icrt(e_f0)))
+            assert np.array_equal(unmont(cm0.as_ref(), mont), CO.commit(A, e_f0))
+        else:
+            with pytest.raises(LB.DigitOverflow):
+                fs.finish(maybe_mont(rho, mont))
+    scheme.close()
+
+
 def test_step_overlap_gives_identical_commitments():
     """lat_ajtai_set_step_overlap: consecutive device-resident steps whose kernels overlap (next witness kernel
     under the draining matrix-vector kernel, alternating witness buffers) commit exactly what serialised steps do,
