@@ -135,6 +135,40 @@ def test_commit_vs_oracle_ragged(kappa, n, mont):
     scheme.close()
 
 
+def test_degenerate_rand_matrix_all_rows_equal():
+    # AjtaiCommitmentScheme::rand is vec![vec![R::rand(rng); n]; kappa] (LF/commitment/commitment_scheme.rs:56-58): ONE sampled
+    # ring element in every entry, so every row of every commitment equals a * sum_j f_j.  The engine must not
+    # special-case it -- and must get it right.
+    kappa, n = 32, 4099
+    scheme = LB.AjtaiCommitmentScheme.rand(kappa, n, seed=9)
+    a = S._uniform((1, 24), 9)[0]
+    f = CO.fill_uniform((n, 24), 201)
+    cm = scheme.commit_ntt(f).as_ref()
+    total = np.zeros(24, dtype=object)
+    for row in f.astype(object):
+        total = (total + row) % Q
+    exp = S._fq3_mul_scalar_vec(total.astype(np.uint64).reshape(1, 24), a, False)[0]
+    assert all(np.array_equal(cm[i], exp) for i in range(kappa))
+    scheme.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_commit_random_shapes(seed):
+    # random (kappa, n) including every row-group count of the matrix layout, both representations, batch of 1..3
+    rng = np.random.default_rng(1000 + seed)
+    kappa = int(rng.integers(1, 41))
+    n = int(rng.integers(1, 3000))
+    count = int(rng.integers(1, 4))
+    mont = bool(rng.integers(0, 2))
+    A = CO.fill_uniform((kappa, n, 24), 2000 + seed)
+    fs = CO.fill_uniform((count, n, 24), 3000 + seed)
+    scheme = make_scheme(A, mont)
+    got = scheme.commit_ntt_batch(maybe_mont(fs, mont))
+    for p in range(count):
+        assert np.array_equal(unmont(got[p].as_ref(), mont), CO.commit(A, fs[p])), (kappa, n, count, mont, p)
+    scheme.close()
+
+
 def test_commit_extreme_values():
     # every operand q-1: the lazy accumulators see the largest possible products
     kappa, n = 32, 4096
