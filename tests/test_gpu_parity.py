@@ -946,6 +946,36 @@ def test_ntt_negacyclic_large_properties(log2_d):
     assert np.array_equal(LB.ntt_negacyclic(prod, inverse=True), shifted)
 
 
+@pytest.mark.parametrize("log2_d", [4, 5, 7, 11])
+def test_ntt_negacyclic_more_sizes_and_unaligned_buffers(log2_d):
+    """Every pass structure (radix-16 passes + a 1-3 stage remainder), non-canonical inputs, and device buffers that
+    are only 8-byte aligned (the kernel then uses scalar loads and stores)."""
+    import ctypes as C
+    import torch
+    from oracle import lattice_oracle as PO
+
+    d = 1 << log2_d
+    batch = 4099 // d + 3  # a ragged last block
+    a = CO.fill_uniform((batch, d), 170 + log2_d)
+    a[0, :4] = [Q, 2**64 - 1, Q + 5, 0]  # representatives >= q are accepted and reduced
+    ref = a % np.uint64(Q)
+    fwd = LB.ntt_negacyclic(a)
+    assert fwd.max() < Q
+    for p in (0, 1, batch - 1):
+        assert fwd[p].tolist() == PO.ntt_negacyclic([int(v) for v in ref[p]]), p
+    assert np.array_equal(LB.ntt_negacyclic(fwd, inverse=True), ref)
+    assert np.array_equal(LB.ntt_negacyclic(LB.ntt_negacyclic(a, inverse=True)), ref)
+    L = capi.lib()
+    buf_in = torch.zeros(batch * d + 1, dtype=torch.int64, device="cuda")
+    buf_out = torch.zeros(batch * d + 1, dtype=torch.int64, device="cuda")
+    buf_in[1:] = torch.from_numpy(a.view(np.int64).reshape(-1)).cuda()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream or 1)
+    for inverse, exp in ((0, fwd), (1, LB.ntt_negacyclic(a, inverse=True))):
+        assert L.lat_ntt_negacyclic_dev(buf_in.data_ptr() + 8, batch, log2_d, inverse, buf_out.data_ptr() + 8, stream) == 0
+        torch.cuda.synchronize()
+        assert np.array_equal(buf_out[1:].cpu().numpy().view(np.uint64).reshape(batch, d), exp)
+
+
 def test_ntt_negacyclic_argument_checks():
     x = np.zeros((2, 8), np.uint64)
     out = np.empty_like(x)

@@ -1,4 +1,4 @@
-"""A few launches of the standalone negacyclic NTT (d = 1024 and 4096, 2^22 coefficients): a small target for ncu."""
+"""A few launches of the standalone negacyclic NTT (default d = 64 and 4096; 2^24 coefficients): a small target for ncu."""
 import ctypes as C
 import os
 import sys
@@ -12,8 +12,8 @@ from latticeum_b200 import _capi as capi
 L = capi.lib()
 rng = np.random.default_rng(0)
 stream = C.c_void_p(torch.cuda.current_stream().cuda_stream or 1)
-for lg_d in (10, 12):
-    polys = 1 << (22 - lg_d)
+for lg_d in [int(v) for v in sys.argv[1:]] or (6, 12):
+    polys = 1 << (24 - lg_d)
     x = torch.from_numpy(rng.integers(0, 2**63, size=(polys, 1 << lg_d), dtype=np.int64)).cuda()
     y = torch.empty_like(x)
     for inverse in (0, 1):
