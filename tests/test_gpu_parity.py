@@ -987,13 +987,15 @@ def test_ntt_negacyclic_argument_checks():
         LB.ntt_negacyclic(np.zeros((2, 12), np.uint64))
 
 
-def test_cpp_host_mirror_example():
-    # latticeum_b200/host/ajtai.hpp: the C++ mirror of the reference API, on the reference's closed-form commit test
+@pytest.mark.parametrize("name,marker", [("example", "example ok"), ("example_ivc", "ivc example ok")])
+def test_cpp_host_mirror_example(name, marker):
+    # latticeum_b200/host/ajtai.hpp, the C++ mirror of the reference API: the reference's closed-form commit test, and
+    # the zkVM's folding loop (zkvm/src/main.rs:140-182) over fold_step_begin / fold_step_finish
     import subprocess
 
-    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "latticeum_b200", "host", "example")
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "latticeum_b200", "host", name)
     if not os.path.exists(exe):
         pytest.skip("example not built (run __graft_entry__.build())")
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "example ok" in out.stdout
+    assert marker in out.stdout
