@@ -976,6 +976,33 @@ def test_ntt_negacyclic_more_sizes_and_unaligned_buffers(log2_d):
         assert np.array_equal(buf_out[1:].cpu().numpy().view(np.uint64).reshape(batch, d), exp)
 
 
+@pytest.mark.parametrize("log2_d", [2, 6, 9, 12, 14])
+def test_ntt_negacyclic_extreme_values(log2_d):
+    """Inputs that sit on the lazy arithmetic's correction paths: q - 1 everywhere, 2^64 - 1 everywhere, values whose high
+    word is all ones (>= q, or just below it), zeros with a single extreme entry."""
+    from oracle import lattice_oracle as PO
+
+    d = 1 << log2_d
+    rng = np.random.default_rng(200 + log2_d)
+    hi_ones = (np.uint64(0xFFFFFFFF) << np.uint64(32)) | rng.integers(0, 2**32, size=d, dtype=np.uint64)
+    just_below = np.uint64(Q) - rng.integers(1, 2**20, size=d, dtype=np.uint64)
+    spike = np.zeros(d, np.uint64)
+    spike[d - 1] = np.uint64(2**64 - 1)
+    a = np.stack([np.full(d, Q - 1, np.uint64), np.full(d, 2**64 - 1, np.uint64), hi_ones, just_below, spike,
+                  rng.integers(0, 2**64, size=d, dtype=np.uint64)])
+    ref = [[int(v) % Q for v in row] for row in a]
+    fwd = LB.ntt_negacyclic(a)
+    inv = LB.ntt_negacyclic(a, inverse=True)
+    assert fwd.max() < Q and inv.max() < Q
+    pts = [0, 1, d // 2, d - 1] + rng.integers(0, d, size=4).tolist()
+    for p in range(a.shape[0]):
+        for i in pts:
+            assert int(fwd[p, i]) == PO.ntt_eval_at(ref[p], int(i)), (p, i)
+            assert int(inv[p, i]) == PO.ntt_eval_at(ref[p], int(i), inverse=True), (p, i)
+    assert np.array_equal(LB.ntt_negacyclic(fwd, inverse=True), np.array(ref, dtype=np.uint64))
+    assert np.array_equal(LB.ntt_negacyclic(inv), np.array(ref, dtype=np.uint64))
+
+
 def test_ntt_negacyclic_argument_checks():
     x = np.zeros((2, 8), np.uint64)
     out = np.empty_like(x)
