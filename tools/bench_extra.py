@@ -55,7 +55,8 @@ for lg_d, lg_total in ((6, 24), (8, 24), (10, 24), (12, 24), (14, 24)):
     y = torch.empty_like(x)
     t_f = timeit(lambda: L.lat_ntt_negacyclic_dev(x.data_ptr(), polys, lg_d, 0, y.data_ptr(), stream))
     t_i = timeit(lambda: L.lat_ntt_negacyclic_dev(x.data_ptr(), polys, lg_d, 1, y.data_ptr(), stream))
-    wide = polys * (d // 2) * lg_d * 4  # one general multiplication = 4 IMAD.WIDE per butterfly
+    # wide multiplies per butterfly: 5 in a general stage (4 for the product, 1 in the fold), 1 in the (up to 4) shift stages
+    wide = polys * (d // 2) * (5 * max(lg_d - 4, 0) + min(lg_d, 4))
     ntt.append({"log2_d": lg_d, "polys": polys, "fwd_us": t_f * 1e3, "inv_us": t_i * 1e3,
                 "coeffs_per_s": polys * d / (t_f * 1e-3), "GBps": polys * d * 16 / t_f / 1e6,
                 "imad_pipe_frac": wide / (t_f * 1e-3) / 9.154e12})
