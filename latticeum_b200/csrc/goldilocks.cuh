@@ -75,6 +75,40 @@ __host__ __device__ __forceinline__ u64 neg(u64 a) { return a ? Q - a : 0; }
 
 // x = lo + 2^64 * hi  ->  canonical.   x = lo - hi_hi + hi_lo * (2^32 - 1)  (mod q)
 __host__ __device__ __forceinline__ u64 reduce128(u64 lo, u64 hi) {
+#ifdef __CUDA_ARCH__
+    // carry chains instead of compare/select (17 instructions for a shift-multiply against 25): lo - hi_hi (+ q on
+    // borrow), + hi_lo (2^32 - 1) as one wide multiply-add (+ 2^32 - 1 on carry, written as (hi:lo) - c + (c << 32)),
+    // then x >= q  <=>  high word all ones and low word >= 1
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 w0, w1, h0, h1, c, m;\n\t"
+        ".reg .u64 t, x;\n\t"
+        ".reg .pred p;\n\t"
+        "mov.b64 {w0, w1}, %1;\n\t"
+        "mov.b64 {h0, h1}, %2;\n\t"
+        "sub.cc.u32 w0, w0, h1;\n\t"
+        "subc.cc.u32 w1, w1, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 w0, w0, m;\n\t"
+        "subc.u32 w1, w1, 0;\n\t"
+        "mov.b64 t, {w0, w1};\n\t"
+        "mul.wide.u32 x, h0, 0xFFFFFFFF;\n\t"
+        "add.cc.u64 t, t, x;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "neg.s32 m, c;\n\t"
+        "mov.b64 {w0, w1}, t;\n\t"
+        "sub.cc.u32 w0, w0, c;\n\t"
+        "subc.u32 w1, w1, m;\n\t"
+        "setp.eq.u32 p, w1, 0xFFFFFFFF;\n\t"
+        "setp.ne.and.u32 p, w0, 0, p;\n\t"
+        "@p add.u32 w0, w0, 0xFFFFFFFF;\n\t"
+        "@p mov.u32 w1, 0;\n\t"
+        "mov.b64 %0, {w0, w1};\n\t"
+        "}"
+        : "=l"(r)
+        : "l"(lo), "l"(hi));
+    return r;
+#else
     u64 hi_hi = hi >> 32, hi_lo = hi & EPS;
     u64 t0 = lo - hi_hi;
     if (lo < hi_hi) t0 -= EPS;
@@ -83,6 +117,32 @@ __host__ __device__ __forceinline__ u64 reduce128(u64 lo, u64 hi) {
     if (r < t1) r += EPS;
     u64 c = r + EPS;  // canonicalise
     return (c < r) ? c : r;
+#endif
+}
+
+// lo + 2^64 hi for hi < 2^32 (the shift-multiplies by less than 2^32): the fold and the canonicalisation only
+__device__ __forceinline__ u64 reduce96(u64 lo, u32 hi) {
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 w0, w1, c, m;\n\t"
+        ".reg .u64 t, x;\n\t"
+        ".reg .pred p;\n\t"
+        "mul.wide.u32 x, %2, 0xFFFFFFFF;\n\t"
+        "add.cc.u64 t, %1, x;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "neg.s32 m, c;\n\t"
+        "mov.b64 {w0, w1}, t;\n\t"
+        "sub.cc.u32 w0, w0, c;\n\t"
+        "subc.u32 w1, w1, m;\n\t"
+        "setp.eq.u32 p, w1, 0xFFFFFFFF;\n\t"
+        "setp.ne.and.u32 p, w0, 0, p;\n\t"
+        "@p add.u32 w0, w0, 0xFFFFFFFF;\n\t"
+        "@p mov.u32 w1, 0;\n\t"
+        "mov.b64 %0, {w0, w1};\n\t"
+        "}"
+        : "=l"(r)
+        : "l"(lo), "r"(hi));
+    return r;
 }
 
 __device__ __forceinline__ u64 mul(u64 a, u64 b) { return reduce128(a * b, __umul64hi(a, b)); }
@@ -95,6 +155,8 @@ __device__ __forceinline__ u64 mul_pow2(u64 a) {
         return a;
     } else if constexpr (K >= 96) {
         return neg(mul_pow2<K - 96>(a));  // 2^96 = -1
+    } else if constexpr (K <= 32) {
+        return reduce96(a << K, (u32)(a >> (64 - K)));
     } else if constexpr (K < 64) {
         return reduce128(a << K, a >> (64 - K));
     } else if constexpr (K == 64) {
