@@ -145,7 +145,37 @@ __device__ __forceinline__ u64 reduce96(u64 lo, u32 hi) {
     return r;
 }
 
-__device__ __forceinline__ u64 mul(u64 a, u64 b) { return reduce128(a * b, __umul64hi(a, b)); }
+// 128-bit product: a0 b0, a1 b1 and the 65-bit middle term a0 b1 + a1 b0 (one multiply-add with carry-out), joined by one
+// three-word carry chain -- 4 wide multiplies + 4 instructions (a * b with __umul64hi compiles to 5-6 wide multiplies + 6)
+__device__ __forceinline__ void mul_wide(u64 a, u64 b, u64 &lo, u64 &hi) {
+    asm("{\n\t"
+        ".reg .u32 a0, a1, b0, b1, w0, w1, w2, w3, ml, mh, c;\n\t"
+        ".reg .u64 p0, p3, t, x, mid;\n\t"
+        "mov.b64 {a0, a1}, %2;\n\t"
+        "mov.b64 {b0, b1}, %3;\n\t"
+        "mul.wide.u32 p0, a0, b0;\n\t"
+        "mul.wide.u32 p3, a1, b1;\n\t"
+        "mul.wide.u32 t, a0, b1;\n\t"
+        "mul.wide.u32 x, a1, b0;\n\t"
+        "add.cc.u64 mid, t, x;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "mov.b64 {w0, w1}, p0;\n\t"
+        "mov.b64 {w2, w3}, p3;\n\t"
+        "mov.b64 {ml, mh}, mid;\n\t"
+        "add.cc.u32 w1, w1, ml;\n\t"
+        "addc.cc.u32 w2, w2, mh;\n\t"
+        "addc.u32 w3, w3, c;\n\t"
+        "mov.b64 %0, {w0, w1};\n\t"
+        "mov.b64 %1, {w2, w3};\n\t"
+        "}"
+        : "=l"(lo), "=l"(hi)
+        : "l"(a), "l"(b));
+}
+__device__ __forceinline__ u64 mul(u64 a, u64 b) {
+    u64 lo, hi;
+    mul_wide(a, b, lo, hi);
+    return reduce128(lo, hi);
+}
 
 // a * 2^K mod q for a compile-time K in [0, 192).
 template <int K>

@@ -225,30 +225,51 @@ __device__ __forceinline__ void witness_body(const u64 *__restrict__ w, u64 w_le
         if (stage_input) load3(wstage, o.e - (u64)blockIdx.x * OPB, o.sl, c);
         else load3(w, o.e, o.sl, c);
         if (!in_coeff) ring8::icrt8(c, tw);
-        bool negative[3];
+        u32 sgn[3];   // 0 or 0xFFFFFFFF: the digit sequence of -m is the negated digit sequence of m (mod.rs:76-92)
         u64 m[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             if constexpr (MONT) c[k] = gl::from_mont(c[k]);
-            ring::signed_rep(c[k], negative[k], m[k]);  // fq_convertible.rs:22-34
+            bool negative;
+            ring::signed_rep(c[k], negative, m[k]);  // fq_convertible.rs:22-34
+            sgn[k] = negative ? 0xFFFFFFFFu : 0u;
         }
-        const u64 B = 1ull << log2b, half = B >> 1;
-        int16_t *trow = tile + (threadIdx.x >> 3) * (L * ring::D) + 3 * o.sl;
-        for (int l = 0; l < L; ++l) {  // balanced_decomposition/mod.rs:76-97 on the magnitudes, limb by limb
-            const u64 elem = o.e * (u64)L + l;  // out[i*L + l] = limb l of element i (mod.rs:163-175)
+        // balanced_decomposition/mod.rs:76-97 on the magnitudes, limb by limb; out[i*L + l] = limb l of element i
+        // (mod.rs:163-175).  log2b <= 15, so a remainder is a 32-bit quantity: and, 64-bit shift, compare, conditional
+        // subtract of B, carry into the magnitude, re-sign, store -- about a dozen instructions per digit.
+        const u32 Bv = 1u << log2b, mask = Bv - 1, half = Bv >> 1;
+        auto next_digit = [&](int k) -> int {
+            const u32 rem = (u32)m[k] & mask;
+            const u32 up = rem > half ? 1u : 0u;   // |rem| == b/2 is kept (mod.rs:79)
+            m[k] = (m[k] >> log2b) + up;
+            const u32 dg = rem - (up ? Bv : 0u);
+            return (int)((dg ^ sgn[k]) - sgn[k]);
+        };
+        if (tiled) {
+            int16_t *trow = tile + (threadIdx.x >> 3) * (L * ring::D) + 3 * o.sl;
+            u64 *gcoeff = (o.valid && f_coeff) ? f_coeff + (o.e * (u64)L) * ring::D + 3 * o.sl : nullptr;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                u64 rem = m[k] & (B - 1);
-                m[k] >>= log2b;
-                int dg = (int)rem;
-                if (rem > half) {  // |rem| == b/2 is kept (mod.rs:79)
-                    dg -= (int)B;
-                    m[k] += 1;
+            for (int l = 0; l < WIT_MAX_L; ++l) {
+                if (l < L) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int dg = next_digit(k);
+                        trow[l * ring::D + k] = (int16_t)dg;
+                        if (gcoeff) gcoeff[l * ring::D + k] = gl::from_small<MONT>(dg);
+                    }
                 }
-                if (negative[k]) dg = -dg;
-                if (tiled) trow[l * ring::D + k] = (int16_t)dg;
-                else if (o.valid) f16[elem * ring::D + 3 * o.sl + k] = (int16_t)dg;  // standalone decompositions with L > 8
-                if (o.valid && f_coeff) f_coeff[elem * ring::D + 3 * o.sl + k] = gl::from_small<MONT>(dg);
+            }
+        } else {   // standalone decompositions with L > 8 (lat_ring_gadget_decompose only)
+            for (int l = 0; l < L; ++l) {
+                const u64 at = (o.e * (u64)L + l) * ring::D + 3 * o.sl;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int dg = next_digit(k);
+                    if (o.valid) {
+                        f16[at + k] = (int16_t)dg;
+                        if (f_coeff) f_coeff[at + k] = gl::from_small<MONT>(dg);
+                    }
+                }
             }
         }
         // the reference would index out of bounds (mod.rs:80) if a value needed more than L digits
