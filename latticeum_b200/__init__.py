@@ -25,6 +25,7 @@ from .scheme import (  # noqa: F401
     WrongCommitmentLength,
     WrongWitnessLength,
     from_mont,
+    gadget_decompose,
     gadget_recompose,
     digits_to_fq,
     get_fhat,
@@ -37,6 +38,6 @@ from .scheme import (  # noqa: F401
 
 __all__ = [
     "AjtaiCommitmentScheme", "Commitment", "ntt_negacyclic", "CommitPipeline", "pinned_empty", "CommitmentError", "DecompositionParams", "DigitOverflow", "EngineError",
-    "GoldiLocksDP", "KAPPA", "LFDecompositionProver", "LFFoldingProver", "gadget_recompose", "N", "W_SIZE", "Witness", "WrongAjtaiMatrixDimensions",
+    "GoldiLocksDP", "KAPPA", "LFDecompositionProver", "LFFoldingProver", "gadget_decompose", "gadget_recompose", "N", "W_SIZE", "Witness", "WrongAjtaiMatrixDimensions",
     "WrongCommitmentLength", "WrongWitnessLength", "from_mont", "get_fhat", "get_fhat_from_digits", "digits_to_fq", "FoldStep", "ntt_from_scalar", "to_mont",
 ]

@@ -576,6 +576,16 @@ def gadget_recompose(f, params: DecompositionParams = GoldiLocksDP, device: int 
     return out
 
 
+def gadget_decompose(v, log2_b: int, L: int, mont: bool = False, device: int = 0) -> np.ndarray:
+    """GadgetDecompose for &[R] in coefficient form (balanced_decomposition/mod.rs:163-175, coeff_form.rs:588-606):
+    out[i*L + l] = limb l (base 2^log2_b, balanced) of v[i].  Raises DigitOverflow if a coefficient needs more than L
+    limbs (the reference indexes out of bounds there, mod.rs:80)."""
+    v = _as_u64(v, "v").reshape(-1, D)
+    out = np.empty((v.shape[0] * L, D), np.uint64)
+    _raise(capi.lib().lat_ring_gadget_decompose(_ptr(v), v.shape[0], log2_b, L, _ptr(out), 1 if mont else 0, device))
+    return out
+
+
 # ---- helpers ----------------------------------------------------------------------------------------------------------------
 def _uniform(shape, seed: int) -> np.ndarray:
     """Uniform in [0, q) by rejection from numpy's PCG64 (not the reference's sampler; unpinned)."""

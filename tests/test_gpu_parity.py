@@ -745,6 +745,69 @@ def test_witness_from_w_ccs_compact_vs_oracle():
         scheme.close()
 
 
+@pytest.mark.parametrize("log2_b,L", [(15, 5), (8, 8), (7, 10), (2, 32), (1, 32), (15, 1)])
+def test_gadget_decompose_vs_oracle(log2_b, L):
+    # RING/balanced_decomposition/mod.rs:163-175 for &[R]; L <= 8 goes through the kernel's shared-memory tile, L > 8
+    # through the direct path; values are drawn so that exactly L balanced limbs suffice
+    rng = np.random.default_rng(300 + 10 * log2_b + L)
+    b = 1 << log2_b
+    bound = min((b // 2) * (b**L - 1) // (b - 1), (Q - 1) // 2)  # largest magnitude with L balanced limbs
+    mag = np.array([[int(rng.integers(0, bound + 1)) if bound < 2**63 else int(rng.integers(0, 2**63)) % (bound + 1)
+                     for _ in range(24)] for _ in range(77)], dtype=object)
+    mag[0, :] = 0
+    mag[1, :] = bound
+    mag[2, :3] = [min(t, bound) for t in (b // 2, b // 2 + 1, max(b // 2 - 1, 0))]  # the tie rule: |rem| == b/2 is kept
+    sign = rng.integers(0, 2, size=mag.shape).astype(bool)
+    v = np.array([[(Q - int(m)) % Q if s else int(m) for m, s in zip(rm, rs)] for rm, rs in zip(mag, sign)], dtype=np.uint64)
+    exp = CO.gadget_decompose(v, b, L)
+    assert np.array_equal(LB.gadget_decompose(v, log2_b, L), exp)
+    assert np.array_equal(unmont(LB.gadget_decompose(S.to_mont(v), log2_b, L, mont=True), True), exp)
+    if bound < (Q - 1) // 2:
+        v2 = v.copy()
+        v2[5, 7] = np.uint64(bound + 1)
+        with pytest.raises(LB.DigitOverflow):
+            LB.gadget_decompose(v2, log2_b, L)
+
+
+def test_device_pointer_entry_points_for_matrix_and_transforms():
+    """lat_ajtai_upload_rows_dev (matrix rows already on the device, with a row stride) and lat_ring_crt_dev /
+    lat_ring_icrt_dev (both kernel paths: below and above the one-thread-per-element threshold, in place and out of
+    place) against the host-buffer entry points and the oracle."""
+    import ctypes as C
+    import torch
+
+    L = capi.lib()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream or 1)
+    kappa, n, stride = 5, 333, 400
+    wide = CO.fill_uniform((kappa, stride, 24), 310)  # a column block [0, n) of a wider matrix
+    f = CO.fill_uniform((n, 24), 311)
+    for mont in (False, True):
+        scheme = LB.AjtaiCommitmentScheme(kappa, n, mont=mont)
+        dev = torch.from_numpy(maybe_mont(wide, mont).view(np.int64)).cuda()
+        assert L.lat_ajtai_upload_rows_dev(scheme._h, 0, 2, dev.data_ptr(), stride) == 0, capi.last_error()
+        assert L.lat_ajtai_upload_rows_dev(scheme._h, 2, kappa - 2, dev[2:].data_ptr(), stride) == 0, capi.last_error()
+        assert np.array_equal(unmont(scheme.commit_ntt(maybe_mont(f, mont)).as_ref(), mont), CO.commit(wide[:, :n], f))
+        assert L.lat_ajtai_upload_rows_dev(scheme._h, 4, 2, dev.data_ptr(), stride) == capi.LAT_E_WRONG_MATRIX_DIMENSIONS
+        assert L.lat_ajtai_upload_rows_dev(scheme._h, 0, 1, dev.data_ptr(), n - 1) == capi.LAT_E_WRONG_MATRIX_DIMENSIONS
+        scheme.close()
+    for count in (37, (1 << 14) + 5):
+        x = CO.fill_uniform((count, 24), 312 + count % 7)
+        xd = torch.from_numpy(x.view(np.int64)).cuda()
+        yd = torch.empty_like(xd)
+        assert L.lat_ring_crt_dev(xd.data_ptr(), count, yd.data_ptr(), stream) == 0
+        torch.cuda.synchronize()
+        fwd = yd.cpu().numpy().view(np.uint64)
+        assert np.array_equal(fwd, CO.crt(x)) and np.array_equal(fwd, gpu_crt(x))
+        assert L.lat_ring_icrt_dev(yd.data_ptr(), count, yd.data_ptr(), stream) == 0  # in place
+        torch.cuda.synchronize()
+        assert np.array_equal(yd.cpu().numpy().view(np.uint64), x)
+        assert L.lat_ring_icrt_dev(xd.data_ptr(), count, yd.data_ptr(), stream) == 0
+        torch.cuda.synchronize()
+        assert np.array_equal(yd.cpu().numpy().view(np.uint64), CO.icrt(x))
+    assert L.lat_ring_crt_dev(None, 0, None, stream) == 0
+    assert L.lat_ring_crt_dev(None, 3, None, stream) == capi.LAT_E_INVALID_ARGUMENT
+
+
 def test_gadget_recompose_vs_oracle():
     # RING/balanced_decomposition/mod.rs:177-190 in CRT form: recompose(from_w_ccs(w).f) == w  (LF/arith.rs:516-548)
     w = CO.fill_uniform((333, 24), 96)
