@@ -75,6 +75,33 @@ def test_invalid_arguments(built):
     assert L.lat_ajtai_commit_ntt(None, None, 0, None) == capi.LAT_E_INVALID_ARGUMENT
 
 
+def test_every_handle_entry_point_rejects_a_null_handle(built):
+    """Every exported function that takes the engine handle returns LAT_E_INVALID_ARGUMENT for a NULL handle (and does
+    not touch CUDA or crash); the handle-less ones accept an empty batch.  Runs without a GPU."""
+    import ctypes as C
+
+    L = capi.lib()
+    checked = 0
+    for name, (res, args) in capi.SIGNATURES.items():
+        if not name.startswith("lat_ajtai_") or name in ("lat_ajtai_create", "lat_ajtai_destroy"):
+            continue
+        zero = [None if (a is C.c_void_p or hasattr(a, "contents")) else 0 for a in args]
+        got = getattr(L, name)(*zero)
+        if name in ("lat_ajtai_kappa", "lat_ajtai_width"):
+            assert got == 0, name
+        else:
+            assert got == capi.LAT_E_INVALID_ARGUMENT, (name, got)
+        checked += 1
+    assert checked >= 30
+    L.lat_ajtai_destroy(None)  # a no-op
+    for name in ("lat_ring_crt", "lat_ring_icrt"):
+        assert getattr(L, name)(None, 0, None, 0) == 0
+    assert L.lat_ring_gadget_decompose(None, 0, 15, 5, None, 0, 0) == 0
+    assert L.lat_ring_gadget_recompose(None, 0, 15, 5, None, 0, 0) == 0
+    assert L.lat_ntt_negacyclic(None, 0, 3, 0, None, 0) == 0
+    assert L.lat_commitment_sum(None, 0, 0, None, 0) in (0, capi.LAT_E_INVALID_ARGUMENT)
+
+
 def test_commitment_ops_match_reference_semantics():
     # latticefold/src/commitment/homomorphic_commitment.rs:54-80
     rng = np.random.default_rng(0)
