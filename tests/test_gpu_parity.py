@@ -808,6 +808,39 @@ def test_device_pointer_entry_points_for_matrix_and_transforms():
     assert L.lat_ring_crt_dev(None, 3, None, stream) == capi.LAT_E_INVALID_ARGUMENT
 
 
+def test_null_and_zero_arguments_never_crash_and_leave_the_handle_usable():
+    """Every lat_ajtai_* entry point called on a live handle with NULL pointers and zero sizes returns one of the
+    documented status codes; afterwards the handle still commits correctly."""
+    import ctypes as C
+
+    kappa, wl = 3, 40
+    n = wl * DP.L
+    A = CO.fill_uniform((kappa, n, 24), 320)
+    scheme = make_scheme(A)
+    L = capi.lib()
+    known = {capi.LAT_OK, capi.LAT_E_INVALID_ARGUMENT, capi.LAT_E_WRONG_WITNESS_LENGTH, capi.LAT_E_WRONG_MATRIX_DIMENSIONS,
+             capi.LAT_E_CUDA, capi.LAT_E_DIGIT_OVERFLOW, capi.LAT_E_MATRIX_INCOMPLETE, capi.LAT_E_WRONG_COMMITMENT_LENGTH}
+    skip = {"lat_ajtai_create", "lat_ajtai_destroy", "lat_ajtai_kappa", "lat_ajtai_width", "lat_ajtai_set_stream",
+            "lat_ajtai_wait"}  # set_stream(NULL) is meaningful (own stream); wait(0) has nothing to wait for
+    for name, (res, args) in capi.SIGNATURES.items():
+        if not name.startswith("lat_ajtai_") or name in skip:
+            continue
+        zero = [None if (a is C.c_void_p or hasattr(a, "contents")) else 0 for a in args]
+        zero[0] = scheme._h
+        got = getattr(L, name)(*zero)
+        assert got in known, (name, got)
+    assert L.lat_ajtai_synchronize(scheme._h) in known
+    L.lat_ajtai_set_step_overlap(scheme._h, 0)
+    L.lat_ajtai_set_profiling(scheme._h, 0)
+    f = CO.fill_uniform((n, 24), 321)
+    assert np.array_equal(scheme.commit_ntt(f).as_ref(), CO.commit(A, f))
+    w = CO.fill_uniform((wl, 24), 322)
+    f_coeff, fw = CO.witness_from_w_ccs(w, DP.B, DP.L)
+    wit, cm = LB.Witness.from_w_ccs(scheme, w, commit=True)
+    assert np.array_equal(wit.f_coeff, f_coeff) and np.array_equal(cm.as_ref(), CO.commit(A, fw))
+    scheme.close()
+
+
 def test_gadget_recompose_vs_oracle():
     # RING/balanced_decomposition/mod.rs:177-190 in CRT form: recompose(from_w_ccs(w).f) == w  (LF/arith.rs:516-548)
     w = CO.fill_uniform((333, 24), 96)
