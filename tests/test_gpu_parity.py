@@ -841,6 +841,43 @@ def test_null_and_zero_arguments_never_crash_and_leave_the_handle_usable():
     scheme.close()
 
 
+def test_two_host_threads_with_their_own_handles():
+    """Two host threads, each with its own engine handle on the same GPU, plus the handle-less transform calls (which
+    share one per-device scratch behind a lock), all running at once (ctypes drops the GIL during the calls)."""
+    import threading
+
+    kappa, wl = 4, 64
+    n = wl * DP.L
+    errors = []
+
+    def worker(seed):
+        try:
+            A = CO.fill_uniform((kappa, n, 24), seed)
+            scheme = make_scheme(A, mont=bool(seed & 1))
+            mont = bool(seed & 1)
+            for it in range(12):
+                w = CO.fill_uniform((wl, 24), seed * 100 + it)
+                f_coeff, f = CO.witness_from_w_ccs(w, DP.B, DP.L)
+                wit, cm = LB.Witness.from_w_ccs(scheme, maybe_mont(w, mont), commit=True)
+                assert np.array_equal(unmont(cm.as_ref(), mont), CO.commit(A, f)), (seed, it)
+                assert np.array_equal(unmont(wit.f_coeff, mont), f_coeff), (seed, it)
+                x = CO.fill_uniform((50 + it, 24), seed * 1000 + it)
+                assert np.array_equal(gpu_crt(gpu_crt(x), inverse=True), x)
+                a = CO.fill_uniform((3, 64), seed * 2000 + it)
+                assert np.array_equal(LB.ntt_negacyclic(LB.ntt_negacyclic(a), inverse=True), a)
+            scheme.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append((seed, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(330 + i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    assert not any(t.is_alive() for t in threads)
+
+
 def test_gadget_recompose_vs_oracle():
     # RING/balanced_decomposition/mod.rs:177-190 in CRT form: recompose(from_w_ccs(w).f) == w  (LF/arith.rs:516-548)
     w = CO.fill_uniform((333, 24), 96)
