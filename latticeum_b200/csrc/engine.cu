@@ -180,7 +180,13 @@ struct lat_ajtai {
     cudaEvent_t witness_done = nullptr;          // digits / witness outputs complete: their downloads overlap the matrix-vector kernels
     bool copy_stream_busy = false;               // downloads in flight on copy_stream: finish() waits for them
 
-    DevBuf A;            // re-laid-out matrix, canonical form
+    DevBuf A;            // re-laid-out matrix, canonical form, 3 words per Fq3 entry (the single-witness kernel)
+    // the same matrix as Toom-3 evaluations, 5 words per entry: what the launches with several witnesses read (the K-1
+    // planes of a decomposition, commit batches).  Derived on the device from A when such a launch first needs it and
+    // again after rows were uploaded; 5/3 of A's bytes, never touched by the single-witness path.
+    DevBuf A5;
+    lat::MatLayout lay5{};
+    uint64_t a_version = 1, a5_version = 0;
     std::vector<uint8_t> row_done;
     uint32_t rows_done = 0;
 
@@ -276,11 +282,35 @@ struct lat_ajtai {
         return fail(LAT_E_WRONG_WITNESS_LENGTH, "Wrong length of the witness: " + std::to_string(got) +
                                                     ", expected: " + std::to_string(n));
     }
-    // mac + reduce into cms_dev for `count` witnesses in the extended layout, count x stride x 48
-    int mac_fx(const u64 *Fx, u64 stride, uint32_t count, u64 *cms_dev, const lat::MacReport &report = lat::MacReport()) {
-        lat::MacPlan plan = lat::plan_mac(lay, count, sm_count);
+    int ensure_a5() {
+        if (a5_version == a_version) return LAT_OK;
+        const size_t bytes = lay5.total_elems() * sizeof(u64);
+        const bool fresh = A5.bytes < bytes;
+        int st = A5.ensure(bytes);
+        if (st) return st;
+        if (fresh) CK(cudaMemsetAsync(A5.p, 0, bytes, stream));  // zero padding columns; rows beyond kappa evaluate to 0
+        lat::launch_derive_toom(A.as<u64>(), lay, A5.as<u64>(), lay5, stream);
+        CK(cudaGetLastError());
+        a5_version = a_version;
+        return LAT_OK;
+    }
+    // mac + reduce into cms_dev for `count` witnesses in the extended layout, count x stride x 48.  toom: Fx is in the
+    // Toom-3 form (planes_kernel, fext with toom) and the launch reads the 5-word matrix; else Karatsuba form on A.
+    int mac_fx(const u64 *Fx, u64 stride, uint32_t count, u64 *cms_dev, const lat::MacReport &report = lat::MacReport(),
+               bool toom = false) {
+        int st;
+        if (toom && count > 4 && count % 4) {
+            // four witnesses per thread is the fastest instance: the largest multiple of 4 first, the rest behind it
+            const uint32_t head = count - count % 4;
+            if ((st = mac_fx(Fx, stride, head, cms_dev, lat::MacReport(), true))) return st;
+            return mac_fx(Fx + (size_t)head * stride * lat::FX_WORDS, stride, count - head,
+                          cms_dev + (size_t)head * kappa * LAT_RING_DEGREE, report, true);
+        }
+        if (toom && (st = ensure_a5())) return st;
+        const lat::MatLayout &ml = toom ? lay5 : lay;
+        lat::MacPlan plan = lat::plan_mac(ml, count, sm_count);
         size_t had = ws.bytes;
-        int st = ws.ensure(plan.ws_elems * sizeof(u64));
+        st = ws.ensure(plan.ws_elems * sizeof(u64));
         if (st) return st;
         if (ws.bytes != had) CK(cudaMemsetAsync(ws.p, 0, ws.bytes, stream));  // the kernel keeps it zero afterwards
         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -292,7 +322,7 @@ struct lat_ajtai {
             e1 = ev1[i];
             ev_pending[i] = 1;
         }
-        lat::launch_mac(A.as<u64>(), lay, Fx, stride, count, plan, ws.as<u64>(), cms_dev, stream, e0, e1, report);
+        lat::launch_mac(toom ? A5.as<u64>() : A.as<u64>(), ml, Fx, stride, count, plan, ws.as<u64>(), cms_dev, stream, e0, e1, report);
         CK(cudaGetLastError());
         last_mac_src = Fx;
         last_op_was_mac = true;
@@ -302,10 +332,11 @@ struct lat_ajtai {
     int mac(const u64 *F, u64 stride, uint32_t count, u64 *cms_dev) {
         int st = fx.ensure((size_t)count * n * lat::FX_WORDS * sizeof(u64));
         if (st) return st;
+        const bool toom = count > 1;  // a batch shares every matrix entry between its witnesses
         for (uint32_t p = 0; p < count; ++p)
-            lat::launch_fext(F + (size_t)p * stride * LAT_RING_DEGREE, n, fx.as<u64>() + (size_t)p * n * lat::FX_WORDS, stream);
+            lat::launch_fext(F + (size_t)p * stride * LAT_RING_DEGREE, n, fx.as<u64>() + (size_t)p * n * lat::FX_WORDS, stream, toom);
         CK(cudaGetLastError());
-        return mac_fx(fx.as<u64>(), n, count, cms_dev);
+        return mac_fx(fx.as<u64>(), n, count, cms_dev, lat::MacReport(), toom);
     }
     int clear_flag() {
         CK(cudaMemsetAsync(flag.p, 0, sizeof(int), stream));
@@ -394,6 +425,7 @@ int lat_ajtai_create(lat_ajtai **out, uint32_t kappa, uint64_t n, uint32_t log2_
     h->L = L;
     h->K = K;
     h->lay = lat::make_layout(kappa, n);
+    h->lay5 = lat::make_layout(kappa, n, true);
     h->row_done.assign(kappa, 0);
     int st = LAT_OK;
     cudaError_t e;
@@ -441,7 +473,7 @@ void lat_ajtai_destroy(lat_ajtai *h) {
     cudaSetDevice(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     if (h->stream && h->stream != h->own_stream) cudaStreamSynchronize(h->stream);  // steps in flight write into our buffers
-    DevBuf *bufs[] = {&h->A, &h->stage, &h->in, &h->f16, &h->f, &h->fx, &h->fcoeff64, &h->planes, &h->planes_fx[0], &h->planes_fx[1],
+    DevBuf *bufs[] = {&h->A, &h->A5, &h->stage, &h->in, &h->f16, &h->f, &h->fx, &h->fcoeff64, &h->planes, &h->planes_fx[0], &h->planes_fx[1],
                       &h->rho, &h->f0, &h->planes_coeff, &h->cms, &h->cm_in, &h->ws, &h->flag, &h->fx_alt,
                       &h->f16_acc, &h->cms_side[0], &h->cms_side[1], &h->cm_step, &h->cm_acc};
     for (DevBuf *b : bufs) b->release();
@@ -492,6 +524,7 @@ int lat_ajtai_synchronize(lat_ajtai *h) {
 }
 
 static int mark_rows(lat_ajtai *h, uint32_t row0, uint32_t nrows) {
+    h->a_version++;  // the 5-word copy (ensure_a5) is stale now
     for (uint32_t r = row0; r < row0 + nrows; ++r)
         if (!h->row_done[r]) {
             h->row_done[r] = 1;
@@ -875,7 +908,8 @@ static int planes_core(lat_ajtai *h, const u64 *cm_dev, u64 *planes_coeff_dev, u
     }
     if (cms_dev) {
         if (h->K > 1) {
-            st = h->mac_fx(pfx + h->n * lat::FX_WORDS, h->n, h->K - 1, cms_dev + (size_t)h->kappa * LAT_RING_DEGREE);
+            st = h->mac_fx(pfx + h->n * lat::FX_WORDS, h->n, h->K - 1, cms_dev + (size_t)h->kappa * LAT_RING_DEGREE,
+                           lat::MacReport(), true);  // planes are in the Toom-3 form
             if (st) return st;
         }
         if (cm_dev) {  // column-sharded callers derive y_0 after the exchange (lat_commitment_y0_dev)

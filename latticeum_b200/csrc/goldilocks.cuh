@@ -387,6 +387,60 @@ struct Fq3Acc {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// Toom-3 form of the same accumulation, for launches where SEVERAL witnesses meet the same matrix entry (the K-1 planes
+// of a decomposition, commit batches): a degree-2 by degree-2 product has 5 coefficients d0..d4, so 5 point products
+// determine it.  Both operands are evaluated at t = 0, infinity, 1, -1, 2,
+//     e = (x0, x2, x0+x1+x2, x0-x1+x2, x0+2 x1+4 x2)    (mod q, any 64-bit representative),
+// the five products are summed lazily over the columns -- sum_j a_j(t) y_j(t) is the evaluation of sum_j a_j y_j, the
+// interpolation is linear -- and interpolated ONCE per output:
+//     d0 = V0, d4 = Vinf, d2 = (V1+Vm1)/2 - d0 - d4, S = (V1-Vm1)/2 = d1+d3, T = (V2 - d0 - 4 d2 - 16 d4)/2 = d1+4 d3,
+//     d3 = (T-S)/3, d1 = S-d3;   c0 = d0 + NR d3, c1 = d1 + NR d4, c2 = d2.
+// 5 x 4 = 20 wide multiplies per Fq3 MAC instead of Karatsuba's 24 and no pre-additions in the loop at all: the matrix
+// side is stored evaluated (5 words per entry instead of 3: lat::derive_toom_kernel), the witness side arrives evaluated
+// from its producer (toom_eval below).  The single-witness kernel stays Karatsuba on the 3-word matrix: it is bound by
+// the bytes of the matrix, and 5 words per entry would cost more HBM time than the four multiplies save.
+// ---------------------------------------------------------------------------------------------------------
+constexpr u64 INV3 = 0xAAAAAAAA00000001ull;  // 3 * INV3 = 2 q + 1
+
+// x / 2 mod q for canonical x: (x + q) / 2 when x is odd, and (q + 1) / 2 = 2^63 - 2^31 + 1
+__host__ __device__ __forceinline__ u64 half(u64 x) { return (x >> 1) + ((x & 1) ? 0x7FFFFFFF80000001ull : 0ull); }
+
+// canonical (x0, x1, x2) -> the evaluations at 1, -1 and 2, canonical (the values at 0 and infinity are x0 and x2)
+__device__ __forceinline__ void toom_eval(u64 x0, u64 x1, u64 x2, u64 &t1, u64 &tm, u64 &t2) {
+    const u64 e = add(x0, x2);
+    t1 = add(e, x1);
+    tm = sub(e, x1);
+    u64 w = add(add(x2, x2), x1);  // x1 + 2 x2
+    t2 = add(add(w, w), x0);
+}
+
+struct ToomAcc {
+    WideAcc v0, vinf, v1, vm1, v2;
+    __device__ __forceinline__ void clear() {
+        v0.clear(); vinf.clear(); v1.clear(); vm1.clear(); v2.clear();
+    }
+    // a*: the matrix entry's evaluations in the order (0, infinity, 1, -1, 2); y*: the witness slot's, same order
+    __device__ __forceinline__ void mac(u64 a0, u64 ainf, u64 a1, u64 am1, u64 a2, u64 y0, u64 yinf, u64 y1, u64 ym1, u64 y2) {
+        v0.mac(a0, y0);
+        vinf.mac(ainf, yinf);
+        v1.mac(a1, y1);
+        vm1.mac(am1, ym1);
+        v2.mac(a2, y2);
+    }
+    __device__ __forceinline__ void finish(u64 &c0, u64 &c1, u64 &c2) const {
+        const u64 d0 = v0.reduce(), d4 = vinf.reduce(), r1 = v1.reduce(), rm = vm1.reduce(), r2 = v2.reduce();
+        const u64 d2 = sub(sub(half(add(r1, rm)), d0), d4);
+        const u64 s = half(sub(r1, rm));
+        const u64 t = half(sub(sub(sub(r2, d0), mul_pow2<2>(d2)), mul_pow2<4>(d4)));
+        const u64 d3 = mul(sub(t, s), INV3);
+        const u64 d1 = sub(s, d3);
+        c0 = add(d0, mul_pow2<40>(d3));
+        c1 = add(d1, mul_pow2<40>(d4));
+        c2 = d2;
+    }
+};
+
 // Plain (eager) Fq3 product, for the small kernels.
 __device__ __forceinline__ void fq3_mul(const u64 a[3], const u64 b[3], u64 c[3]) {
     u64 t12 = add(mul(a[1], b[2]), mul(a[2], b[1]));

@@ -39,7 +39,7 @@ void launch_witness(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool i
 
 // int16 coefficients -> K base-2 digit planes: plane k of element j = sign * bit_k(|c|).
 //   planes_f     : K x n x 24 CRT form, or nullptr
-//   planes_fx    : K x n x 48 CRT form in the extended layout, or nullptr
+//   planes_fx    : K x n x 48 CRT form in the extended layout, Toom-3 form (see FX_WORDS), or nullptr
 //   planes_coeff : K x n x 24 coefficient form, or nullptr
 void launch_planes(const int16_t *f16, u64 n, int K, bool mont, u64 *planes_f, u64 *planes_fx, u64 *planes_coeff,
                    cudaStream_t stream);
@@ -62,13 +62,19 @@ struct MatLayout {
     uint32_t rg;         // row groups (warps along rows) per CTA = rb / 4
     uint32_t cg;         // column groups (warps along columns) per CTA
     uint32_t tj;         // columns per tile
+    uint32_t nc;         // u64 per Fq3 entry: 3 (components; the single-witness kernel) or 5 (Toom-3 evaluations; several witnesses)
     u64 n;               // logical columns
     u64 n_pad;           // columns incl. zero padding (multiple of tj)
     u64 ntiles;          // n_pad / tj
-    __host__ __device__ u64 tile_elems() const { return (u64)tj * 3 * rb * 8; }           // u64 per tile
+    __host__ __device__ u64 tile_elems() const { return (u64)tj * nc * rb * 8; }          // u64 per tile
     __host__ __device__ u64 total_elems() const { return tile_elems() * ntiles * nrb; }   // u64 in the whole matrix
 };
-MatLayout make_layout(uint32_t kappa, u64 n);
+MatLayout make_layout(uint32_t kappa, u64 n, bool toom = false);
+
+// The 5-word matrix of the several-witness kernels, derived on the device from the 3-word one (both canonical): entry
+// (a0, a1, a2) -> its values at 0, infinity, 1, -1, 2 = (a0, a2, a0+a1+a2, a0-a1+a2, a0+2 a1+4 a2) mod q.  A5_dev must be
+// zero where it is padding (columns >= n); only columns < n are written.
+void launch_derive_toom(const u64 *A_dev, const MatLayout &lay, u64 *A5_dev, const MatLayout &lay5, cudaStream_t stream);
 
 // rows: nrows x row_stride x 24 (CRT form, caller's representation) -> tiles of A_dev (canonical form).
 void launch_relayout(const u64 *rows, uint32_t row0, uint32_t nrows, u64 row_stride, bool mont, const MatLayout &lay,
@@ -85,13 +91,17 @@ struct MacPlan {
 };
 MacPlan plan_mac(const MatLayout &lay, uint32_t planes, int sm_count);
 
-// Extended witness layout consumed by the MAC kernel: per element 8 slots x 6 u64 = (f0, f1, f2, f0+f1, f0+f2, f1+f2).
+// Extended witness layout consumed by the MAC kernel: per element 8 slots x 6 u64, in one of two forms --
+//   Karatsuba (one witness per launch):  (f0, f1, f2, f0+f1, f0+f2, f1+f2)
+//   Toom-3 (several witnesses, planes):  (f0, f1, f2, f(1), f(-1), f(2)) = (.., f0+f1+f2, f0-f1+f2, f0+2 f1+4 f2)
+// The producer and the launch must agree: witness_kernel writes the first form, planes_kernel the second, fext either.
 constexpr int FX_WORDS = 48;
 // f (count x 24, CRT form, any representation) -> fx (count x 48)
-void launch_fext(const u64 *f, u64 count, u64 *fx, cudaStream_t stream);
+void launch_fext(const u64 *f, u64 count, u64 *fx, cudaStream_t stream, bool toom = false);
 
 // cms[p][i][24] = sum_j A[i][j] * F[p][j]   for p < planes;  Fx: planes x f_stride x 48 in the extended layout
-// (f_stride >= n in elements; no padding needed).
+// (f_stride >= n in elements; no padding needed).  lay.nc selects the form: 3 = A_dev in components and Fx in the
+// Karatsuba form, 5 = A_dev in Toom-3 evaluations (launch_derive_toom) and Fx in the Toom-3 form.
 // Optional completion report straight into page-locked host memory (pipelined host-buffer steps): the last CTA also
 // stores the commitment to cm_host, moves the step's overflow flag to flag_host (clearing the device copy) and then
 // publishes done_value in *done_host with system scope -- no copy, no event, nothing between two kernels in the stream.
@@ -110,7 +120,8 @@ void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_str
 void launch_y0(const u64 *cm, u64 *cms, uint32_t K, uint32_t kappa, cudaStream_t stream);
 
 // f0[j] = sum_{i < nplanes} rho[i] (*) planes[i][j]  (slot-wise Fq3), planes given as `nsides` extended-layout
-// buffers of planes_per_side x n x 48 each.  rho: nplanes x 24 in the caller's representation.  f0: n x 24.
+// buffers of planes_per_side x n x 48 each (Toom-3 form, as planes_kernel writes them).  rho: nplanes x 24 in the
+// caller's representation.  f0: n x 24.
 void launch_fold(const u64 *const *sides_fx, int nsides, int planes_per_side, u64 n, const u64 *rho, bool mont, u64 *f0,
                  cudaStream_t stream);
 

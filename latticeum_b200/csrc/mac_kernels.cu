@@ -28,6 +28,7 @@
 //    commitment comes out in the caller's representation without any conversion (the map is Fq-linear).
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "kernels.h"
 #include "ring24.cuh"
@@ -46,9 +47,15 @@ constexpr int FX = 48;  // u64 per element in the extended witness layout (8 slo
 // Compile-time geometry per row-group count RG (rows per block RB = 4 RG <= 32).
 __host__ __device__ constexpr int geo_cg(int rg) { return rg == 1 ? 8 : rg == 2 ? 4 : rg <= 4 ? 2 : 1; }
 __host__ __device__ constexpr int geo_tj(int rg) { return ((LAT_TJ_BYTES / (4 * rg)) / geo_cg(rg)) * geo_cg(rg) < geo_cg(rg) ? geo_cg(rg) : ((LAT_TJ_BYTES / (4 * rg)) / geo_cg(rg)) * geo_cg(rg); }
+// the 5-word (Toom-3) matrix: a column is 5/3 as many bytes, so fewer columns per tile keep a tile at 38-48 KB
+#ifndef LAT_TJ5_BYTES
+#define LAT_TJ5_BYTES 153
+#endif
+__host__ __device__ constexpr int geo_tj5(int rg) { return ((LAT_TJ5_BYTES / (4 * rg)) / geo_cg(rg)) * geo_cg(rg) < geo_cg(rg) ? geo_cg(rg) : ((LAT_TJ5_BYTES / (4 * rg)) / geo_cg(rg)) * geo_cg(rg); }
 
-MatLayout make_layout(uint32_t kappa, u64 n) {
+MatLayout make_layout(uint32_t kappa, u64 n, bool toom) {
     MatLayout l{};
+    l.nc = toom ? 5 : 3;
     l.kappa = kappa;
     l.n = n;
     uint32_t k4 = (kappa + 3) / 4 * 4;
@@ -62,7 +69,7 @@ MatLayout make_layout(uint32_t kappa, u64 n) {
     l.nrb = l.kappa_pad / l.rb;
     l.rg = l.rb / 4;
     l.cg = geo_cg((int)l.rg);
-    l.tj = geo_tj((int)l.rg);  // ~48 KB tiles (tj * rb * 192 B): per-tile barrier/refill costs favour large tiles
+    l.tj = toom ? geo_tj5((int)l.rg) : geo_tj((int)l.rg);  // ~48 KB tiles (tj * rb * 192 B): per-tile barrier/refill costs favour large tiles
     l.ntiles = (n + l.tj - 1) / l.tj;
     if (l.ntiles == 0) l.ntiles = 1;
     l.n_pad = l.ntiles * l.tj;
@@ -104,9 +111,52 @@ void launch_relayout(const u64 *rows, uint32_t row0, uint32_t nrows, u64 row_str
     else relayout_kernel<false><<<grid, 256, 0, stream>>>(rows, row0, nrows, row_stride, lay, A_dev);
 }
 
+// ---- 3-word matrix -> 5-word (Toom-3 evaluations) matrix, on the device ------------------------------------------------
+// One thread per (row block, column, row, slot); (row, slot) fastest, so a warp reads and writes 32 consecutive u64 of a
+// component / an evaluation.  Padding rows are zero in A and stay zero (every evaluation of 0 is 0).
+__global__ void __launch_bounds__(256)
+derive_toom_kernel(const u64 *__restrict__ A3, MatLayout lay, u64 *__restrict__ A5, MatLayout lay5) {
+    const u64 per_col = (u64)lay.rb * 8;
+    const u64 idx = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (u64)lay.nrb * lay.n * per_col) return;
+    const u64 w = idx % per_col;  // il * 8 + s
+    const u64 cj = idx / per_col;
+    const u64 j = cj % lay.n;
+    const u64 rbk = cj / lay.n;
+    const u64 t3 = j / lay.tj, jj3 = j - t3 * lay.tj;
+    const u64 *src = A3 + (rbk * lay.ntiles + t3) * lay.tile_elems() + jj3 * 3 * per_col + w;
+    const u64 a0 = src[0], a1 = src[per_col], a2 = src[2 * per_col];
+    u64 t1, tm, t2;
+    gl::toom_eval(a0, a1, a2, t1, tm, t2);
+    const u64 t5 = j / lay5.tj, jj5 = j - t5 * lay5.tj;
+    u64 *dst = A5 + (rbk * lay5.ntiles + t5) * lay5.tile_elems() + jj5 * 5 * per_col + w;
+    dst[0] = a0;
+    dst[per_col] = a2;
+    dst[2 * per_col] = t1;
+    dst[3 * per_col] = tm;
+    dst[4 * per_col] = t2;
+}
+void launch_derive_toom(const u64 *A_dev, const MatLayout &lay, u64 *A5_dev, const MatLayout &lay5, cudaStream_t stream) {
+    const u64 total = (u64)lay.nrb * lay.n * lay.rb * 8;
+    if (!total) return;
+    derive_toom_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(A_dev, lay, A5_dev, lay5);
+}
+
 // ---- witness -> extended layout (only for caller-supplied CRT-form witnesses; the CRT kernels emit it directly) -----
 // One thread per PAIR of slots: 48 bytes in (three 16-byte loads), 96 bytes out as three 256-bit stores -- whole 32-byte
 // sectors, so L2 never has to read-merge a half-written one (the 16-byte stores of round 1 ran at 3.2 TB/s).
+// the three derived words of a slot: Karatsuba sums (any representative) or Toom-3 evaluations (see kernels.h FX_WORDS)
+template <bool TOOM>
+__device__ __forceinline__ void fx_derived(u64 f0, u64 f1, u64 f2, u64 &d0, u64 &d1, u64 &d2) {
+    if constexpr (TOOM) {
+        gl::toom_eval(f0, f1, f2, d0, d1, d2);
+    } else {
+        d0 = gl::add_lazy(f0, f1);
+        d1 = gl::add_lazy(f0, f2);
+        d2 = gl::add_lazy(f1, f2);
+    }
+}
+template <bool TOOM>
 __global__ void __launch_bounds__(256)
 fext_kernel(const u64 *__restrict__ f, u64 count_pairs, u64 *__restrict__ fx) {
     asm volatile("griddepcontrol.launch_dependents;");  // the MAC behind it may start its prologue (see mac_kernel)
@@ -117,11 +167,15 @@ fext_kernel(const u64 *__restrict__ f, u64 count_pairs, u64 *__restrict__ fx) {
     const u64 a0 = gl::reduce128(v0.x, 0), a1 = gl::reduce128(v0.y, 0), a2 = gl::reduce128(v1.x, 0);
     const u64 b0 = gl::reduce128(v1.y, 0), b1 = gl::reduce128(v2.x, 0), b2 = gl::reduce128(v2.y, 0);
     u64 *o = fx + i * 12;
-    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(o), "l"(a0), "l"(a1), "l"(a2), "l"(gl::add_lazy(a0, a1)) : "memory");
-    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "l"(gl::add_lazy(a0, a2)), "l"(gl::add_lazy(a1, a2)), "l"(b0), "l"(b1) : "memory");
-    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(o + 8), "l"(b2), "l"(gl::add_lazy(b0, b1)), "l"(gl::add_lazy(b0, b2)), "l"(gl::add_lazy(b1, b2)) : "memory");
+    u64 x0, x1, x2, y0, y1, y2;
+    fx_derived<TOOM>(a0, a1, a2, x0, x1, x2);
+    fx_derived<TOOM>(b0, b1, b2, y0, y1, y2);
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(o), "l"(a0), "l"(a1), "l"(a2), "l"(x0) : "memory");
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "l"(x1), "l"(x2), "l"(b0), "l"(b1) : "memory");
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(o + 8), "l"(b2), "l"(y0), "l"(y1), "l"(y2) : "memory");
 }
 // unaligned callers (a witness pointer that is not 16-byte aligned): one thread per slot, 8-byte accesses
+template <bool TOOM>
 __global__ void __launch_bounds__(256)
 fext_kernel_unaligned(const u64 *__restrict__ f, u64 count_slots, u64 *__restrict__ fx) {
     asm volatile("griddepcontrol.launch_dependents;");
@@ -129,19 +183,25 @@ fext_kernel_unaligned(const u64 *__restrict__ f, u64 count_slots, u64 *__restric
     if (i >= count_slots) return;
     u64 f0 = f[i * 3], f1 = f[i * 3 + 1], f2 = f[i * 3 + 2];
     f0 = gl::reduce128(f0, 0); f1 = gl::reduce128(f1, 0); f2 = gl::reduce128(f2, 0);
+    u64 d0, d1, d2;
+    fx_derived<TOOM>(f0, f1, f2, d0, d1, d2);
     ulonglong2 *o = reinterpret_cast<ulonglong2 *>(fx + i * 6);
     o[0] = make_ulonglong2(f0, f1);
-    o[1] = make_ulonglong2(f2, gl::add_lazy(f0, f1));
-    o[2] = make_ulonglong2(gl::add_lazy(f0, f2), gl::add_lazy(f1, f2));
+    o[1] = make_ulonglong2(f2, d0);
+    o[2] = make_ulonglong2(d1, d2);
 }
-void launch_fext(const u64 *f, u64 count, u64 *fx, cudaStream_t stream) {
+void launch_fext(const u64 *f, u64 count, u64 *fx, cudaStream_t stream, bool toom) {
     if (!count) return;
     if ((reinterpret_cast<uintptr_t>(f) & 15) == 0 && (reinterpret_cast<uintptr_t>(fx) & 31) == 0) {
         const u64 pairs = count * (ring::NSLOT / 2);
-        fext_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, stream>>>(f, pairs, fx);
+        const unsigned grid = (unsigned)((pairs + 255) / 256);
+        if (toom) fext_kernel<true><<<grid, 256, 0, stream>>>(f, pairs, fx);
+        else fext_kernel<false><<<grid, 256, 0, stream>>>(f, pairs, fx);
     } else {
         const u64 slots = count * ring::NSLOT;
-        fext_kernel_unaligned<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(f, slots, fx);
+        const unsigned grid = (unsigned)((slots + 255) / 256);
+        if (toom) fext_kernel_unaligned<true><<<grid, 256, 0, stream>>>(f, slots, fx);
+        else fext_kernel_unaligned<false><<<grid, 256, 0, stream>>>(f, slots, fx);
     }
 }
 
@@ -150,13 +210,14 @@ void launch_fext(const u64 *f, u64 count, u64 *fx, cudaStream_t stream) {
 // Shared memory: STAGES x { A tile | PT x TJ x 48 u64 of extended witness } + 2*STAGES mbarriers.
 // Workspace: ws[2*i], ws[2*i+1] = sums of the low / high 32-bit halves of output i = (p * kappa + row) * 24 + s*3 + c;
 // ws[2 * nout] = finished-CTA counter.  Must be zero before the first launch; every launch leaves it zero again.
-template <int PT, int RG>
+template <int PT, int RG, bool TOOM>
 struct MacGeo {
-    static constexpr int RB = 4 * RG, CG = geo_cg(RG), TJ = geo_tj(RG);
+    static constexpr int RB = 4 * RG, CG = geo_cg(RG), TJ = TOOM ? geo_tj5(RG) : geo_tj(RG);
+    static constexpr int NC = TOOM ? 5 : 3;  // u64 per matrix entry
     // RG*CG warps, all consumers; lane 0 of warp 0 also issues the TMA copies.  (A dedicated 9th producer warp
     // halves the occupancy: warp slots are handed out four at a time -- measured with the occupancy API.)
     static constexpr int NCONS = RG * CG, THREADS = NCONS * 32;
-    static constexpr u32 TILE_ELEMS = TJ * 3 * RB * 8;
+    static constexpr u32 TILE_ELEMS = TJ * NC * RB * 8;
     static constexpr u32 TILE_BYTES = TILE_ELEMS * 8;
     static constexpr u32 F_BYTES = TJ * FX * 8;  // per plane per tile
     static constexpr u32 STAGE_BYTES = TILE_BYTES + PT * F_BYTES;
@@ -183,11 +244,11 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define TRACE(k)
 #endif
 
-template <int PT, int RG>
-__global__ void __launch_bounds__(MacGeo<PT, RG>::THREADS, MacGeo<PT, RG>::MIN_CTAS)
+template <int PT, int RG, bool TOOM>
+__global__ void __launch_bounds__(MacGeo<PT, RG, TOOM>::THREADS, MacGeo<PT, RG, TOOM>::MIN_CTAS)
 mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__ Fx, u64 f_stride, uint32_t planes,
            uint32_t stages, u64 *__restrict__ ws, u64 *__restrict__ cms, uint32_t dependent_launch, MacReport report) {
-    using G = MacGeo<PT, RG>;
+    using G = MacGeo<PT, RG, TOOM>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // after the stages: [full mbarrier x stages][release counter x stages]
     u64 *bars = reinterpret_cast<u64 *>(smem_raw + (size_t)stages * G::STAGE_BYTES);
@@ -222,7 +283,7 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
     auto issue_matrix = [&](u32 nt, u32 st) {
         mbar_arrive_expect_tx(&bars[st], G::TILE_BYTES + PT * witness_bytes(nt));
 #ifndef LAT_NO_L2_HINT
-        if constexpr (PT == 1)  // streamed once; with several plane groups the other groups' CTAs re-read the tile from L2
+        if constexpr (PT == 1 && !TOOM)  // streamed once; with several plane groups the other groups' CTAs re-read the tile from L2
             tma_bulk_g2s_hint(smem_raw + (size_t)st * G::STAGE_BYTES, a_src + (u64)nt * G::TILE_ELEMS, G::TILE_BYTES, &bars[st],
                               L2_EVICT_FIRST);
         else
@@ -270,7 +331,7 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
 
     const u32 rgi = warp / G::CG, cgi = warp % G::CG;
     const u32 il = rgi * 4 + (lane >> 3), s = lane & 7;
-    gl::Fq3Acc acc[PT];
+    typename std::conditional<TOOM, gl::ToomAcc, gl::Fq3Acc>::type acc[PT];
 #pragma unroll
     for (int p = 0; p < PT; ++p) acc[p].clear();
 
@@ -294,21 +355,24 @@ mac_kernel(const u64 *__restrict__ A_dev, MatLayout lay, const u64 *__restrict__
 #pragma unroll
         for (int q = 0; q < G::TJ / G::CG; ++q) {
             const u32 jj = cgi + q * G::CG;
-            const u64 *pa = sa + jj * (3 * G::RB * 8);
+            const u64 *pa = sa + jj * (G::NC * G::RB * 8);
             u64 a0 = pa[0], a1 = pa[G::RB * 8], a2 = pa[2 * G::RB * 8];
-            if constexpr (PT == 1) {
+            if constexpr (TOOM) {
+                // the entry's evaluations at (0, infinity, 1, -1, 2) against each witness slot's (f0, f1, f2, f(1), f(-1), f(2))
+                const u64 a3 = pa[3 * G::RB * 8], a4 = pa[4 * G::RB * 8];
+#pragma unroll
+                for (int p = 0; p < PT; ++p) {
+                    const ulonglong2 *pf = sf + (p * G::TJ + jj) * (FX / 2);
+                    const u64 y0 = reinterpret_cast<const u64 *>(pf)[0];
+                    const ulonglong2 y = pf[1], z = pf[2];
+                    acc[p].mac(a0, a1, a2, a3, a4, y0, y.x, y.y, z.x, z.y);
+                }
+            } else if constexpr (PT == 1) {
                 // one witness: exact 65-bit sums, the carry goes straight into the accumulator (fewest instructions)
                 ulonglong2 x = sf[jj * (FX / 2)], y = sf[jj * (FX / 2) + 1], z = sf[jj * (FX / 2) + 2];
                 acc[0].mac(a0, a1, a2, x.x, x.y, y.x, y.y, z.x, z.y);
             } else {
-                // several witnesses share the matrix entry: fold its three sums to 64 bits once
-                const u64 a01 = gl::add_fold(a0, a1), a02 = gl::add_fold(a0, a2), a12 = gl::add_fold(a1, a2);
-#pragma unroll
-                for (int p = 0; p < PT; ++p) {
-                    const ulonglong2 *pf = sf + (p * G::TJ + jj) * (FX / 2);
-                    ulonglong2 x = pf[0], y = pf[1], z = pf[2];
-                    acc[p].mac_presummed(a0, a1, a2, a01, a02, a12, x.x, x.y, y.x, y.y, z.x, z.y);
-                }
+                static_assert(TOOM || PT == 1, "launches with several witnesses take the Toom-3 instance");
             }
         }
         __syncwarp();
@@ -388,19 +452,18 @@ extern "C" int lat_debug_mac_trace(unsigned long long *out, int ctas) {
 }
 #endif
 
-template <int PT, int RG>
-static size_t mac_stage_bytes() { return MacGeo<PT, RG>::STAGE_BYTES; }
-
-static size_t stage_bytes_for(uint32_t pt, uint32_t rg) {
-    size_t tile = (size_t)geo_tj((int)rg) * 3 * (4 * rg) * 64;
-    return tile + (size_t)pt * geo_tj((int)rg) * FX * 8;
+static size_t stage_bytes_for(uint32_t pt, const MatLayout &lay) {
+    return (size_t)lay.tile_elems() * 8 + (size_t)pt * lay.tj * FX * 8;
 }
 
 MacPlan plan_mac(const MatLayout &lay, uint32_t planes, int sm_count) {
     MacPlan m{};
-    m.pt = (planes % 2 == 0) ? 2 : 1;
-    size_t stage_bytes = stage_bytes_for(m.pt, lay.rg);
-    uint32_t occ_cap = (m.pt == 1) ? 2 : 1;
+    // witnesses per thread: the Toom-3 accumulators of 4 witnesses still fit the register file (250 registers, no spills),
+    // and every doubling halves the matrix bytes an SM pulls from L2 per witness -- at 2 per thread the 5-word matrix
+    // runs into the L2 -> SM port (about 44 GB/s per SM measured) before the multiply pipe is full
+    m.pt = lay.nc != 5 ? 1 : planes % 4 == 0 ? 4 : planes % 2 == 0 ? 2 : 1;
+    size_t stage_bytes = stage_bytes_for(m.pt, lay);
+    uint32_t occ_cap = (m.pt == 1) ? 2 : 1;  // = MacGeo::MIN_CTAS
     // as many stages as fit next to occ_cap resident CTAs (227 KB usable, 1 KB reserved per CTA), at most 6
     size_t per_cta = (227 * 1024) / occ_cap - SM_RESERVED_SMEM - 1024;  // 16 B of sync state per stage
     uint32_t stages = (uint32_t)(per_cta / stage_bytes);
@@ -423,7 +486,7 @@ MacPlan plan_mac(const MatLayout &lay, uint32_t planes, int sm_count) {
     return m;
 }
 
-template <int PT, int RG>
+template <int PT, int RG, bool TOOM>
 static void launch_mac_t(dim3 grid, const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes,
                          const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream, bool pdl, const MacReport &report) {
     // function attributes are per device: a process may hold handles on several GPUs
@@ -432,22 +495,22 @@ static void launch_mac_t(dim3 grid, const u64 *A_dev, const MatLayout &lay, cons
     cudaGetDevice(&dev);
     bool &attr_set = attr_set_on[dev & 63];
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mac_kernel<PT, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // minus the static bytes
-        if (e != cudaSuccess) fprintf(stderr, "lattice_ajtai: cudaFuncSetAttribute(mac_kernel<%d,%d>): %s\n", PT, RG, cudaGetErrorString(e));
+        cudaError_t e = cudaFuncSetAttribute(mac_kernel<PT, RG, TOOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // minus the static bytes
+        if (e != cudaSuccess) fprintf(stderr, "lattice_ajtai: cudaFuncSetAttribute(mac_kernel<%d,%d,%d>): %s\n", PT, RG, (int)TOOM, cudaGetErrorString(e));
         attr_set = true;
     }
     if (getenv("LAT_DEBUG")) {
         cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, mac_kernel<PT, RG>);
+        cudaFuncGetAttributes(&fa, mac_kernel<PT, RG, TOOM>);
         int occ = -1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mac_kernel<PT, RG>, MacGeo<PT, RG>::THREADS, plan.smem_bytes);
-        fprintf(stderr, "mac_kernel<%d,%d>: grid=(%u,%u,%u) block=%d smem=%zu stages=%u regs=%d maxDyn=%d static=%zu occ=%d maxThreads=%d\n",
-                PT, RG, grid.x, grid.y, grid.z, MacGeo<PT, RG>::THREADS, plan.smem_bytes, plan.stages, fa.numRegs,
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mac_kernel<PT, RG, TOOM>, MacGeo<PT, RG, TOOM>::THREADS, plan.smem_bytes);
+        fprintf(stderr, "mac_kernel<%d,%d,%d>: grid=(%u,%u,%u) block=%d smem=%zu stages=%u regs=%d maxDyn=%d static=%zu occ=%d maxThreads=%d\n",
+                PT, RG, (int)TOOM, grid.x, grid.y, grid.z, MacGeo<PT, RG, TOOM>::THREADS, plan.smem_bytes, plan.stages, fa.numRegs,
                 fa.maxDynamicSharedSizeBytes, fa.sharedSizeBytes, occ, fa.maxThreadsPerBlock);
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(MacGeo<PT, RG>::THREADS);
+    cfg.blockDim = dim3(MacGeo<PT, RG, TOOM>::THREADS);
     cfg.dynamicSmemBytes = plan.smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -455,21 +518,21 @@ static void launch_mac_t(dim3 grid, const u64 *A_dev, const MatLayout &lay, cons
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, mac_kernel<PT, RG>, A_dev, lay, Fx, f_stride, planes, plan.stages, workspace, cms, (uint32_t)(pdl ? 1 : 0), report);
+    cudaLaunchKernelEx(&cfg, mac_kernel<PT, RG, TOOM>, A_dev, lay, Fx, f_stride, planes, plan.stages, workspace, cms, (uint32_t)(pdl ? 1 : 0), report);
 }
 
-template <int PT>
+template <int PT, bool TOOM>
 static void launch_mac_pt(dim3 grid, const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_stride, uint32_t planes,
                           const MacPlan &plan, u64 *workspace, u64 *cms, cudaStream_t stream, bool pdl, const MacReport &report) {
     switch (lay.rg) {
-        case 1: launch_mac_t<PT, 1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
-        case 2: launch_mac_t<PT, 2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
-        case 3: launch_mac_t<PT, 3>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
-        case 4: launch_mac_t<PT, 4>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
-        case 5: launch_mac_t<PT, 5>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
-        case 6: launch_mac_t<PT, 6>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
-        case 7: launch_mac_t<PT, 7>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
-        default: launch_mac_t<PT, 8>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 1: launch_mac_t<PT, 1, TOOM>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 2: launch_mac_t<PT, 2, TOOM>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 3: launch_mac_t<PT, 3, TOOM>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 4: launch_mac_t<PT, 4, TOOM>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 5: launch_mac_t<PT, 5, TOOM>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 6: launch_mac_t<PT, 6, TOOM>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        case 7: launch_mac_t<PT, 7, TOOM>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
+        default: launch_mac_t<PT, 8, TOOM>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report); break;
     }
 }
 
@@ -481,8 +544,13 @@ void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_str
     static const bool pdl_off = getenv("LAT_NO_PDL") != nullptr;
     const bool pdl = !ev_begin && !pdl_off;
     if (ev_begin) cudaEventRecord(ev_begin, stream);
-    if (plan.pt == 1) launch_mac_pt<1>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report);
-    else launch_mac_pt<2>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report);
+    if (lay.nc == 5) {  // several witnesses: Toom-3 evaluations on both sides
+        if (plan.pt == 1) launch_mac_pt<1, true>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report);
+        else if (plan.pt == 4) launch_mac_pt<4, true>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report);
+        else launch_mac_pt<2, true>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report);
+    } else {            // one witness: Karatsuba on the 3-word matrix (bound by the bytes of the matrix)
+        launch_mac_pt<1, false>(grid, A_dev, lay, Fx, f_stride, planes, plan, workspace, cms, stream, pdl, report);
+    }
     if (ev_end) cudaEventRecord(ev_end, stream);
 }
 
@@ -503,8 +571,9 @@ void launch_y0(const u64 *cm, u64 *cms, uint32_t K, uint32_t kappa, cudaStream_t
 
 // ---- compute_f_0: f0[j] = sum_i rho_i (*) f_i[j] over the 2K resident planes (LF/nifs/folding.rs:258-268) --------------
 // One thread per (element, slot): it walks the planes (a 48-byte extended-layout slot each, consecutive threads read
-// consecutive slots), multiplies by rho_i's slot from shared memory and accumulates lazily with the same Karatsuba
-// accumulators as the MAC; one reduction at the end.  HBM-bound on reading the planes once (2K x n x 384 B).
+// consecutive slots; Toom-3 form, as planes_kernel writes them), multiplies by rho_i's slot -- evaluated at the same five
+// points once per block, in shared memory -- and accumulates lazily with the same Toom-3 accumulators as the MAC; one
+// interpolation and reduction at the end.  HBM-bound on reading the planes once (2K x n x 384 B).
 constexpr int FOLD_MAX_PLANES = 64;
 constexpr int FOLD_THREADS = 256, FOLD_STAGES = 4;
 constexpr u32 FOLD_STAGE_BYTES = FOLD_THREADS * 6 * 8;  // one plane's 48-byte slots of the block's 256 (element, slot) items
@@ -517,7 +586,7 @@ fold_kernel(const u64 *__restrict__ s0, const u64 *__restrict__ s1, int nsides, 
     // arithmetic (plain loads left the kernel latency-bound at 4.1 TB/s: two 256-thread blocks per SM cannot keep
     // enough 16-byte loads in flight).
     extern __shared__ __align__(128) unsigned char fold_smem[];
-    __shared__ u64 s_rho[FOLD_MAX_PLANES * ring::D];
+    __shared__ u64 s_rho[FOLD_MAX_PLANES * ring::NSLOT * 5];  // per (plane, slot): rho's values at 0, infinity, 1, -1, 2
     __shared__ __align__(8) u64 bars[FOLD_STAGES];
     const int nplanes = nsides * pps;
     const u64 total = n * ring::NSLOT;
@@ -533,15 +602,23 @@ fold_kernel(const u64 *__restrict__ s0, const u64 *__restrict__ s1, int nsides, 
             tma_bulk_g2s(fold_smem + (size_t)p * FOLD_STAGE_BYTES, plane_src(p), bytes, &bars[p]);
         }
     }
-    for (int i = threadIdx.x; i < nplanes * ring::D; i += blockDim.x) {
-        u64 v = rho[i];
-        s_rho[i] = MONT ? gl::from_mont(v) : gl::reduce128(v, 0);  // canonical(rho) * repr(f) = repr(rho * f)
+    for (int i = threadIdx.x; i < nplanes * ring::NSLOT; i += blockDim.x) {  // (plane, slot)
+        u64 r[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const u64 v = rho[i * 3 + c];
+            r[c] = MONT ? gl::from_mont(v) : gl::reduce128(v, 0);  // canonical(rho) * repr(f) = repr(rho * f)
+        }
+        u64 *o = s_rho + i * 5;
+        o[0] = r[0];
+        o[1] = r[2];
+        gl::toom_eval(r[0], r[1], r[2], o[2], o[3], o[4]);
     }
     __syncthreads();
     const u64 idx = item0 + threadIdx.x;  // (element, slot)
     const bool active = threadIdx.x < nitems;
     const u32 sl = (u32)(idx & 7);
-    gl::Fq3Acc acc;
+    gl::ToomAcc acc;
     acc.clear();
     int st = 0;
     u32 ph = 0;
@@ -550,8 +627,8 @@ fold_kernel(const u64 *__restrict__ s0, const u64 *__restrict__ s1, int nsides, 
         if (active) {
             const ulonglong2 *pf = reinterpret_cast<const ulonglong2 *>(fold_smem + (size_t)st * FOLD_STAGE_BYTES) + threadIdx.x * 3;
             const ulonglong2 x = pf[0], y = pf[1], z = pf[2];
-            const u64 *r = s_rho + p * ring::D + 3 * sl;
-            acc.mac(r[0], r[1], r[2], x.x, x.y, y.x, y.y, z.x, z.y);
+            const u64 *r = s_rho + (p * ring::NSLOT + sl) * 5;
+            acc.mac(r[0], r[1], r[2], r[3], r[4], x.x, y.x, y.y, z.x, z.y);
         }
         __syncthreads();  // everyone has read the stage
         if (threadIdx.x == 0 && p + FOLD_STAGES < nplanes) {

@@ -93,14 +93,25 @@ __device__ __forceinline__ void row_put_fx(ulonglong2 *tile, int row, const u64 
 __device__ __forceinline__ void st256(u64 *p, u64 a, u64 b, u64 c, u64 d) {
     asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
+// TOOM: the slot's derived words are its values at 1, -1, 2 (planes, read by the several-witness kernels and fold_kernel)
+// instead of the three Karatsuba sums (the single witness) -- kernels.h, FX_WORDS.
+template <bool TOOM = false>
 __device__ __forceinline__ void store_fx_row(u64 *__restrict__ o, const u64 (&x)[ring::D]) {
 #pragma unroll
     for (int s = 0; s < ring::NSLOT; s += 2) {
         const u64 a0 = x[3 * s], a1 = x[3 * s + 1], a2 = x[3 * s + 2];
         const u64 b0 = x[3 * s + 3], b1 = x[3 * s + 4], b2 = x[3 * s + 5];
-        st256(o + s * 6, a0, a1, a2, gl::add_lazy(a0, a1));
-        st256(o + s * 6 + 4, gl::add_lazy(a0, a2), gl::add_lazy(a1, a2), b0, b1);
-        st256(o + s * 6 + 8, b2, gl::add_lazy(b0, b1), gl::add_lazy(b0, b2), gl::add_lazy(b1, b2));
+        u64 p0, p1, p2, q0, q1, q2;
+        if constexpr (TOOM) {
+            gl::toom_eval(a0, a1, a2, p0, p1, p2);
+            gl::toom_eval(b0, b1, b2, q0, q1, q2);
+        } else {
+            p0 = gl::add_lazy(a0, a1); p1 = gl::add_lazy(a0, a2); p2 = gl::add_lazy(a1, a2);
+            q0 = gl::add_lazy(b0, b1); q1 = gl::add_lazy(b0, b2); q2 = gl::add_lazy(b1, b2);
+        }
+        st256(o + s * 6, a0, a1, a2, p0);
+        st256(o + s * 6 + 4, p1, p2, b0, b1);
+        st256(o + s * 6 + 8, b2, q0, q1, q2);
     }
 }
 // block-wide: copy `nrows` rows of ROW_UNITS units from the padded tile to the contiguous global run at `dst`
@@ -402,7 +413,7 @@ planes_kernel(const int16_t *__restrict__ f16, u64 n, int K, u64 *__restrict__ p
                 if (active) row_put(otile, threadIdx.x, c);
                 rows_out<PLAIN_UNITS>(otile, planes_f + elem0 * ring::D, nrows);
             }
-            if (planes_fx && active) store_fx_row(planes_fx + ((u64)k * n + e) * FX_WORDS, c);
+            if (planes_fx && active) store_fx_row<true>(planes_fx + ((u64)k * n + e) * FX_WORDS, c);
         }
     }
 }
