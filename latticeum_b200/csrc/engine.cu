@@ -202,7 +202,8 @@ struct lat_ajtai {
     bool mac_was_last = false;           // snapshot of the above at the start of the current entry point
     DevBuf fcoeff64;     // f_coeff as u64 for host output
     DevBuf planes;       // K x n x 24 CRT-form planes (only when a caller wants them)
-    DevBuf planes_fx[2]; // K x n x 48 CRT-form planes, extended layout (MAC input), one buffer per fold side
+    DevBuf planes_fx[2]; // K x n x 48 CRT-form planes, extended layout (MAC input, Toom-3 form), one buffer per fold side
+    DevBuf planes_lut;   // 48 KB subset-sum table of the planes' transform (planes_kernel), built at first use
     bool side_ready[2] = {false, false};
     int cur_side = 0;
     // fold step (lat_ajtai_fold_step_*): the running accumulator's coefficients as int16 digits, the 2 x K commitments of
@@ -473,7 +474,7 @@ void lat_ajtai_destroy(lat_ajtai *h) {
     cudaSetDevice(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     if (h->stream && h->stream != h->own_stream) cudaStreamSynchronize(h->stream);  // steps in flight write into our buffers
-    DevBuf *bufs[] = {&h->A, &h->A5, &h->stage, &h->in, &h->f16, &h->f, &h->fx, &h->fcoeff64, &h->planes, &h->planes_fx[0], &h->planes_fx[1],
+    DevBuf *bufs[] = {&h->A, &h->A5, &h->planes_lut, &h->stage, &h->in, &h->f16, &h->f, &h->fx, &h->fcoeff64, &h->planes, &h->planes_fx[0], &h->planes_fx[1],
                       &h->rho, &h->f0, &h->planes_coeff, &h->cms, &h->cm_in, &h->ws, &h->flag, &h->fx_alt,
                       &h->f16_acc, &h->cms_side[0], &h->cms_side[1], &h->cm_step, &h->cm_acc};
     for (DevBuf *b : bufs) b->release();
@@ -903,7 +904,11 @@ static int planes_core(lat_ajtai *h, const u64 *cm_dev, u64 *planes_coeff_dev, u
         h->side_ready[h->cur_side] = true;
     }
     if (pfx || planes_f_dev || planes_coeff_dev) {
-        lat::launch_planes(src16, h->n, (int)h->K, h->mont, planes_f_dev, pfx, planes_coeff_dev, h->stream);
+        if (!h->planes_lut.p) {  // once per handle: the subset-sum table of the planes' transform
+            if ((st = h->planes_lut.ensure(lat::PLANES_LUT_WORDS * sizeof(u64)))) return st;
+            lat::launch_planes_lut(h->mont, h->planes_lut.as<u64>(), h->stream);
+        }
+        lat::launch_planes(src16, h->n, (int)h->K, h->mont, h->planes_lut.as<u64>(), planes_f_dev, pfx, planes_coeff_dev, h->stream);
         CK(cudaGetLastError());
     }
     if (cms_dev) {

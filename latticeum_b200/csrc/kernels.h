@@ -41,8 +41,13 @@ void launch_witness(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool i
 //   planes_f     : K x n x 24 CRT form, or nullptr
 //   planes_fx    : K x n x 48 CRT form in the extended layout, Toom-3 form (see FX_WORDS), or nullptr
 //   planes_coeff : K x n x 24 coefficient form, or nullptr
-void launch_planes(const int16_t *f16, u64 n, int K, bool mont, u64 *planes_f, u64 *planes_fx, u64 *planes_coeff,
-                   cudaStream_t stream);
+//   lut          : the 3 x 256 x 8 subset-sum table of launch_planes_lut for the same representation
+void launch_planes(const int16_t *f16, u64 n, int K, bool mont, const u64 *lut, u64 *planes_f, u64 *planes_fx,
+                   u64 *planes_coeff, cudaStream_t stream);
+// lut[(c * 256 + pat) * 8 + s] = sum over the bits i of pat of the word of slot s that CRT(X^(3i+c)) is nonzero in
+// (PLANES_LUT_WORDS u64, canonical values in the representation `mont` names); see planes_kernel.
+constexpr int PLANES_LUT_WORDS = 3 * 256 * 8;
+void launch_planes_lut(bool mont, u64 *lut, cudaStream_t stream);
 
 // int16 digits (n x 24) -> Witness::get_fhat tables: fhat[j][i][3 s] = digit 8 j + s of element i as a field element in
 // the caller's representation, the other two components of every slot zero; fhat: 3 x n x 24.

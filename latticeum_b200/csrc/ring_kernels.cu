@@ -368,47 +368,125 @@ void launch_witness(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool i
 
 // ---- int16 coefficients -> K sign*bit planes, each CRT'd ---------------------------------------------------
 // decompose_B_vec_into_k_vec (latticefold/src/nifs/decomposition/utils.rs:45-49) + the CRT of Witness::from_f_coeff
-// (latticefold/src/arith.rs:327).  One thread per element (there are n = 98 815 of them, times K planes of work
-// each): plane k of it = sign * bit_k(|c|), transformed with the compile-time shift twiddles; every output goes
-// through the coalescing tile.
-constexpr int PLANE_THREADS = 64;
-#ifndef LAT_PLANES_BLOCKS
-#define LAT_PLANES_BLOCKS 8  // 128 registers: 156.8 us for pack + planes against 160.2 at 6 (168 registers); 10 and 12 spill and lose
-#endif
+// (latticefold/src/arith.rs:327).  One thread per element, K planes of work each: plane k of it = sign * bit_k(|c|).
+//
+// The CRT is Fq-linear and a plane's coefficients are -1, 0, 1, so a plane's CRT is a difference of two subset sums of the
+// 24 basis images CRT(X^t).  Coefficient X^(3i+c) only reaches one word of every slot (the ring is Fq[X]/(X^3 - zeta_s)
+// per slot: X^(3i+c) = zeta_s^i X^c), so the 24 coefficients fall into three classes of eight, and a 256-row table per
+// class -- row `pat` = sum of the images of the coefficients whose bit is set in pat, 8 slots each -- turns the whole
+// transform into 6 row reads and 24 modular subtractions:
+//     out[word(c, s)] = T[c][bits of the positive coefficients of class c][s] - T[c][bits of the negative ones][s].
+// The table (3 x 256 x 8 u64 = 48 KB, in the caller's representation) is built once per handle from crt24_small of the
+// unit vectors (planes_lut_kernel: the same arithmetic as every other transform here, so the results are the same bit
+// for bit) and copied into shared memory by every block.  About 600 instructions per element and plane instead of 2 100.
+// Table layout: [class c][slot pair h][pat] x 16 B, so that the 16-byte reads of a warp (one random row per lane) spread
+// over all banks.  Two kernels: planes_fx_kernel writes only the extended (Toom-3) rows the matrix-vector and fold kernels
+// read -- a slot pair at a time, so nothing but six table entries is live -- with the planes split over blockIdx.y;
+// planes_kernel also serves callers that want the plain CRT-form or coefficient-form planes.
+constexpr int PLANE_THREADS = 128;
+constexpr int LUT_ROWS = 3 * 256;
+constexpr int LUT_WORDS = LUT_ROWS * ring::NSLOT;  // 6144 u64
+// word of slot s that class c (coefficients 3i + c) lands in: homogenize_fq3 swaps components 1 and 2 in slots 4..7
+__host__ __device__ constexpr int plane_word(int c, int s) { return 3 * s + (c == 0 ? 0 : (s < 4 ? c : 3 - c)); }
+
 template <bool MONT>
-__global__ void __launch_bounds__(PLANE_THREADS, LAT_PLANES_BLOCKS)
-planes_kernel(const int16_t *__restrict__ f16, u64 n, int K, u64 *__restrict__ planes_f, u64 *__restrict__ planes_fx,
-              u64 *__restrict__ planes_coeff) {
+__global__ void __launch_bounds__(LUT_ROWS) planes_lut_kernel(u64 *__restrict__ lut) {
+    __shared__ u64 basis[ring::D][ring::NSLOT];  // basis[t][s] = the one nonzero word of CRT(X^t) in slot s
+    if (threadIdx.x < ring::D) {
+        int d[ring::D];
+        u64 x[ring::D];
+#pragma unroll
+        for (int t = 0; t < ring::D; ++t) d[t] = (t == (int)threadIdx.x) ? 1 : 0;
+        xf::crt24_small<MONT>(d, x);
+        const int c = threadIdx.x % 3;
+#pragma unroll
+        for (int s = 0; s < ring::NSLOT; ++s) {
+            const int want = plane_word(c, s);  // select without dynamic indexing of x
+            u64 v = 0;
+#pragma unroll
+            for (int j = 3 * s; j < 3 * s + 3; ++j)
+                if (j == want) v = x[j];
+            basis[threadIdx.x][s] = v;
+        }
+    }
+    __syncthreads();
+    const int c = threadIdx.x >> 8, pat = threadIdx.x & 255;
+    u64 acc[ring::NSLOT];
+#pragma unroll
+    for (int s = 0; s < ring::NSLOT; ++s) acc[s] = 0;
+    for (int i = 0; i < 8; ++i)
+        if ((pat >> i) & 1) {
+#pragma unroll
+            for (int s = 0; s < ring::NSLOT; ++s) acc[s] = gl::add(acc[s], basis[3 * i + c][s]);
+        }
+#pragma unroll
+    for (int s = 0; s < ring::NSLOT; ++s) lut[(((size_t)c * 4 + (s >> 1)) * 256 + pat) * 2 + (s & 1)] = acc[s];
+}
+void launch_planes_lut(bool mont, u64 *lut, cudaStream_t stream) {
+    if (mont) planes_lut_kernel<true><<<1, LUT_ROWS, 0, stream>>>(lut);
+    else planes_lut_kernel<false><<<1, LUT_ROWS, 0, stream>>>(lut);
+}
+
+template <bool MONT>
+__global__ void __launch_bounds__(PLANE_THREADS)
+planes_kernel(const int16_t *__restrict__ f16, u64 n, int K, const u64 *__restrict__ lut, u64 *__restrict__ planes_f,
+              u64 *__restrict__ planes_fx, u64 *__restrict__ planes_coeff) {
     asm volatile("griddepcontrol.launch_dependents;");  // the MAC behind it may start its prologue (see mac_kernel)
-    __shared__ __align__(16) ulonglong2 otile[PLANE_THREADS * (PLAIN_UNITS + 1)];  // staging for the plain outputs only
+    // dynamic shared memory: the table, then (only when a plain output is wanted) the staging tile of the plain rows
+    extern __shared__ __align__(16) unsigned char planes_smem[];
+    ulonglong2 *s_lut = reinterpret_cast<ulonglong2 *>(planes_smem);
+    ulonglong2 *otile = s_lut + LUT_WORDS / 2;
+    {
+        const ulonglong2 *g = reinterpret_cast<const ulonglong2 *>(lut);
+        for (int u = threadIdx.x; u < LUT_WORDS / 2; u += PLANE_THREADS) s_lut[u] = g[u];
+    }
+    __syncthreads();
     const u64 e0 = (u64)blockIdx.x * PLANE_THREADS;
     const u64 e = e0 + threadIdx.x;
     const bool active = e < n;
     const u32 nrows = (u32)min((u64)PLANE_THREADS, n - e0);
     int d[ring::D];
-    if (active) load_i16x24(f16 + e * ring::D, d);
+    u32 sgn[3] = {0, 0, 0};  // bit i of sgn[c]: coefficient 3i + c is negative
+    u32 mag[ring::D];
+    if (active) {
+        load_i16x24(f16 + e * ring::D, d);
+#pragma unroll
+        for (int t = 0; t < ring::D; ++t) {
+            mag[t] = (u32)(d[t] < 0 ? -d[t] : d[t]);
+            sgn[t % 3] |= (d[t] < 0 ? 1u : 0u) << (t / 3);
+        }
+    }
     for (int k = 0; k < K; ++k) {
         u64 c[ring::D];
-        int pd[ring::D];
-        if (active) {
-#pragma unroll
-            for (int t = 0; t < ring::D; ++t) {
-                int a = d[t] < 0 ? -d[t] : d[t];
-                int bit = (a >> k) & 1;
-                pd[t] = d[t] < 0 ? -bit : bit;  // digit k base 2 = sign * bit_k(|c|)
-            }
-        }
         const u64 elem0 = (u64)k * n + e0;
         if (planes_coeff) {
             if (active) {
 #pragma unroll
-                for (int t = 0; t < ring::D; ++t) c[t] = gl::from_small<MONT>(pd[t]);
+                for (int t = 0; t < ring::D; ++t) {
+                    const int bit = (int)((mag[t] >> k) & 1u);
+                    c[t] = gl::from_small<MONT>(d[t] < 0 ? -bit : bit);  // digit k base 2 = sign * bit_k(|c|)
+                }
                 row_put(otile, threadIdx.x, c);
             }
             rows_out<PLAIN_UNITS>(otile, planes_coeff + elem0 * ring::D, nrows);
         }
         if (planes_f || planes_fx) {
-            if (active) xf::crt24_small<MONT>(pd, c);
+            if (active) {
+#pragma unroll
+                for (int cl = 0; cl < 3; ++cl) {
+                    u32 m = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) m |= ((mag[3 * i + cl] >> k) & 1u) << i;
+                    const ulonglong2 *rp = s_lut + cl * 1024 + (m & ~sgn[cl]);
+                    const ulonglong2 *rn = s_lut + cl * 1024 + (m & sgn[cl]);
+#pragma unroll
+                    for (int h = 0; h < ring::NSLOT / 2; ++h) {
+                        const ulonglong2 a = rp[h * 256], b = rn[h * 256];
+                        c[plane_word(cl, 2 * h)] = gl::sub(a.x, b.x);
+                        c[plane_word(cl, 2 * h + 1)] = gl::sub(a.y, b.y);
+                    }
+                }
+            }
             if (planes_f) {
                 if (active) row_put(otile, threadIdx.x, c);
                 rows_out<PLAIN_UNITS>(otile, planes_f + elem0 * ring::D, nrows);
@@ -418,12 +496,98 @@ planes_kernel(const int16_t *__restrict__ f16, u64 n, int K, u64 *__restrict__ p
     }
 }
 
-void launch_planes(const int16_t *f16, u64 n, int K, bool mont, u64 *planes_f, u64 *planes_fx, u64 *planes_coeff,
-                   cudaStream_t stream) {
+// The common case: only the extended rows.  Persistent blocks (3 per SM, the table is copied once per block) stride over
+// the work items (block of 256 elements, plane); consecutive blocks write neighbouring rows of the same plane.
+constexpr int PLANE_FX_THREADS = 256;
+__global__ void __launch_bounds__(PLANE_FX_THREADS, 3)
+planes_fx_kernel(const int16_t *__restrict__ f16, u64 n, int K, const u64 *__restrict__ lut, u64 *__restrict__ planes_fx) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    extern __shared__ __align__(16) unsigned char planes_smem[];
+    ulonglong2 *s_lut = reinterpret_cast<ulonglong2 *>(planes_smem);
+    {
+        const ulonglong2 *g = reinterpret_cast<const ulonglong2 *>(lut);
+        for (int u = threadIdx.x; u < LUT_WORDS / 2; u += PLANE_FX_THREADS) s_lut[u] = g[u];
+    }
+    __syncthreads();
+    const u64 neb = (n + PLANE_FX_THREADS - 1) / PLANE_FX_THREADS;
+    for (u64 item = blockIdx.x; item < neb * (u64)K; item += gridDim.x) {
+        const int k = (int)(item / neb);
+        const u64 e = (item - (u64)k * neb) * PLANE_FX_THREADS + threadIdx.x;
+        if (e >= n) continue;
+        int d[ring::D];
+        load_i16x24(f16 + e * ring::D, d);
+        u32 sgn[3] = {0, 0, 0};
+        u32 mag[ring::D];
+#pragma unroll
+        for (int t = 0; t < ring::D; ++t) {
+            mag[t] = (u32)(d[t] < 0 ? -d[t] : d[t]);
+            sgn[t % 3] |= (d[t] < 0 ? 1u : 0u) << (t / 3);
+        }
+        const ulonglong2 *rp[3], *rn[3];
+#pragma unroll
+        for (int cl = 0; cl < 3; ++cl) {
+            u32 m = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m |= ((mag[3 * i + cl] >> k) & 1u) << i;
+            rp[cl] = s_lut + cl * 1024 + (m & ~sgn[cl]);
+            rn[cl] = s_lut + cl * 1024 + (m & sgn[cl]);
+        }
+        u64 *o = planes_fx + ((u64)k * n + e) * FX_WORDS;
+#pragma unroll
+        for (int h = 0; h < ring::NSLOT / 2; ++h) {
+            // slots 2h and 2h+1: word (c, s) of the slot comes from class c for s < 4, classes 1 and 2 swapped above
+            u64 a[3], b[3];
+#pragma unroll
+            for (int cl = 0; cl < 3; ++cl) {
+                const ulonglong2 p = rp[cl][h * 256], q = rn[cl][h * 256];
+                const int w = plane_word(cl, 2 * h) - 6 * h;  // component this class lands in (same for both slots of the pair)
+                a[w] = gl::sub(p.x, q.x);
+                b[w] = gl::sub(p.y, q.y);
+            }
+            u64 p0, p1, p2, q0, q1, q2;
+            gl::toom_eval(a[0], a[1], a[2], p0, p1, p2);
+            gl::toom_eval(b[0], b[1], b[2], q0, q1, q2);
+            st256(o + h * 12, a[0], a[1], a[2], p0);
+            st256(o + h * 12 + 4, p1, p2, b[0], b[1]);
+            st256(o + h * 12 + 8, b[2], q0, q1, q2);
+        }
+    }
+}
+
+void launch_planes(const int16_t *f16, u64 n, int K, bool mont, const u64 *lut, u64 *planes_f, u64 *planes_fx,
+                   u64 *planes_coeff, cudaStream_t stream) {
     if (!n) return;
+    if (!planes_f && !planes_coeff) {
+        if (!planes_fx) return;
+        static int sm_count_on[64] = {};  // 0 = not asked yet; the attribute is set at the same time
+        int dev = 0;
+        cudaGetDevice(&dev);
+        int &sms = sm_count_on[dev & 63];
+        if (!sms) {
+            cudaFuncSetAttribute(planes_fx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_WORDS * 8);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (sms <= 0) sms = 148;
+        }
+        const u64 items = ((n + PLANE_FX_THREADS - 1) / PLANE_FX_THREADS) * (u64)K;
+        const unsigned grid = (unsigned)min(items, (u64)sms * 3);
+        planes_fx_kernel<<<grid, PLANE_FX_THREADS, LUT_WORDS * 8, stream>>>(f16, n, K, lut, planes_fx);
+        return;
+    }
     unsigned grid = (unsigned)((n + PLANE_THREADS - 1) / PLANE_THREADS);
-    if (mont) planes_kernel<true><<<grid, PLANE_THREADS, 0, stream>>>(f16, n, K, planes_f, planes_fx, planes_coeff);
-    else planes_kernel<false><<<grid, PLANE_THREADS, 0, stream>>>(f16, n, K, planes_f, planes_fx, planes_coeff);
+    const bool plain = planes_f || planes_coeff;
+    const size_t smem = (size_t)LUT_WORDS * 8 + (plain ? (size_t)PLANE_THREADS * (PLAIN_UNITS + 1) * 16 : 0);
+    static bool attr_set_on[64] = {};  // per device, as for mac_kernel
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool &attr_set = attr_set_on[dev & 63];
+    if (!attr_set) {
+        const int cap = LUT_WORDS * 8 + PLANE_THREADS * (PLAIN_UNITS + 1) * 16;
+        cudaFuncSetAttribute(planes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        cudaFuncSetAttribute(planes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        attr_set = true;
+    }
+    if (mont) planes_kernel<true><<<grid, PLANE_THREADS, smem, stream>>>(f16, n, K, lut, planes_f, planes_fx, planes_coeff);
+    else planes_kernel<false><<<grid, PLANE_THREADS, smem, stream>>>(f16, n, K, lut, planes_f, planes_fx, planes_coeff);
 }
 
 // ---- Witness::get_fhat (latticefold/src/arith.rs:273-297) from the resident digits ---------------------------------------------
