@@ -496,9 +496,12 @@ planes_kernel(const int16_t *__restrict__ f16, u64 n, int K, const u64 *__restri
     }
 }
 
-// The common case: only the extended rows.  Persistent blocks (3 per SM, the table is copied once per block) stride over
-// the work items (block of 256 elements, plane); consecutive blocks write neighbouring rows of the same plane.
+// The common case: only the extended rows.  One thread per (element, slot pair): the four lanes of an element write its
+// 384-byte row as four adjacent 96-byte pieces, so a warp's three 256-bit stores cover 3 KB without gaps (the mapping of
+// fext_kernel; one thread per row reaches 3.6 TB/s of stores, this one is bound by the table reads instead).  Persistent
+// blocks (3 per SM, the table is copied once per block) stride over the work items (64 elements, a third of the planes).
 constexpr int PLANE_FX_THREADS = 256;
+constexpr int PLANE_FX_ELEMS = PLANE_FX_THREADS / 4;
 __global__ void __launch_bounds__(PLANE_FX_THREADS, 3)
 planes_fx_kernel(const int16_t *__restrict__ f16, u64 n, int K, const u64 *__restrict__ lut, u64 *__restrict__ planes_fx) {
     asm volatile("griddepcontrol.launch_dependents;");
@@ -509,10 +512,12 @@ planes_fx_kernel(const int16_t *__restrict__ f16, u64 n, int K, const u64 *__res
         for (int u = threadIdx.x; u < LUT_WORDS / 2; u += PLANE_FX_THREADS) s_lut[u] = g[u];
     }
     __syncthreads();
-    const u64 neb = (n + PLANE_FX_THREADS - 1) / PLANE_FX_THREADS;
-    for (u64 item = blockIdx.x; item < neb * (u64)K; item += gridDim.x) {
-        const int k = (int)(item / neb);
-        const u64 e = (item - (u64)k * neb) * PLANE_FX_THREADS + threadIdx.x;
+    const u64 neb = (n + PLANE_FX_ELEMS - 1) / PLANE_FX_ELEMS;
+    const int ppi = (K + 2) / 3, ng = (K + ppi - 1) / ppi;  // planes per item, plane groups
+    const u32 h = threadIdx.x & 3;                          // slot pair (slots 2h, 2h+1)
+    for (u64 item = blockIdx.x; item < neb * (u64)ng; item += gridDim.x) {
+        const int g = (int)(item / neb);
+        const u64 e = (item - (u64)g * neb) * PLANE_FX_ELEMS + (threadIdx.x >> 2);
         if (e >= n) continue;
         int d[ring::D];
         load_i16x24(f16 + e * ring::D, d);
@@ -523,33 +528,37 @@ planes_fx_kernel(const int16_t *__restrict__ f16, u64 n, int K, const u64 *__res
             mag[t] = (u32)(d[t] < 0 ? -d[t] : d[t]);
             sgn[t % 3] |= (d[t] < 0 ? 1u : 0u) << (t / 3);
         }
-        const ulonglong2 *rp[3], *rn[3];
-#pragma unroll
-        for (int cl = 0; cl < 3; ++cl) {
-            u32 m = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) m |= ((mag[3 * i + cl] >> k) & 1u) << i;
-            rp[cl] = s_lut + cl * 1024 + (m & ~sgn[cl]);
-            rn[cl] = s_lut + cl * 1024 + (m & sgn[cl]);
-        }
-        u64 *o = planes_fx + ((u64)k * n + e) * FX_WORDS;
-#pragma unroll
-        for (int h = 0; h < ring::NSLOT / 2; ++h) {
-            // slots 2h and 2h+1: word (c, s) of the slot comes from class c for s < 4, classes 1 and 2 swapped above
+        const int k1 = min(K, (g + 1) * ppi);
+        for (int k = g * ppi; k < k1; ++k) {
+            // words of the slot: class c lands in component c for slots 0..3, classes 1 and 2 swap in slots 4..7 (plane_word)
             u64 a[3], b[3];
 #pragma unroll
             for (int cl = 0; cl < 3; ++cl) {
-                const ulonglong2 p = rp[cl][h * 256], q = rn[cl][h * 256];
-                const int w = plane_word(cl, 2 * h) - 6 * h;  // component this class lands in (same for both slots of the pair)
-                a[w] = gl::sub(p.x, q.x);
-                b[w] = gl::sub(p.y, q.y);
+                u32 m = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) m |= ((mag[3 * i + cl] >> k) & 1u) << i;
+                const ulonglong2 p = s_lut[cl * 1024 + h * 256 + (m & ~sgn[cl])];
+                const ulonglong2 q = s_lut[cl * 1024 + h * 256 + (m & sgn[cl])];
+                const u64 x = gl::sub(p.x, q.x), y = gl::sub(p.y, q.y);
+                if (cl == 0) {
+                    a[0] = x; b[0] = y;
+                } else {
+                    const bool swap = h >= 2;
+                    if (cl == 1) { a[1] = x; b[1] = y; }
+                    else {  // cl == 2: after this both classes are known, put them in place
+                        const u64 a1 = a[1], b1 = b[1];
+                        a[1] = swap ? x : a1; b[1] = swap ? y : b1;
+                        a[2] = swap ? a1 : x; b[2] = swap ? b1 : y;
+                    }
+                }
             }
             u64 p0, p1, p2, q0, q1, q2;
             gl::toom_eval(a[0], a[1], a[2], p0, p1, p2);
             gl::toom_eval(b[0], b[1], b[2], q0, q1, q2);
-            st256(o + h * 12, a[0], a[1], a[2], p0);
-            st256(o + h * 12 + 4, p1, p2, b[0], b[1]);
-            st256(o + h * 12 + 8, b[2], q0, q1, q2);
+            u64 *o = planes_fx + ((u64)k * n + e) * FX_WORDS + h * 12;
+            st256(o, a[0], a[1], a[2], p0);
+            st256(o + 4, p1, p2, b[0], b[1]);
+            st256(o + 8, b[2], q0, q1, q2);
         }
     }
 }
@@ -568,7 +577,7 @@ void launch_planes(const int16_t *f16, u64 n, int K, bool mont, const u64 *lut, 
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             if (sms <= 0) sms = 148;
         }
-        const u64 items = ((n + PLANE_FX_THREADS - 1) / PLANE_FX_THREADS) * (u64)K;
+        const u64 items = ((n + PLANE_FX_ELEMS - 1) / PLANE_FX_ELEMS) * 3;
         const unsigned grid = (unsigned)min(items, (u64)sms * 3);
         planes_fx_kernel<<<grid, PLANE_FX_THREADS, LUT_WORDS * 8, stream>>>(f16, n, K, lut, planes_fx);
         return;
