@@ -47,9 +47,12 @@ constexpr int FX = 48;  // u64 per element in the extended witness layout (8 slo
 // Compile-time geometry per row-group count RG (rows per block RB = 4 RG <= 32).
 __host__ __device__ constexpr int geo_cg(int rg) { return rg == 1 ? 8 : rg == 2 ? 4 : rg <= 4 ? 2 : 1; }
 __host__ __device__ constexpr int geo_tj(int rg) { return ((LAT_TJ_BYTES / (4 * rg)) / geo_cg(rg)) * geo_cg(rg) < geo_cg(rg) ? geo_cg(rg) : ((LAT_TJ_BYTES / (4 * rg)) / geo_cg(rg)) * geo_cg(rg); }
-// the 5-word (Toom-3) matrix: a column is 5/3 as many bytes, so fewer columns per tile keep a tile at 38-48 KB
+// the 5-word (Toom-3) matrix: the same columns per tile, i.e. 80 KB tiles and two stages.  The several-witness kernels
+// run one CTA of 8 warps per SM, all of which reach a tile boundary together (barrier poll, release atomic, refill), and
+// that boundary costs more than a shallower ring: 4 / 6 / 8 columns per tile at kappa = 32 gave 1.09 / 1.03 / 1.01 ms for
+// 14 commits, and 2 stages ran as fast as 4 at every size (tools/ab_mac.py).
 #ifndef LAT_TJ5_BYTES
-#define LAT_TJ5_BYTES 153
+#define LAT_TJ5_BYTES 256
 #endif
 __host__ __device__ constexpr int geo_tj5(int rg) { return ((LAT_TJ5_BYTES / (4 * rg)) / geo_cg(rg)) * geo_cg(rg) < geo_cg(rg) ? geo_cg(rg) : ((LAT_TJ5_BYTES / (4 * rg)) / geo_cg(rg)) * geo_cg(rg); }
 

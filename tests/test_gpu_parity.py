@@ -201,6 +201,47 @@ def test_commit_batch_and_errors():
     s2.close()
 
 
+@pytest.mark.parametrize("kappa", [1, 4, 9, 12, 17, 20, 28, 32, 33])
+@pytest.mark.parametrize("mont", [False, True])
+def test_commit_batch_toom_form_every_split(kappa, mont):
+    # launches with several witnesses run in Toom-3 form on the 5-word matrix (csrc/goldilocks.cuh ToomAcc): 4, 2 or 1
+    # witnesses per thread, counts above 4 split into a multiple of 4 and the rest -- every split shape, every row-group
+    # geometry (kappa 1 .. 33), a ragged last tile, both representations
+    n = 131 if kappa != 32 else 517
+    A = CO.fill_uniform((kappa, n, 24), 300 + kappa)
+    scheme = make_scheme(A, mont)
+    for count in (2, 3, 4, 5, 6, 7, 8, 9, 12, 15):
+        fs = CO.fill_uniform((count, n, 24), 900 + count)
+        cms = scheme.commit_ntt_batch(maybe_mont(fs, mont))
+        for k in range(count):
+            assert np.array_equal(unmont(cms[k].as_ref(), mont), CO.commit(A, fs[k])), (kappa, count, k)
+    scheme.close()
+
+
+def test_commit_batch_toom_form_extreme_values_and_reupload():
+    # q-1 everywhere: the largest point values (a(2) = 7 (q-1) mod q, a(-1) = q-1) and the largest lazy sums; then a row
+    # is replaced and the 5-word copy of the matrix must follow
+    kappa, n, count = 32, 2048, 6
+    A = np.full((kappa, n, 24), Q - 1, dtype=np.uint64)
+    fs = np.full((count, n, 24), Q - 1, dtype=np.uint64)
+    fs[1] = 0
+    fs[2, ::2] = 1
+    scheme = make_scheme(A)
+    cms = scheme.commit_ntt_batch(fs)
+    for k in range(count):
+        assert np.array_equal(cms[k].as_ref(), CO.commit(A, fs[k])), k
+    A2 = A.copy()
+    A2[5] = CO.fill_uniform((n, 24), 77)
+    A2[31] = 0
+    scheme.upload_rows(5, A2[5:6])
+    scheme.upload_rows(31, A2[31:32])
+    assert np.array_equal(scheme.commit(fs[0]).as_ref(), CO.commit(A2, fs[0]))  # single witness: the 3-word matrix
+    cms = scheme.commit_ntt_batch(fs)
+    for k in range(count):
+        assert np.array_equal(cms[k].as_ref(), CO.commit(A2, fs[k])), k
+    scheme.close()
+
+
 def test_upload_column_shard_with_stride():
     # a column shard of a wider host matrix: row_stride = full width
     kappa, n_total, lo, hi = 5, 100, 30, 71
