@@ -47,14 +47,20 @@ constexpr int FX = 48;  // u64 per element in the extended witness layout (8 slo
 // Compile-time geometry per row-group count RG (rows per block RB = 4 RG <= 32).
 __host__ __device__ constexpr int geo_cg(int rg) { return rg == 1 ? 8 : rg == 2 ? 4 : rg <= 4 ? 2 : 1; }
 __host__ __device__ constexpr int geo_tj(int rg) { return ((LAT_TJ_BYTES / (4 * rg)) / geo_cg(rg)) * geo_cg(rg) < geo_cg(rg) ? geo_cg(rg) : ((LAT_TJ_BYTES / (4 * rg)) / geo_cg(rg)) * geo_cg(rg); }
-// the 5-word (Toom-3) matrix: the same columns per tile, i.e. 80 KB tiles and two stages.  The several-witness kernels
-// run one CTA of 8 warps per SM, all of which reach a tile boundary together (barrier poll, release atomic, refill), and
-// that boundary costs more than a shallower ring: 4 / 6 / 8 columns per tile at kappa = 32 gave 1.09 / 1.03 / 1.01 ms for
-// 14 commits, and 2 stages ran as fast as 4 at every size (tools/ab_mac.py).
-#ifndef LAT_TJ5_BYTES
-#define LAT_TJ5_BYTES 256
+// the 5-word (Toom-3) matrix: as many columns per tile as let TWO stages of (tile + the witness rows of 4 witnesses) fit
+// the SM's shared memory -- 8 columns = 80 KB tiles at kappa = 32.  The several-witness kernels run one CTA of 8 warps per
+// SM, all of which reach a tile boundary together (barrier poll, release atomic, refill), and that boundary costs more
+// than a shallower ring: 4 / 6 / 8 columns per tile at kappa = 32 gave 1.09 / 1.03 / 1.01 ms for 14 commits, and 2 stages
+// ran as fast as 4 at every size (tools/ab_mac.py).
+#ifndef LAT_TJ5_STAGE_BYTES
+#define LAT_TJ5_STAGE_BYTES 98304
 #endif
-__host__ __device__ constexpr int geo_tj5(int rg) { return ((LAT_TJ5_BYTES / (4 * rg)) / geo_cg(rg)) * geo_cg(rg) < geo_cg(rg) ? geo_cg(rg) : ((LAT_TJ5_BYTES / (4 * rg)) / geo_cg(rg)) * geo_cg(rg); }
+__host__ __device__ constexpr int geo_tj5(int rg) {
+    // bytes per column of a stage: 5 words x 4 rg rows x 8 slots x 8 B of matrix + 4 witnesses x 384 B
+    return (LAT_TJ5_STAGE_BYTES / (1280 * rg + 1536)) / geo_cg(rg) * geo_cg(rg) < geo_cg(rg)
+               ? geo_cg(rg)
+               : (LAT_TJ5_STAGE_BYTES / (1280 * rg + 1536)) / geo_cg(rg) * geo_cg(rg);
+}
 
 MatLayout make_layout(uint32_t kappa, u64 n, bool toom) {
     MatLayout l{};
