@@ -20,6 +20,11 @@
 //    (Karatsuba) = 24 IMAD.WIDE.U32; a single special-form reduction per output at the end.  IMAD.WIDE.U32 runs at
 //    31.5 /clk/SM (measured), so this multiply count, not HBM, is what the batched (PT > 1) case is bound by.
 //    No tensor cores: this is exact 64-bit modular integer work.
+//  * Launches with SEVERAL witnesses (the K-1 planes of a decomposition, commit batches) run in Toom-3 form instead
+//    (TOOM = true; gl::ToomAcc): both operands evaluated at 0, infinity, 1, -1, 2 -- the witness rows by their producer,
+//    the matrix as a second device copy with 5 words per entry (derive_toom_kernel) -- so one Fq3 MAC is 5 products =
+//    20 IMAD.WIDE.U32 and no pre-additions, interpolated once per output.  4 witnesses per thread (250 registers), one
+//    CTA per SM, two stages of 80 KB tiles.  The single witness stays Karatsuba: it is bound by the matrix bytes.
 //  * Programmatic dependent launch: the prologue and the first matrix tiles do not wait for the kernel that
 //    produces the witness, and the next call's kernels may start while this one drains.
 //  * Cross-CTA sum inside the same kernel: canonical partials are added as 32-bit halves with 64-bit REDs into a
