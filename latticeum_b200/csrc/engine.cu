@@ -656,8 +656,10 @@ static int device_view(void *host, void **dev) {
 
 // Host-buffer w (w_ccs, or coefficients when in_coeff) -> resident digits (+ optional u64 outputs on the device) and,
 // with want_cm, the commitment in cm_dev.  Enqueues only; the caller copies results out and calls finish().
+// input_staged: the caller has already copied w into h->in (and made h->stream wait for that copy); w is not touched.
 static int witness_enqueue(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool in_coeff, u64 *d_fc, u64 *d_f, u64 *cm_dev,
-                           bool early_downloads = false, const lat::MacReport &report = lat::MacReport()) {
+                           bool early_downloads = false, const lat::MacReport &report = lat::MacReport(),
+                           bool input_staged = false) {
     int st;
     const size_t in_bytes = w_len * ELEM_BYTES;
     if ((st = h->in.ensure(in_bytes))) return st;
@@ -668,7 +670,7 @@ static int witness_enqueue(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool
     // Pinned (page-locked) host memory is mapped into the device address space: the witness kernel then reads w_ccs
     // straight over PCIe -- no staging copy, no extra launch, the 8-lane loads are contiguous 768-byte runs per warp.
     const u64 *w_mapped = nullptr;
-    {
+    if (!input_staged) {
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, w) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
             w_mapped = static_cast<const u64 *>(attr.devicePointer);
@@ -676,7 +678,12 @@ static int witness_enqueue(lat_ajtai *h, const uint64_t *w, uint64_t w_len, bool
             cudaGetLastError();  // pageable memory: not an error, take the copy path
     }
     u64 nchunks = w_len >= 4096 ? 4 : 1;
-    if (w_mapped) {
+    if (input_staged) {
+        nchunks = 0;
+        lat::launch_witness(h->in.as<u64>(), w_len, (int)h->log2_B, (int)h->L, h->mont, in_coeff, h->f16.as<int16_t>(), d_fc, d_f,
+                            d_fx, h->flag.as<int>(), h->stream);
+        CK(cudaGetLastError());
+    } else if (w_mapped) {
         nchunks = 0;
         static const bool no_stage = getenv("LAT_NO_STAGE_INPUT") != nullptr;
         const bool stage = !no_stage && (reinterpret_cast<uintptr_t>(w_mapped) & 15) == 0;  // bulk copies want 16-byte alignment
@@ -1082,18 +1089,28 @@ int lat_ajtai_fold_step_begin(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_le
         (st = h->cms_side[1].ensure(side_bytes)))
         return st;
     if (cm_acc) CK(cudaMemcpyAsync(h->cm_acc.p, cm_acc, cm_bytes, cudaMemcpyHostToDevice, h->stream));
-    // the step witness and its commitment (ZKVM/main.rs:348-367)
-    if ((st = witness_enqueue(h, w_ccs, w_len, false, nullptr, nullptr, h->cm_step.as<u64>(), f_coeff16 != nullptr))) return st;
-    CK(cudaMemcpyAsync(cm, h->cm_step.p, cm_bytes, cudaMemcpyDeviceToHost, h->stream));
-    if (f_coeff16)  // on copy_stream, beside the 29 matrix-vector products (the digits are not modified by them)
-        CK(cudaMemcpyAsync(f_coeff16, h->f16.p, h->n * LAT_RING_DEGREE * sizeof(int16_t), cudaMemcpyDeviceToHost, h->copy_stream));
-    // side 1: the step witness (lin_cm_i, w_i); side 0: the accumulator (acc, w_acc)      zk_latticefold.rs:60-71
+    // The accumulator's side does not depend on this step's witness: its 15 planes and 14 commits go first, and w_ccs
+    // comes up on the copy engine underneath them (every call ends in finish(), so h->in is free and copy_stream idle).
+    if ((st = h->in.ensure(w_len * ELEM_BYTES))) return st;
+    CK(cudaEventRecord(h->work_done, h->stream));  // whatever the caller still has in flight on the handle's stream goes first
+    CK(cudaStreamWaitEvent(h->copy_stream, h->work_done, 0));
+    CK(cudaMemcpyAsync(h->in.p, w_ccs, w_len * ELEM_BYTES, cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaEventRecord(h->copy_done[0], h->copy_stream));
+    // side 0: the accumulator (acc, w_acc); side 1: the step witness (lin_cm_i, w_i)      zk_latticefold.rs:60-71
     const int side_before = h->cur_side;
-    h->cur_side = 1;
-    st = planes_core(h, h->cm_step.as<u64>(), nullptr, nullptr, h->cms_side[1].as<u64>(), h->f16.as<int16_t>());
+    h->cur_side = 0;
+    st = planes_core(h, h->cm_acc.as<u64>(), nullptr, nullptr, h->cms_side[0].as<u64>(), h->f16_acc.as<int16_t>());
     if (!st) {
-        h->cur_side = 0;
-        st = planes_core(h, h->cm_acc.as<u64>(), nullptr, nullptr, h->cms_side[0].as<u64>(), h->f16_acc.as<int16_t>());
+        // the step witness and its commitment (ZKVM/main.rs:348-367)
+        CK(cudaStreamWaitEvent(h->stream, h->copy_done[0], 0));
+        st = witness_enqueue(h, w_ccs, w_len, false, nullptr, nullptr, h->cm_step.as<u64>(), f_coeff16 != nullptr, lat::MacReport(), true);
+    }
+    if (!st) {
+        CK(cudaMemcpyAsync(cm, h->cm_step.p, cm_bytes, cudaMemcpyDeviceToHost, h->stream));
+        if (f_coeff16)  // on copy_stream, beside the 14 matrix-vector products of side 1 (the digits are not modified by them)
+            CK(cudaMemcpyAsync(f_coeff16, h->f16.p, h->n * LAT_RING_DEGREE * sizeof(int16_t), cudaMemcpyDeviceToHost, h->copy_stream));
+        h->cur_side = 1;
+        st = planes_core(h, h->cm_step.as<u64>(), nullptr, nullptr, h->cms_side[1].as<u64>(), h->f16.as<int16_t>());
     }
     h->cur_side = side_before;
     if (st) return st;
