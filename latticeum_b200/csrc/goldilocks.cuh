@@ -224,7 +224,8 @@ __device__ __forceinline__ u64 from_small(int d) {
 // plus half an IADD3.X (two carries are absorbed per IADD3.X) -- checked in SASS; keeping the accumulator a
 // 64-bit PTX register is what avoids per-iteration IMAD.MOV copies of loop-carried halves.
 // IMAD.WIDE.U32 issues at half the IMAD rate on sm_100a (measured 31.5 /clk/SM, tools/imad_peak.cu), so the
-// multiply count is what bounds the MAC: hence Karatsuba in Fq3 below (6 base products instead of 9).
+// multiply count is what bounds the MAC: hence Karatsuba in Fq3 below (6 base products instead of 9) for the single
+// witness, and Toom-3 (5) where several witnesses share a matrix entry.
 // ---------------------------------------------------------------------------------------------------------
 struct Col {
     u64 acc;
@@ -320,30 +321,6 @@ __device__ __forceinline__ void mac65(WideAcc &A, u64 s, u32 c, u64 y) {
 #endif
 }
 
-// Matrix-side Karatsuba pre-addition folded back to 64 bits: a + b = s + c * 2^64 and 2^64 = 2^32 - 1 (mod q), so
-// add c * (2^32 - 1) as (lo - c, hi + c - borrow).  a, b < q makes the folded value fit 64 bits (s <= 2^64 - 2^33 when
-// c = 1); the result is SOME representative of (a + b) mod q, which is all a lazily reduced product needs.  Six
-// carry-chain instructions, shared by every witness that multiplies the same matrix entry (mac65 above costs five
-// per witness on top of add65).
-__device__ __forceinline__ u64 add_fold(u64 a, u64 b) {
-    u64 s;
-    asm("{\n\t"
-        ".reg .u32 al, ah, bl, bh, c;\n\t"
-        "mov.b64 {al, ah}, %1;\n\t"
-        "mov.b64 {bl, bh}, %2;\n\t"
-        "add.cc.u32 al, al, bl;\n\t"
-        "addc.cc.u32 ah, ah, bh;\n\t"
-        "addc.u32 c, 0, 0;\n\t"
-        "sub.cc.u32 al, al, c;\n\t"
-        "subc.u32 ah, ah, 0;\n\t"
-        "add.u32 ah, ah, c;\n\t"
-        "mov.b64 %0, {al, ah};\n\t"
-        "}"
-        : "=l"(s)
-        : "l"(a), "l"(b));
-    return s;
-}
-
 // Accumulators of one Fq3 output, Karatsuba form: for x = (x0,x1,x2), y = (y0,y1,y2) in Fq[u]/(u^3 - 2^40),
 // with x01 = x0+x1 etc.:
 //   P0 = sum x0 y0, P1 = sum x1 y1, P2 = sum x2 y2, P01 = sum x01 y01, P02 = sum x02 y02, P12 = sum x12 y12
@@ -367,16 +344,6 @@ struct Fq3Acc {
         mac65(p01, s01, k01, b01);
         mac65(p02, s02, k02, b02);
         mac65(p12, s12, k12, b12);
-    }
-    // the same with the three matrix-side sums already folded to 64 bits (shared by several accumulators)
-    __device__ __forceinline__ void mac_presummed(u64 a0, u64 a1, u64 a2, u64 a01, u64 a02, u64 a12, u64 b0, u64 b1, u64 b2,
-                                                  u64 b01, u64 b02, u64 b12) {
-        p0.mac(a0, b0);
-        p1.mac(a1, b1);
-        p2.mac(a2, b2);
-        p01.mac(a01, b01);
-        p02.mac(a02, b02);
-        p12.mac(a12, b12);
     }
     __device__ __forceinline__ void finish(u64 &c0, u64 &c1, u64 &c2) const {
         u64 r0 = p0.reduce(), r1 = p1.reduce(), r2 = p2.reduce();

@@ -11,9 +11,8 @@
 //    last warp to release a stage issues its refill (no producer warp: a 9th warp halves the occupancy).
 //  * The witness side comes in the "extended" layout [element][slot][6] = (f0, f1, f2, f0+f1, f0+f2, f1+f2): the
 //    Karatsuba pre-additions of the witness are done once by whoever produces it (the CRT kernels, or fext_kernel
-//    for a caller-supplied witness), not once per matrix row.  The matrix-side pre-additions are 3 lazy adds per
-//    thread per column (exact 65-bit sums for one witness; folded to 64 bits once per entry when several
-//    witnesses share it).
+//    for a caller-supplied witness), not once per matrix row.  The matrix-side pre-additions are 3 exact 65-bit sums
+//    per thread per column.
 //  * Split-K over columns: every CTA owns a contiguous range of tiles and keeps, per thread, the UNREDUCED
 //    accumulators of one output (row, slot) for PT witnesses ("planes"): 6 sums x 3 columns x (64+32) bits
 //    (gl::Fq3Acc).  One 64x64 product = 4 IMAD.WIDE.U32 with carry-out + 2 IADD3.X; 6 products per Fq3 MAC

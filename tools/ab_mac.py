@@ -1,4 +1,5 @@
-"""A/B timing of mac_kernel (default plan) for the library selected by LAT_LIB: planes = 1 and 14 at the zkVM shape.
+"""A/B timing of mac_kernel (default plan) for the library selected by LAT_LIB: planes = 1 (Karatsuba, 3-word matrix) and 14
+(Toom-3, 5-word matrix, 12 + 2 planes) at the zkVM shape.
     for v in a b; do LAT_LIB=latticeum_b200/lib/variants/$v/liblattice_ajtai.so python tools/ab_mac.py; done"""
 import os
 import sys
@@ -31,5 +32,5 @@ for planes in (1, 14):
         eng.commit_ntt(f, cm)
     s, c = eng.mac_profile()
     eng.set_profiling(False)
-    res.append(f"planes={planes}: {s / c * 1e3:8.1f} us")
+    res.append(f"planes={planes}: {s / 30 * 1e3:8.1f} us per call in {c // 30} launch(es)")  # 14 planes = 12 + 2: two launches
 print((os.environ.get("LAT_LIB") or "x/default/x").split("/")[-2], " ".join(res), flush=True)
