@@ -1130,17 +1130,36 @@ int lat_ajtai_fold_step_finish(lat_ajtai *h, const uint64_t *rho, int16_t *f0_co
     const size_t n_bytes = h->n * ELEM_BYTES, rho_bytes = (size_t)2 * h->K * ELEM_BYTES, cm_bytes = (size_t)h->kappa * ELEM_BYTES;
     if ((st = h->rho.ensure(rho_bytes)) || (st = h->f0.ensure(n_bytes)) || (st = h->in.ensure(n_bytes))) return st;
     CK(cudaMemcpyAsync(h->rho.p, rho, rho_bytes, cudaMemcpyHostToDevice, h->stream));
-    // f_0 = sum rho_i f_i (folding.rs:258-268), f_0 coefficients (arith.rs:299-313)
-    if ((st = lat_ajtai_fold_witness_dev(h, h->rho.as<uint64_t>(), h->f0.as<uint64_t>(), h->in.as<uint64_t>()))) return st;
+    if (!h->side_ready[0] || !h->side_ready[1]) return fail(LAT_E_INVALID_ARGUMENT, "both sides must be decomposed first");
+    if ((st = h->f16_acc.ensure(h->n * LAT_RING_DEGREE * sizeof(int16_t)))) return st;
+    // f_0 = sum rho_i f_i (folding.rs:258-268), its coefficients (arith.rs:299-313), and those packed as the next
+    // accumulator (they must stay below 2^K, the protocol's norm bound) -- in four ranges of elements when the caller wants
+    // the digits back, so that the 4.7 MB download of a range runs under the fold of the next one
+    {
+        const u64 *sides[2] = {h->planes_fx[0].as<u64>(), h->planes_fx[1].as<u64>()};
+        const int nch = (f0_coeff16 && h->n >= 4096) ? 4 : 1;
+        for (int c = 0; c < nch; ++c) {
+            const u64 e0 = h->n * c / nch, cnt = h->n * (c + 1) / nch - e0;
+            lat::launch_fold(sides, 2, (int)h->K, h->n, h->rho.as<u64>(), h->mont, h->f0.as<u64>(), h->stream, e0, cnt);
+            lat::launch_icrt(h->f0.as<u64>() + e0 * LAT_RING_DEGREE, h->in.as<u64>() + e0 * LAT_RING_DEGREE, cnt, h->stream);
+            lat::launch_pack_coeff(h->in.as<u64>() + e0 * LAT_RING_DEGREE, cnt, h->mont, (int)h->K,
+                                   h->f16_acc.as<int16_t>() + e0 * LAT_RING_DEGREE, h->flag.as<int>(), h->stream);
+            CK(cudaGetLastError());
+            if (f0_coeff16) {
+                CK(cudaEventRecord(h->copy_done[c], h->stream));
+                CK(cudaStreamWaitEvent(h->copy_stream, h->copy_done[c], 0));
+                CK(cudaMemcpyAsync(f0_coeff16 + e0 * LAT_RING_DEGREE, h->f16_acc.as<int16_t>() + e0 * LAT_RING_DEGREE,
+                                   cnt * LAT_RING_DEGREE * sizeof(int16_t), cudaMemcpyDeviceToHost, h->copy_stream));
+                h->copy_stream_busy = true;
+            }
+        }
+        h->acc_ready = true;
+    }
     // cm_0 = sum rho_i cm_i (folding/utils.rs:466-472): the next step's accumulator commitment, kept resident
     lat::launch_lincomb(h->rho.as<u64>(), h->cms_side[0].as<u64>(), h->cms_side[1].as<u64>(), (int)h->K, h->kappa, h->mont,
                         h->cm_acc.as<u64>(), h->stream);
     CK(cudaGetLastError());
     h->cm_acc_ready = true;
-    // the folded witness becomes the accumulator: its coefficients must stay below 2^K (the protocol's norm bound)
-    if ((st = set_accumulator_dev(h, h->in.as<u64>()))) return st;
-    if (f0_coeff16)
-        CK(cudaMemcpyAsync(f0_coeff16, h->f16_acc.p, h->n * LAT_RING_DEGREE * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
     if (f0) CK(cudaMemcpyAsync(f0, h->f0.p, n_bytes, cudaMemcpyDeviceToHost, h->stream));
     if (cm0) CK(cudaMemcpyAsync(cm0, h->cm_acc.p, cm_bytes, cudaMemcpyDeviceToHost, h->stream));
     if (w_ccs0) {  // Witness::from_f rebuilds w_ccs = gadget_recompose(f_0) (arith.rs:305): n / L elements, CRT form

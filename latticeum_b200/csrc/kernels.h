@@ -127,8 +127,9 @@ void launch_y0(const u64 *cm, u64 *cms, uint32_t K, uint32_t kappa, cudaStream_t
 // f0[j] = sum_{i < nplanes} rho[i] (*) planes[i][j]  (slot-wise Fq3), planes given as `nsides` extended-layout
 // buffers of planes_per_side x n x 48 each (Toom-3 form, as planes_kernel writes them).  rho: nplanes x 24 in the
 // caller's representation.  f0: n x 24.
+// elem0 / count: fold only that range of elements (f0 is still the full n x 24 array; count = ~0 means "to the end").
 void launch_fold(const u64 *const *sides_fx, int nsides, int planes_per_side, u64 n, const u64 *rho, bool mont, u64 *f0,
-                 cudaStream_t stream);
+                 cudaStream_t stream, u64 elem0 = 0, u64 count = ~0ull);
 
 // out[i] = sum_{p < 2K} rho[p] (*) cms[p][i]  over the K commitments of side 0 followed by the K of side 1 (each
 // K x kappa x 24); the folded commitment cm_0 (LF/nifs/folding/utils.rs:466-472).  rho in the caller's representation.
