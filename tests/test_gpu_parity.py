@@ -770,6 +770,38 @@ def test_fold_step_begin_finish_vs_oracle(mont):
     scheme.close()
 
 
+def test_fold_step_finish_in_element_ranges_vs_oracle():
+    # from n = 4096 on, lat_ajtai_fold_step_finish folds, inverts and packs f_0 in four ranges of elements and sends each
+    # range's digits down while the next one folds; n = 5105 makes every range boundary ragged (not a multiple of 4, of
+    # the 32 elements of a fold block, or of the 64 of a planes block)
+    kappa, wl, mont = 4, 1021, True
+    n = wl * DP.L
+    A = CO.fill_uniform((kappa, n, 24), 260)
+    scheme = make_scheme(A, mont)
+    fs = LB.FoldStep(scheme)
+    rng = np.random.default_rng(261)
+    acc_fc = signed_to_fq(np.clip(np.rint(rng.normal(0.0, 350.0, size=(n, 24))), -(2**15 - 1), 2**15 - 1).astype(np.int64))
+    acc_cm = CO.commit(A, CO.crt(acc_fc))
+    fs.set_accumulator(maybe_mont(acc_fc, mont), LB.Commitment(maybe_mont(acc_cm, mont), mont))
+    for step in range(2):
+        w = CO.fill_uniform((wl, 24), 270 + step)
+        rho = CO.crt(signed_to_fq(rng.integers(-32, 32, size=(2 * DP.K, 24))))
+        e_fc, e_cm, e_ys0, e_ys1, e_f0, e_f0c, e_cm0 = oracle_fold_step(A, w, acc_fc, acc_cm, rho)
+        cm, ys0, ys1, d16 = fs.begin(maybe_mont(w, mont))
+        assert np.array_equal(unmont(cm.as_ref(), mont), e_cm)
+        assert np.array_equal(fq_to_signed(e_fc), d16.astype(np.int64))
+        for k in range(DP.K):
+            assert np.array_equal(unmont(ys0[k].as_ref(), mont), e_ys0[k]), (step, 0, k)
+            assert np.array_equal(unmont(ys1[k].as_ref(), mont), e_ys1[k]), (step, 1, k)
+        cm0, f0d, f0, w0 = fs.finish(maybe_mont(rho, mont), want_f0=True, want_w_ccs=True)
+        assert np.array_equal(unmont(f0, mont), e_f0)
+        assert np.array_equal(f0d.astype(np.int64), fq_to_signed(e_f0c))
+        assert np.array_equal(unmont(cm0.as_ref(), mont), e_cm0)
+        assert np.array_equal(unmont(w0, mont), CO.gadget_recompose_ntt(e_f0, DP.B, DP.L))
+        acc_fc, acc_cm = e_f0c, e_cm0
+    scheme.close()
+
+
 def test_witness_from_w_ccs_compact_vs_oracle():
     kappa, wl = 9, 777
     A = CO.fill_uniform((kappa, wl * DP.L, 24), 190)
