@@ -234,7 +234,7 @@ struct MacGeo {
     static constexpr u32 TILE_BYTES = TILE_ELEMS * 8;
     static constexpr u32 F_BYTES = TJ * FX * 8;  // per plane per tile
     static constexpr u32 STAGE_BYTES = TILE_BYTES + PT * F_BYTES;
-    static constexpr int MIN_CTAS = PT == 1 ? 2 : 1;
+    static constexpr int MIN_CTAS = (PT == 1 && !TOOM) ? 2 : 1;
 };
 
 #ifdef LAT_MAC_TRACE
@@ -476,7 +476,9 @@ MacPlan plan_mac(const MatLayout &lay, uint32_t planes, int sm_count) {
     // runs into the L2 -> SM port (about 44 GB/s per SM measured) before the multiply pipe is full
     m.pt = lay.nc != 5 ? 1 : planes % 4 == 0 ? 4 : planes % 2 == 0 ? 2 : 1;
     size_t stage_bytes = stage_bytes_for(m.pt, lay);
-    uint32_t occ_cap = (m.pt == 1) ? 2 : 1;  // = MacGeo::MIN_CTAS
+    // resident CTAs per SM the grid is sized for: two for the single-witness (3-word) kernel; the 5-word tiles leave room
+    // for one CTA only, whatever the number of witnesses per thread
+    uint32_t occ_cap = (m.pt == 1 && lay.nc != 5) ? 2 : 1;
     // as many stages as fit next to occ_cap resident CTAs (227 KB usable, 1 KB reserved per CTA), at most 6
     size_t per_cta = (227 * 1024) / occ_cap - SM_RESERVED_SMEM - 1024;  // 16 B of sync state per stage
     uint32_t stages = (uint32_t)(per_cta / stage_bytes);
