@@ -202,7 +202,14 @@ struct lat_ajtai {
     bool mac_was_last = false;           // snapshot of the above at the start of the current entry point
     DevBuf fcoeff64;     // f_coeff as u64 for host output
     DevBuf planes;       // K x n x 24 CRT-form planes (only when a caller wants them)
-    DevBuf planes_fx[2]; // K x n x 48 CRT-form planes, extended layout (MAC input, Toom-3 form), one buffer per fold side
+    // CRT-form planes of both fold sides, extended layout (MAC input, Toom-3 form), 2K x n x 48 in ONE buffer laid out
+    // [side 0: planes 1..K-1][side 1: planes 1..K-1][side 0: plane 0][side 1: plane 0]: the 2 (K-1) planes that get
+    // committed are contiguous, so a fold step commits them in one launch (lat_ajtai_fold_step_begin)
+    DevBuf planes_all;
+    size_t plane_words() const { return (size_t)n * lat::FX_WORDS; }
+    int ensure_planes() { return planes_all.ensure((size_t)2 * K * plane_words() * sizeof(u64)); }
+    u64 *planes_k1(int side) { return planes_all.as<u64>() + (size_t)side * (K - 1) * plane_words(); }
+    u64 *planes_k0(int side) { return planes_all.as<u64>() + ((size_t)2 * (K - 1) + side) * plane_words(); }
     DevBuf planes_lut;   // 48 KB subset-sum table of the planes' transform (planes_kernel), built at first use
     bool side_ready[2] = {false, false};
     int cur_side = 0;
@@ -474,7 +481,7 @@ void lat_ajtai_destroy(lat_ajtai *h) {
     cudaSetDevice(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     if (h->stream && h->stream != h->own_stream) cudaStreamSynchronize(h->stream);  // steps in flight write into our buffers
-    DevBuf *bufs[] = {&h->A, &h->A5, &h->planes_lut, &h->stage, &h->in, &h->f16, &h->f, &h->fx, &h->fcoeff64, &h->planes, &h->planes_fx[0], &h->planes_fx[1],
+    DevBuf *bufs[] = {&h->A, &h->A5, &h->planes_lut, &h->stage, &h->in, &h->f16, &h->f, &h->fx, &h->fcoeff64, &h->planes, &h->planes_all,
                       &h->rho, &h->f0, &h->planes_coeff, &h->cms, &h->cm_in, &h->ws, &h->flag, &h->fx_alt,
                       &h->f16_acc, &h->cms_side[0], &h->cms_side[1], &h->cm_step, &h->cm_acc};
     for (DevBuf *b : bufs) b->release();
@@ -899,28 +906,27 @@ int lat_ajtai_wait(lat_ajtai *h, uint64_t ticket) {
 
 // ---- decompose_witness + commit_witnesses ---------------------------------------------------------------------------
 // f16 already holds the coefficients; produce planes (to caller buffers or internal), K-1 commits and y_0.
+// planes_only: stop after the planes (the fold step commits both sides' planes in one launch of its own).
 static int planes_core(lat_ajtai *h, const u64 *cm_dev, u64 *planes_coeff_dev, u64 *planes_f_dev, u64 *cms_dev,
-                       const int16_t *src16 = nullptr) {
+                       const int16_t *src16 = nullptr, bool planes_only = false) {
     int st;
     if (!src16) src16 = h->f16.as<int16_t>();
-    u64 *pfx = nullptr;
-    {   // the extended-layout planes of this side stay resident for lat_ajtai_fold_witness
-        DevBuf &buf = h->planes_fx[h->cur_side];
-        if ((st = buf.ensure((size_t)h->K * h->n * lat::FX_WORDS * sizeof(u64)))) return st;
-        pfx = buf.as<u64>();
-        h->side_ready[h->cur_side] = true;
-    }
-    if (pfx || planes_f_dev || planes_coeff_dev) {
+    // the extended-layout planes of this side stay resident for lat_ajtai_fold_witness
+    if ((st = h->ensure_planes())) return st;
+    u64 *pfx = h->planes_k1(h->cur_side);
+    h->side_ready[h->cur_side] = true;
+    {
         if (!h->planes_lut.p) {  // once per handle: the subset-sum table of the planes' transform
             if ((st = h->planes_lut.ensure(lat::PLANES_LUT_WORDS * sizeof(u64)))) return st;
             lat::launch_planes_lut(h->mont, h->planes_lut.as<u64>(), h->stream);
         }
-        lat::launch_planes(src16, h->n, (int)h->K, h->mont, h->planes_lut.as<u64>(), planes_f_dev, pfx, planes_coeff_dev, h->stream);
+        lat::launch_planes(src16, h->n, (int)h->K, h->mont, h->planes_lut.as<u64>(), planes_f_dev, pfx, h->planes_k0(h->cur_side),
+                           planes_coeff_dev, h->stream);
         CK(cudaGetLastError());
     }
-    if (cms_dev) {
+    if (cms_dev && !planes_only) {
         if (h->K > 1) {
-            st = h->mac_fx(pfx + h->n * lat::FX_WORDS, h->n, h->K - 1, cms_dev + (size_t)h->kappa * LAT_RING_DEGREE,
+            st = h->mac_fx(pfx, h->n, h->K - 1, cms_dev + (size_t)h->kappa * LAT_RING_DEGREE,
                            lat::MacReport(), true);  // planes are in the Toom-3 form
             if (st) return st;
         }
@@ -1015,8 +1021,8 @@ int lat_ajtai_fold_witness_dev(lat_ajtai *h, const uint64_t *rho_dev, uint64_t *
         if ((st = h->f0.ensure(h->n * ELEM_BYTES))) return st;
         f0 = h->f0.as<u64>();
     }
-    const u64 *sides[2] = {h->planes_fx[0].as<u64>(), h->planes_fx[1].as<u64>()};
-    lat::launch_fold(sides, 2, (int)h->K, h->n, (const u64 *)rho_dev, h->mont, f0, h->stream);
+    const u64 *sides[2] = {h->planes_k1(0), h->planes_k1(1)}, *sides0[2] = {h->planes_k0(0), h->planes_k0(1)};
+    lat::launch_fold(sides, sides0, 2, (int)h->K, h->n, (const u64 *)rho_dev, h->mont, f0, h->stream);
     CK(cudaGetLastError());
     if (f0_coeff_dev) {
         lat::launch_icrt(f0, (u64 *)f0_coeff_dev, h->n, h->stream);
@@ -1089,8 +1095,11 @@ int lat_ajtai_fold_step_begin(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_le
         (st = h->cms_side[1].ensure(side_bytes)))
         return st;
     if (cm_acc) CK(cudaMemcpyAsync(h->cm_acc.p, cm_acc, cm_bytes, cudaMemcpyHostToDevice, h->stream));
-    // The accumulator's side does not depend on this step's witness: its 15 planes and 14 commits go first, and w_ccs
-    // comes up on the copy engine underneath them (every call ends in finish(), so h->in is free and copy_stream idle).
+    // The accumulator's side does not depend on this step's witness: its 15 planes go first, and w_ccs comes up on the
+    // copy engine underneath them (every call ends in finish(), so h->in is free and copy_stream idle).  The 2 (K-1)
+    // planes that get committed sit back to back in planes_all, so ONE launch commits both sides: 7 groups of 4 planes
+    // share every matrix tile in L2 (one pass over HBM instead of four) and there is no 2-plane tail launch that would
+    // stream the whole 5-word matrix for two planes.
     if ((st = h->in.ensure(w_len * ELEM_BYTES))) return st;
     CK(cudaEventRecord(h->work_done, h->stream));  // whatever the caller still has in flight on the handle's stream goes first
     CK(cudaStreamWaitEvent(h->copy_stream, h->work_done, 0));
@@ -1099,7 +1108,7 @@ int lat_ajtai_fold_step_begin(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_le
     // side 0: the accumulator (acc, w_acc); side 1: the step witness (lin_cm_i, w_i)      zk_latticefold.rs:60-71
     const int side_before = h->cur_side;
     h->cur_side = 0;
-    st = planes_core(h, h->cm_acc.as<u64>(), nullptr, nullptr, h->cms_side[0].as<u64>(), h->f16_acc.as<int16_t>());
+    st = planes_core(h, nullptr, nullptr, nullptr, nullptr, h->f16_acc.as<int16_t>(), true);
     if (!st) {
         // the step witness and its commitment (ZKVM/main.rs:348-367)
         CK(cudaStreamWaitEvent(h->stream, h->copy_done[0], 0));
@@ -1110,10 +1119,24 @@ int lat_ajtai_fold_step_begin(lat_ajtai *h, const uint64_t *w_ccs, uint64_t w_le
         if (f_coeff16)  // on copy_stream, beside the 14 matrix-vector products of side 1 (the digits are not modified by them)
             CK(cudaMemcpyAsync(f_coeff16, h->f16.p, h->n * LAT_RING_DEGREE * sizeof(int16_t), cudaMemcpyDeviceToHost, h->copy_stream));
         h->cur_side = 1;
-        st = planes_core(h, h->cm_step.as<u64>(), nullptr, nullptr, h->cms_side[1].as<u64>(), h->f16.as<int16_t>());
+        st = planes_core(h, nullptr, nullptr, nullptr, nullptr, h->f16.as<int16_t>(), true);
     }
     h->cur_side = side_before;
     if (st) return st;
+    if (h->K > 1) {  // commit_witnesses of both sides (decomposition.rs:185-187), one launch
+        const uint32_t per_side = h->K - 1;
+        if ((st = h->cms.ensure((size_t)2 * per_side * cm_bytes))) return st;
+        if ((st = h->mac_fx(h->planes_k1(0), h->n, 2 * per_side, h->cms.as<u64>(), lat::MacReport(), true))) return st;
+        for (int s = 0; s < 2; ++s)  // behind each side's slot for y_0
+            CK(cudaMemcpyAsync(h->cms_side[s].as<u64>() + (size_t)h->kappa * LAT_RING_DEGREE,
+                               h->cms.as<u64>() + (size_t)s * per_side * h->kappa * LAT_RING_DEGREE, per_side * cm_bytes,
+                               cudaMemcpyDeviceToDevice, h->stream));
+    }
+    // y_0 = cm - sum 2^k y_k for either side (decomposition.rs:189-197)
+    lat::launch_y0(h->cm_acc.as<u64>(), h->cms_side[0].as<u64>(), h->K, h->kappa, h->stream);
+    lat::launch_y0(h->cm_step.as<u64>(), h->cms_side[1].as<u64>(), h->K, h->kappa, h->stream);
+    CK(cudaGetLastError());
+    h->last_op_was_mac = false;
     CK(cudaMemcpyAsync(cms, h->cms_side[0].p, side_bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(cms + (size_t)h->K * h->kappa * LAT_RING_DEGREE, h->cms_side[1].p, side_bytes, cudaMemcpyDeviceToHost,
                        h->stream));
@@ -1136,11 +1159,11 @@ int lat_ajtai_fold_step_finish(lat_ajtai *h, const uint64_t *rho, int16_t *f0_co
     // accumulator (they must stay below 2^K, the protocol's norm bound) -- in four ranges of elements when the caller wants
     // the digits back, so that the 4.7 MB download of a range runs under the fold of the next one
     {
-        const u64 *sides[2] = {h->planes_fx[0].as<u64>(), h->planes_fx[1].as<u64>()};
+        const u64 *sides[2] = {h->planes_k1(0), h->planes_k1(1)}, *sides0[2] = {h->planes_k0(0), h->planes_k0(1)};
         const int nch = (f0_coeff16 && h->n >= 4096) ? 4 : 1;
         for (int c = 0; c < nch; ++c) {
             const u64 e0 = h->n * c / nch, cnt = h->n * (c + 1) / nch - e0;
-            lat::launch_fold(sides, 2, (int)h->K, h->n, h->rho.as<u64>(), h->mont, h->f0.as<u64>(), h->stream, e0, cnt);
+            lat::launch_fold(sides, sides0, 2, (int)h->K, h->n, h->rho.as<u64>(), h->mont, h->f0.as<u64>(), h->stream, e0, cnt);
             lat::launch_icrt(h->f0.as<u64>() + e0 * LAT_RING_DEGREE, h->in.as<u64>() + e0 * LAT_RING_DEGREE, cnt, h->stream);
             lat::launch_pack_coeff(h->in.as<u64>() + e0 * LAT_RING_DEGREE, cnt, h->mont, (int)h->K,
                                    h->f16_acc.as<int16_t>() + e0 * LAT_RING_DEGREE, h->flag.as<int>(), h->stream);

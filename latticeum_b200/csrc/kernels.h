@@ -39,11 +39,13 @@ void launch_witness(const u64 *w, u64 w_len, int log2b, int L, bool mont, bool i
 
 // int16 coefficients -> K base-2 digit planes: plane k of element j = sign * bit_k(|c|).
 //   planes_f     : K x n x 24 CRT form, or nullptr
-//   planes_fx    : K x n x 48 CRT form in the extended layout, Toom-3 form (see FX_WORDS), or nullptr
+//   planes_fx    : CRT form in the extended layout, Toom-3 form (see FX_WORDS), or nullptr: planes 1 .. K-1 as
+//                  (K-1) x n x 48 starting here, plane 0 (never committed: y_0 is derived) as n x 48 at planes_fx0 --
+//                  so that the committed planes of several decompositions can sit back to back for ONE launch
 //   planes_coeff : K x n x 24 coefficient form, or nullptr
 //   lut          : the 3 x 256 x 8 subset-sum table of launch_planes_lut for the same representation
 void launch_planes(const int16_t *f16, u64 n, int K, bool mont, const u64 *lut, u64 *planes_f, u64 *planes_fx,
-                   u64 *planes_coeff, cudaStream_t stream);
+                   u64 *planes_fx0, u64 *planes_coeff, cudaStream_t stream);
 // lut[(c * 256 + pat) * 8 + s] = sum over the bits i of pat of the word of slot s that CRT(X^(3i+c)) is nonzero in
 // (PLANES_LUT_WORDS u64, canonical values in the representation `mont` names); see planes_kernel.
 constexpr int PLANES_LUT_WORDS = 3 * 256 * 8;
@@ -124,12 +126,12 @@ void launch_mac(const u64 *A_dev, const MatLayout &lay, const u64 *Fx, u64 f_str
 // cms[0] = cm - sum_{k=1..K-1} 2^k cms[k]      (LF/nifs/decomposition.rs:189-197)
 void launch_y0(const u64 *cm, u64 *cms, uint32_t K, uint32_t kappa, cudaStream_t stream);
 
-// f0[j] = sum_{i < nplanes} rho[i] (*) planes[i][j]  (slot-wise Fq3), planes given as `nsides` extended-layout
-// buffers of planes_per_side x n x 48 each (Toom-3 form, as planes_kernel writes them).  rho: nplanes x 24 in the
-// caller's representation.  f0: n x 24.
+// f0[j] = sum_{i < nplanes} rho[i] (*) planes[i][j]  (slot-wise Fq3), planes given per side as launch_planes writes them
+// (Toom-3 form): sides_fx[s] = planes 1 .. planes_per_side-1 of side s, (planes_per_side-1) x n x 48; sides_fx0[s] = its
+// plane 0, n x 48.  rho: nplanes x 24 in the caller's representation, side-major.  f0: n x 24.
 // elem0 / count: fold only that range of elements (f0 is still the full n x 24 array; count = ~0 means "to the end").
-void launch_fold(const u64 *const *sides_fx, int nsides, int planes_per_side, u64 n, const u64 *rho, bool mont, u64 *f0,
-                 cudaStream_t stream, u64 elem0 = 0, u64 count = ~0ull);
+void launch_fold(const u64 *const *sides_fx, const u64 *const *sides_fx0, int nsides, int planes_per_side, u64 n, const u64 *rho,
+                 bool mont, u64 *f0, cudaStream_t stream, u64 elem0 = 0, u64 count = ~0ull);
 
 // out[i] = sum_{p < 2K} rho[p] (*) cms[p][i]  over the K commitments of side 0 followed by the K of side 1 (each
 // K x kappa x 24); the folded commitment cm_0 (LF/nifs/folding/utils.rs:466-472).  rho in the caller's representation.

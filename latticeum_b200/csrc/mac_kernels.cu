@@ -594,8 +594,8 @@ constexpr int FOLD_THREADS = 256, FOLD_STAGES = 4;
 constexpr u32 FOLD_STAGE_BYTES = FOLD_THREADS * 6 * 8;  // one plane's 48-byte slots of the block's 256 (element, slot) items
 template <bool MONT>
 __global__ void __launch_bounds__(FOLD_THREADS)
-fold_kernel(const u64 *__restrict__ s0, const u64 *__restrict__ s1, int nsides, int pps, u64 n, u64 plane_stride,
-            const u64 *__restrict__ rho, u64 *__restrict__ f0) {
+fold_kernel(const u64 *__restrict__ s0, const u64 *__restrict__ s1, const u64 *__restrict__ z0, const u64 *__restrict__ z1,
+            int nsides, int pps, u64 n, u64 plane_stride, const u64 *__restrict__ rho, u64 *__restrict__ f0) {
     // The block's items are consecutive (element, slot) pairs, so plane p's share of them is ONE contiguous run of
     // 256 x 48 B: it is streamed with a TMA bulk copy into a ring of stages, FOLD_STAGES planes ahead of the
     // arithmetic (plain loads left the kernel latency-bound at 4.1 TB/s: two 256-thread blocks per SM cannot keep
@@ -608,8 +608,13 @@ fold_kernel(const u64 *__restrict__ s0, const u64 *__restrict__ s1, int nsides, 
     const u64 item0 = (u64)blockIdx.x * FOLD_THREADS;
     const u32 nitems = (u32)min((u64)FOLD_THREADS, total - item0);
     const u32 bytes = nitems * 48;
-    // n elements starting at s0 / s1 / f0 (the caller offsets all three for a sub-range); planes are plane_stride elements apart
-    auto plane_src = [&](int p) { return (p < pps ? s0 + (u64)p * plane_stride * FX : s1 + (u64)(p - pps) * plane_stride * FX) + item0 * 6; };
+    // n elements starting at s* / z* / f0 (the caller offsets them for a sub-range).  Side s: plane 0 at z_s, planes 1 .. pps-1
+    // at s_s, plane_stride elements apart (launch_planes keeps the committed planes of both sides back to back)
+    auto plane_src = [&](int p) {
+        const int side = p >= pps ? 1 : 0, k = p - side * pps;
+        const u64 *base = k == 0 ? (side ? z1 : z0) : (side ? s1 : s0) + (u64)(k - 1) * plane_stride * FX;
+        return base + item0 * 6;
+    };
     if (threadIdx.x == 0) {
         for (int st = 0; st < FOLD_STAGES; ++st) mbar_init(&bars[st], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -662,14 +667,15 @@ fold_kernel(const u64 *__restrict__ s0, const u64 *__restrict__ s1, int nsides, 
     u64 *o = f0 + idx * 3;  // element * 24 + slot * 3
     o[0] = c0; o[1] = c1; o[2] = c2;
 }
-void launch_fold(const u64 *const *sides_fx, int nsides, int planes_per_side, u64 n, const u64 *rho, bool mont, u64 *f0,
-                 cudaStream_t stream, u64 elem0, u64 count) {
+void launch_fold(const u64 *const *sides_fx, const u64 *const *sides_fx0, int nsides, int planes_per_side, u64 n, const u64 *rho,
+                 bool mont, u64 *f0, cudaStream_t stream, u64 elem0, u64 count) {
     const u64 plane_stride = n;
     if (count == ~0ull) count = n - elem0;
     n = count;
     if (!n) return;
     unsigned grid = (unsigned)((n * ring::NSLOT + FOLD_THREADS - 1) / FOLD_THREADS);
     const u64 *a = sides_fx[0] + elem0 * FX, *b = nsides > 1 ? sides_fx[1] + elem0 * FX : nullptr;
+    const u64 *za = sides_fx0[0] + elem0 * FX, *zb = nsides > 1 ? sides_fx0[1] + elem0 * FX : nullptr;
     f0 += elem0 * ring::D;
     const size_t smem = (size_t)FOLD_STAGES * FOLD_STAGE_BYTES;
     static bool attr_set_on[64] = {};  // per device, as for mac_kernel
@@ -681,8 +687,8 @@ void launch_fold(const u64 *const *sides_fx, int nsides, int planes_per_side, u6
         cudaFuncSetAttribute(fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
-    if (mont) fold_kernel<true><<<grid, FOLD_THREADS, smem, stream>>>(a, b, nsides, planes_per_side, n, plane_stride, rho, f0);
-    else fold_kernel<false><<<grid, FOLD_THREADS, smem, stream>>>(a, b, nsides, planes_per_side, n, plane_stride, rho, f0);
+    if (mont) fold_kernel<true><<<grid, FOLD_THREADS, smem, stream>>>(a, b, za, zb, nsides, planes_per_side, n, plane_stride, rho, f0);
+    else fold_kernel<false><<<grid, FOLD_THREADS, smem, stream>>>(a, b, za, zb, nsides, planes_per_side, n, plane_stride, rho, f0);
 }
 
 // ---- cm_0 = sum_i rho_i (*) cm_i over the 2K commitments of a fold step (LF/nifs/folding/utils.rs:466-472) -----------------

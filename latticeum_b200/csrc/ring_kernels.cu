@@ -430,7 +430,7 @@ void launch_planes_lut(bool mont, u64 *lut, cudaStream_t stream) {
 template <bool MONT>
 __global__ void __launch_bounds__(PLANE_THREADS)
 planes_kernel(const int16_t *__restrict__ f16, u64 n, int K, const u64 *__restrict__ lut, u64 *__restrict__ planes_f,
-              u64 *__restrict__ planes_fx, u64 *__restrict__ planes_coeff) {
+              u64 *__restrict__ planes_fx, u64 *__restrict__ planes_fx0, u64 *__restrict__ planes_coeff) {
     asm volatile("griddepcontrol.launch_dependents;");  // the MAC behind it may start its prologue (see mac_kernel)
     // dynamic shared memory: the table, then (only when a plain output is wanted) the staging tile of the plain rows
     extern __shared__ __align__(16) unsigned char planes_smem[];
@@ -491,7 +491,8 @@ planes_kernel(const int16_t *__restrict__ f16, u64 n, int K, const u64 *__restri
                 if (active) row_put(otile, threadIdx.x, c);
                 rows_out<PLAIN_UNITS>(otile, planes_f + elem0 * ring::D, nrows);
             }
-            if (planes_fx && active) store_fx_row<true>(planes_fx + ((u64)k * n + e) * FX_WORDS, c);
+            if (planes_fx && active)
+                store_fx_row<true>((k == 0 ? planes_fx0 : planes_fx + (u64)(k - 1) * n * FX_WORDS) + e * FX_WORDS, c);
         }
     }
 }
@@ -506,7 +507,8 @@ constexpr int PLANE_FX_ELEMS = PLANE_FX_THREADS / 4;
 #define LAT_PLANES_FX_BLOCKS 3  // 71 registers; 4 blocks per SM (63 registers) measured 138.5 us against 133.8 for pack + planes
 #endif
 __global__ void __launch_bounds__(PLANE_FX_THREADS, LAT_PLANES_FX_BLOCKS)
-planes_fx_kernel(const int16_t *__restrict__ f16, u64 n, int K, const u64 *__restrict__ lut, u64 *__restrict__ planes_fx) {
+planes_fx_kernel(const int16_t *__restrict__ f16, u64 n, int K, const u64 *__restrict__ lut, u64 *__restrict__ planes_fx,
+                 u64 *__restrict__ planes_fx0) {
     asm volatile("griddepcontrol.launch_dependents;");
     extern __shared__ __align__(16) unsigned char planes_smem[];
     ulonglong2 *s_lut = reinterpret_cast<ulonglong2 *>(planes_smem);
@@ -558,7 +560,7 @@ planes_fx_kernel(const int16_t *__restrict__ f16, u64 n, int K, const u64 *__res
             u64 p0, p1, p2, q0, q1, q2;
             gl::toom_eval(a[0], a[1], a[2], p0, p1, p2);
             gl::toom_eval(b[0], b[1], b[2], q0, q1, q2);
-            u64 *o = planes_fx + ((u64)k * n + e) * FX_WORDS + h * 12;
+            u64 *o = (k == 0 ? planes_fx0 : planes_fx + (u64)(k - 1) * n * FX_WORDS) + e * FX_WORDS + h * 12;
             st256(o, a[0], a[1], a[2], p0);
             st256(o + 4, p1, p2, b[0], b[1]);
             st256(o + 8, b[2], q0, q1, q2);
@@ -567,7 +569,7 @@ planes_fx_kernel(const int16_t *__restrict__ f16, u64 n, int K, const u64 *__res
 }
 
 void launch_planes(const int16_t *f16, u64 n, int K, bool mont, const u64 *lut, u64 *planes_f, u64 *planes_fx,
-                   u64 *planes_coeff, cudaStream_t stream) {
+                   u64 *planes_fx0, u64 *planes_coeff, cudaStream_t stream) {
     if (!n) return;
     if (!planes_f && !planes_coeff) {
         if (!planes_fx) return;
@@ -582,7 +584,7 @@ void launch_planes(const int16_t *f16, u64 n, int K, bool mont, const u64 *lut, 
         }
         const u64 items = ((n + PLANE_FX_ELEMS - 1) / PLANE_FX_ELEMS) * 3;
         const unsigned grid = (unsigned)min(items, (u64)sms * LAT_PLANES_FX_BLOCKS);
-        planes_fx_kernel<<<grid, PLANE_FX_THREADS, LUT_WORDS * 8, stream>>>(f16, n, K, lut, planes_fx);
+        planes_fx_kernel<<<grid, PLANE_FX_THREADS, LUT_WORDS * 8, stream>>>(f16, n, K, lut, planes_fx, planes_fx0);
         return;
     }
     unsigned grid = (unsigned)((n + PLANE_THREADS - 1) / PLANE_THREADS);
@@ -598,8 +600,8 @@ void launch_planes(const int16_t *f16, u64 n, int K, bool mont, const u64 *lut, 
         cudaFuncSetAttribute(planes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         attr_set = true;
     }
-    if (mont) planes_kernel<true><<<grid, PLANE_THREADS, smem, stream>>>(f16, n, K, lut, planes_f, planes_fx, planes_coeff);
-    else planes_kernel<false><<<grid, PLANE_THREADS, smem, stream>>>(f16, n, K, lut, planes_f, planes_fx, planes_coeff);
+    if (mont) planes_kernel<true><<<grid, PLANE_THREADS, smem, stream>>>(f16, n, K, lut, planes_f, planes_fx, planes_fx0, planes_coeff);
+    else planes_kernel<false><<<grid, PLANE_THREADS, smem, stream>>>(f16, n, K, lut, planes_f, planes_fx, planes_fx0, planes_coeff);
 }
 
 // ---- Witness::get_fhat (latticefold/src/arith.rs:273-297) from the resident digits ---------------------------------------------
