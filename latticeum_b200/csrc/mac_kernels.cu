@@ -692,33 +692,44 @@ void launch_fold(const u64 *const *sides_fx, const u64 *const *sides_fx0, int ns
 }
 
 // ---- cm_0 = sum_i rho_i (*) cm_i over the 2K commitments of a fold step (LF/nifs/folding/utils.rs:466-472) -----------------
-// One thread per (row, slot) of the kappa x 8 outputs; 2K lazily accumulated Fq3 products, one reduction.
+// One WARP per (row, slot) of the kappa x 8 outputs, one lane per commitment: each lane's Fq3 product is independent (one
+// round of loads instead of 2K dependent ones -- this kernel sits alone on the critical path of lat_ajtai_fold_step_finish),
+// then a shuffle tree of modular additions.  Exact arithmetic mod q: the order of the sum does not matter.
 template <bool MONT>
 __global__ void __launch_bounds__(256)
 lincomb_kernel(const u64 *__restrict__ rho, const u64 *__restrict__ cms0, const u64 *__restrict__ cms1, int K, uint32_t kappa,
                u64 *__restrict__ out) {
-    const u32 idx = blockIdx.x * 256 + threadIdx.x;  // row * 8 + slot
-    if (idx >= kappa * ring::NSLOT) return;
+    const u32 lane = threadIdx.x & 31;
+    const u32 idx = blockIdx.x * 8 + (threadIdx.x >> 5);  // row * 8 + slot
+    if (idx >= kappa * ring::NSLOT) return;               // the whole warp leaves together
     const u32 sl = idx & 7;
-    gl::Fq3Acc acc;
-    acc.clear();
-    for (int p = 0; p < 2 * K; ++p) {
+    u64 acc[3] = {0, 0, 0};
+    for (int p = lane; p < 2 * K; p += 32) {
         const u64 *c = (p < K ? cms0 + (u64)p * kappa * ring::D : cms1 + (u64)(p - K) * kappa * ring::D) + (u64)idx * 3;
         const u64 *r = rho + p * ring::D + 3 * sl;
-        u64 r0 = r[0], r1 = r[1], r2 = r[2];
-        if constexpr (MONT) { r0 = gl::from_mont(r0); r1 = gl::from_mont(r1); r2 = gl::from_mont(r2); }  // canonical(rho) * repr(cm)
-        else { r0 = gl::reduce128(r0, 0); r1 = gl::reduce128(r1, 0); r2 = gl::reduce128(r2, 0); }
-        const u64 y0 = gl::reduce128(c[0], 0), y1 = gl::reduce128(c[1], 0), y2 = gl::reduce128(c[2], 0);
-        acc.mac(r0, r1, r2, y0, y1, y2, gl::add_lazy(y0, y1), gl::add_lazy(y0, y2), gl::add_lazy(y1, y2));
+        u64 a[3], y[3], t[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            a[k] = MONT ? gl::from_mont(r[k]) : gl::reduce128(r[k], 0);  // canonical(rho) * repr(cm) = repr(rho * cm)
+            y[k] = gl::reduce128(c[k], 0);
+        }
+        gl::fq3_mul(a, y, t);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc[k] = gl::add(acc[k], t[k]);
     }
-    u64 c0, c1, c2;
-    acc.finish(c0, c1, c2);
-    u64 *o = out + (u64)idx * 3;
-    o[0] = c0; o[1] = c1; o[2] = c2;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc[k] = gl::add(acc[k], __shfl_down_sync(0xFFFFFFFFu, acc[k], off));
+    }
+    if (lane == 0) {
+        u64 *o = out + (u64)idx * 3;
+        o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2];
+    }
 }
 void launch_lincomb(const u64 *rho, const u64 *cms0, const u64 *cms1, int K, uint32_t kappa, bool mont, u64 *out,
                     cudaStream_t stream) {
-    const unsigned grid = (kappa * ring::NSLOT + 255) / 256;
+    const unsigned grid = (kappa * ring::NSLOT + 7) / 8;
     if (mont) lincomb_kernel<true><<<grid, 256, 0, stream>>>(rho, cms0, cms1, K, kappa, out);
     else lincomb_kernel<false><<<grid, 256, 0, stream>>>(rho, cms0, cms1, K, kappa, out);
 }
