@@ -505,7 +505,9 @@ constexpr int PLANE_FX_THREADS = 256;
 constexpr int PLANE_FX_ELEMS = PLANE_FX_THREADS / 4;
 #ifndef LAT_PLANES_FX_BLOCKS
 #define LAT_PLANES_FX_BLOCKS 3  // 71 registers; 4 blocks per SM (63 registers) measured 138.5 us against 133.8 for pack + planes;
-                                // requesting the next item's digits one item ahead changed nothing (133.8): the store path is the limit
+                                // requesting the next item's digits one item ahead changed nothing (133.8): the store path is the limit;
+                                // staging an item's 64 rows in shared memory and writing them with one 24 KB bulk store
+                                // (cp.async.bulk.global.shared::cta, single-buffered) was slower: 169.6 us
 #endif
 __global__ void __launch_bounds__(PLANE_FX_THREADS, LAT_PLANES_FX_BLOCKS)
 planes_fx_kernel(const int16_t *__restrict__ f16, u64 n, int K, const u64 *__restrict__ lut, u64 *__restrict__ planes_fx,
